@@ -1,0 +1,123 @@
+/* vdetr_b200.h -- C ABI of libvdetr_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the V-DETR Vertex-RPE decoder hot path.  The reference has no C-ABI plugin; its
+ * boundary is (1) the pybind11 module `pointnet2._ext`
+ * (third_party/pointnet2/_ext_src/src/bindings.cpp:9-21) and (2) the nn.Module classes of
+ * models/vdetr_transformer.py.  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions:
+ *   - plain C types only; all pointers are DEVICE pointers unless named h_*; tensors are dense,
+ *     row-major, in the layout written next to each argument;
+ *   - the caller allocates every output and workspace; the library owns nothing across calls;
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; functions are re-entrant across streams;
+ *   - return value: 0 = ok, VDETR_ERR_* (>0x1000) = bad argument, otherwise a cudaError_t value.
+ *     The library never calls exit() (the reference does: include/cuda_utils.h:32-41).
+ */
+#ifndef VDETR_B200_H
+#define VDETR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDETR_OK 0
+#define VDETR_ERR_BAD_ARG 0x1001
+#define VDETR_ERR_UNSUPPORTED 0x1002
+#define VDETR_ERR_WORKSPACE 0x1003
+#define VDETR_ERR_NO_DRIVER 0x1004
+
+/* Library / build identification: returns e.g. "vdetr_b200 0.1 sm_100a". */
+const char* vdetr_version(void);
+/* Human readable text for a non-zero return code of this library. */
+const char* vdetr_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * pointnet2 seed ops  (replace third_party/pointnet2/_ext_src)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* furthest_point_sampling(points[B,N,3] f32, nsamples) -> int32[B,M]
+ * Replaces: src/sampling.cpp:67-88 + src/sampling_gpu.cu:72-232 (bindings.cpp:12).
+ * Bit-exact indices incl. the reference's tie-break and its |p|^2 <= 1e-3 skip rule.
+ * workspace: vdetr_pn2_fps_workspace_bytes(B,N,M) bytes (may be 0); idx is fully overwritten. */
+size_t vdetr_pn2_fps_workspace_bytes(int B, int N, int M);
+int vdetr_pn2_fps(const float* xyz /*[B,N,3]*/, int B, int N, int M, int32_t* idx /*[B,M]*/,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* gather_points(points[B,C,N], idx[B,M]) -> out[B,C,M]        (src/sampling.cpp:17-40, sampling_gpu.cu:11-33) */
+int vdetr_pn2_gather(const float* points, const int32_t* idx, int B, int C, int N, int M, float* out,
+                     void* stream);
+/* gather_points_grad(grad_out[B,C,M], idx[B,M], N) -> grad_points[B,C,N]  (src/sampling.cpp:42-66,
+ * sampling_gpu.cu:37-60).  grad_points must be zero-filled by the caller (the reference does torch::zeros). */
+int vdetr_pn2_gather_grad(const float* grad_out, const int32_t* idx, int B, int C, int N, int M,
+                          float* grad_points, void* stream);
+
+/* ball_query(new_xyz[B,M,3], xyz[B,N,3], radius, nsample) -> int32 idx[B,M,nsample]
+ * Replaces: src/ball_query.cpp:11-35 + src/ball_query_gpu.cu:12-57.  idx is fully written (rows with no
+ * neighbour are zero, like the reference's torch::zeros). Bit-exact. */
+int vdetr_pn2_ball_query(const float* new_xyz, const float* xyz, int B, int N, int M, float radius,
+                         int nsample, int32_t* idx, void* stream);
+
+/* group_points(points[B,C,N], idx[B,M,S]) -> out[B,C,M,S]    (src/group_points.cpp:15-38, group_points_gpu.cu:11-42) */
+int vdetr_pn2_group(const float* points, const int32_t* idx, int B, int C, int N, int M, int S, float* out,
+                    void* stream);
+/* group_points_grad(grad_out[B,C,M,S], idx[B,M,S], N) -> grad_points[B,C,N] (zero-filled by caller)
+ * (src/group_points.cpp:40-63, group_points_gpu.cu:46-78) */
+int vdetr_pn2_group_grad(const float* grad_out, const int32_t* idx, int B, int C, int N, int M, int S,
+                         float* grad_points, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vertex-RPE cross-attention core  (replaces the body of GlobalShareCrossAttention.forward,
+ * models/vdetr_transformer.py:708-753, between the q/k/v Linear layers and `proj`)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct VdetrXattnShape {
+  int B;        /* scenes */
+  int nQ;       /* queries per scene */
+  int nK;       /* key tokens per scene */
+  int H;        /* query heads (must be 4) */
+  int hd;       /* head dim (must be 64) */
+  int grid_n;   /* table points per axis (10 for rpe_quant=bilinear_4_10) */
+  float log_scale;  /* args.log_scale (512) */
+  float max_value;  /* 4 for bilinear_4_10 */
+  int rotate;   /* 1: angle_type=="object_coords": deltas are rotated by ref_angle per query */
+  int kv_heads; /* 1 = shared K/V head (MQA, cross attention and ShareSelfAttention); H = per-head K/V (MHA) */
+  int has_bias; /* 1 = add the Vertex-RPE bias; 0 = plain attention (decoder self-attention) */
+} VdetrXattnShape;
+
+/* Forward:  O = softmax_k(Q K^T + rpe(ref_pts, xyz, tables)) V        (fp32 in / fp32 out interface)
+ *   q       [B,nQ,H,hd] f32, ALREADY multiplied by hd^-0.5            (vdetr_transformer.py:736-738)
+ *   k, v    [B,nK,kv_heads,hd] f32                                    (:734-735)
+ *   xyz     [B,nK,3] f32 ; ref_pts [B,nQ,8,3] f32 ; ref_angle [B,nQ] f32 or NULL   (:708-720)
+ *   tables  [8,grid_n,grid_n,grid_n,H] f32 = cpb_mlps[i](relative_coords_table), a=z,b=y,c=x (:725)
+ *   out     [B,nQ,H,hd] f32  (heads concatenated h-major = the input of `proj`, :755)
+ *   lse     [B,H,nQ] f32 natural-log-sum-exp of the logits (saved for backward)
+ * impl: 0 = tcgen05/TMA fused kernel (product path), 1 = SIMT validation kernel.
+ * workspace: vdetr_xattn_fwd_workspace_bytes(&shape, impl). */
+size_t vdetr_xattn_fwd_workspace_bytes(const VdetrXattnShape* s, int impl);
+int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v,
+                    const float* xyz, const float* ref_pts, const float* ref_angle, const float* tables,
+                    float* out, float* lse, void* workspace, size_t workspace_bytes, int impl,
+                    void* stream);
+
+/* Backward of the same op (dropout disabled):
+ *   in : q,k,v,xyz,ref_pts,ref_angle,tables as forward; out, lse from forward; dout [B,nQ,H,hd]
+ *   out: dq [B,nQ,H,hd], dk, dv [B,nK,kv_heads,hd], dtables [8,n,n,n,H]  -- all fully overwritten.
+ *   No gradient is produced for xyz / ref_pts (detached in the reference, vdetr_transformer.py:369-412). */
+size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl);
+int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v,
+                    const float* xyz, const float* ref_pts, const float* ref_angle, const float* tables,
+                    const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv,
+                    float* dtables, void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* Bias only (debug / return_attn_weights path): rpe [B,H,nQ,nK] f32  (vdetr_transformer.py:708-731). */
+int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
+                   const float* tables, float* rpe, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDETR_B200_H */

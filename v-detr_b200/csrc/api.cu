@@ -1,0 +1,70 @@
+// C ABI dispatch for libvdetr_b200 (see include/vdetr_b200.h).
+#include "common.cuh"
+#include "rpe_internal.h"
+
+extern "C" {
+
+const char* vdetr_version(void) { return "vdetr_b200 0.1 sm_100a"; }
+
+const char* vdetr_error_string(int code) {
+  switch (code) {
+    case VDETR_OK: return "ok";
+    case VDETR_ERR_BAD_ARG: return "vdetr_b200: bad argument";
+    case VDETR_ERR_UNSUPPORTED: return "vdetr_b200: unsupported shape or option";
+    case VDETR_ERR_WORKSPACE: return "vdetr_b200: workspace missing or too small";
+    case VDETR_ERR_NO_DRIVER: return "vdetr_b200: CUDA driver entry point unavailable";
+    default: return cudaGetErrorString((cudaError_t)code);
+  }
+}
+
+size_t vdetr_xattn_fwd_workspace_bytes(const VdetrXattnShape* s, int impl) {
+  if (vdetr_check_shape(s) != 0) return 0;
+  return impl == 0 ? tc_xattn_fwd_workspace(s) : 0;
+}
+
+int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
+                    const float* ref_pts, const float* ref_angle, const float* tables, float* out, float* lse,
+                    void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  int rc = vdetr_check_shape(s);
+  if (rc) return rc;
+  if (s->B == 0 || s->nQ == 0) return 0;
+  if (s->nK == 0) return VDETR_ERR_BAD_ARG;
+  if (!q || !k || !v || !out || !lse) return VDETR_ERR_BAD_ARG;
+  if (s->has_bias && (!xyz || !ref_pts || !tables)) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 1) return simt_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, st);
+  if (impl == 0) return tc_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, workspace, workspace_bytes, st);
+  return VDETR_ERR_BAD_ARG;
+}
+
+size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl) {
+  if (vdetr_check_shape(s) != 0) return 0;
+  return impl == 0 ? tc_xattn_bwd_workspace(s) : 0;
+}
+
+int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
+                    const float* ref_pts, const float* ref_angle, const float* tables, const float* out,
+                    const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dtables,
+                    void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  int rc = vdetr_check_shape(s);
+  if (rc) return rc;
+  if (s->B == 0 || s->nQ == 0 || s->nK == 0) return (s->nK == 0 && s->B && s->nQ) ? VDETR_ERR_BAD_ARG : 0;
+  if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return VDETR_ERR_BAD_ARG;
+  if (s->has_bias && (!xyz || !ref_pts || !tables || !dtables)) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 1) return simt_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, dq, dk, dv, dtables, st);
+  if (impl == 0)
+    return tc_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, dq, dk, dv, dtables, workspace,
+                        workspace_bytes, st);
+  return VDETR_ERR_BAD_ARG;
+}
+
+int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
+                   const float* tables, float* rpe, void* stream) {
+  int rc = vdetr_check_shape(s);
+  if (rc) return rc;
+  if (!s->has_bias || !xyz || !ref_pts || !tables || !rpe) return VDETR_ERR_BAD_ARG;
+  return rpe_bias_launch(s, xyz, ref_pts, ref_angle, tables, rpe, (cudaStream_t)stream);
+}
+
+}  // extern "C"

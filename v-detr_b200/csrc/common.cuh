@@ -1,0 +1,30 @@
+// Shared helpers for libvdetr_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/vdetr_b200.h"
+
+#define VDETR_CUDA_TRY(expr)                          \
+  do {                                                \
+    cudaError_t _e = (expr);                          \
+    if (_e != cudaSuccess) return (int)_e;            \
+  } while (0)
+
+#define VDETR_LAUNCH_CHECK()                          \
+  do {                                                \
+    cudaError_t _e = cudaGetLastError();              \
+    if (_e != cudaSuccess) return (int)_e;            \
+  } while (0)
+
+static inline size_t vdetr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static inline int vdetr_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}

@@ -1,0 +1,100 @@
+"""Autograd wrappers around the attention kernels of libvdetr_b200.
+
+``rpe_attention`` is the fused core of GlobalShareCrossAttention.forward
+(/root/reference/models/vdetr_transformer.py:708-753): Vertex-RPE bias + QK^T + softmax + PV, forward and
+backward, without materialising the [B,H,nQ,nK] bias / attention tensors.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _C
+
+IMPL_TCGEN05 = 0     # product kernels (tcgen05 + TMA)
+IMPL_SIMT = 1        # validation kernels
+
+
+def default_impl() -> int:
+    return int(os.environ.get("VDETR_B200_IMPL", IMPL_TCGEN05))
+
+
+def _shape(q, k, tables, log_scale, max_value, rotate, has_bias):
+    B, nQ, H, hd = q.shape
+    nK, kvh = k.shape[1], k.shape[2]
+    n = tables.shape[1] if has_bias else 0
+    return _C.XattnShape(B, nQ, nK, H, hd, n, float(log_scale), float(max_value), int(rotate), kvh, int(has_bias))
+
+
+class _RpeAttention(Function):
+    @staticmethod
+    def forward(ctx, q, k, v, xyz, ref_pts, ref_angle, tables, log_scale, max_value, impl):
+        has_bias = tables is not None
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            _C.require_cuda(name, t, torch.float32)
+        if has_bias:
+            for name, t in (("xyz", xyz), ("ref_pts", ref_pts), ("tables", tables)):
+                _C.require_cuda(name, t, torch.float32)
+            if ref_angle is not None:
+                _C.require_cuda("ref_angle", ref_angle, torch.float32)
+        s = _shape(q, k, tables, log_scale, max_value, ref_angle is not None, has_bias)
+        out = torch.empty_like(q)
+        lse = torch.empty(s.B, s.H, s.nQ, dtype=torch.float32, device=q.device)
+        L = _C.lib()
+        with torch.cuda.device(q.device):
+            nbytes = L.vdetr_xattn_fwd_workspace_bytes(s, impl)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device) if nbytes else None
+            _C.check(L.vdetr_xattn_fwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
+                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
+        ctx.save_for_backward(q, k, v, xyz, ref_pts, ref_angle, tables, out, lse)
+        ctx.meta = (log_scale, max_value, impl, has_bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, xyz, ref_pts, ref_angle, tables, out, lse = ctx.saved_tensors
+        log_scale, max_value, impl, has_bias = ctx.meta
+        dout = dout.contiguous()
+        s = _shape(q, k, tables, log_scale, max_value, ref_angle is not None, has_bias)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dtab = torch.empty_like(tables) if has_bias else None
+        L = _C.lib()
+        with torch.cuda.device(q.device):
+            nbytes = L.vdetr_xattn_bwd_workspace_bytes(s, impl)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device) if nbytes else None
+            _C.check(L.vdetr_xattn_bwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
+                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(dout), _C.ptr(dq), _C.ptr(dk),
+                                       _C.ptr(dv), _C.ptr(dtab), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
+        return dq, dk, dv, None, None, None, dtab, None, None, None
+
+
+def rpe_attention(q, k, v, xyz=None, ref_pts=None, ref_angle=None, tables=None, log_scale=512.0, max_value=4.0,
+                  impl=None):
+    """softmax_k(q k^T + rpe(ref_pts, xyz, tables)) v.
+
+    q [B,nQ,H,hd] (pre-scaled by hd^-0.5), k/v [B,nK,kvh,hd] (kvh = 1: shared K/V head, kvh = H: per head),
+    xyz [B,nK,3], ref_pts [B,nQ,8,3], ref_angle [B,nQ] or None, tables [8,n,n,n,H] or None (no bias).
+    Returns [B,nQ,H,hd].  Gradients: q, k, v, tables (xyz / ref_pts are detached in the reference).
+    """
+    impl = default_impl() if impl is None else impl
+    return _RpeAttention.apply(q.contiguous(), k.contiguous(), v.contiguous(),
+                               None if xyz is None else xyz.contiguous(),
+                               None if ref_pts is None else ref_pts.contiguous(),
+                               None if ref_angle is None else ref_angle.contiguous(),
+                               None if tables is None else tables.contiguous(), log_scale, max_value, impl)
+
+
+def rpe_bias(xyz, ref_pts, tables, ref_angle=None, log_scale=512.0, max_value=4.0):
+    """Materialise rpe [B,H,nQ,nK] (debug / return_attn_weights path; vdetr_transformer.py:708-731)."""
+    for name, t in (("xyz", xyz), ("ref_pts", ref_pts), ("tables", tables)):
+        _C.require_cuda(name, t, torch.float32)
+    B, nK = xyz.shape[:2]
+    nQ = ref_pts.shape[1]
+    s = _C.XattnShape(B, nQ, nK, 4, 64, tables.shape[1], float(log_scale), float(max_value), int(ref_angle is not None), 1, 1)
+    out = torch.empty(B, 4, nQ, nK, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _C.check(_C.lib().vdetr_rpe_bias(s, _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle), _C.ptr(tables), _C.ptr(out),
+                                         _C.stream_ptr()))
+    return out
