@@ -1,6 +1,7 @@
 // Internal (non-ABI) entry points shared between the translation units of libvdetr_b200.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include "../../include/vdetr_b200.h"
 
 int vdetr_check_shape(const VdetrXattnShape* s);
@@ -24,3 +25,19 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
                  const float* ref, const float* ang, const float* tables, const float* out, const float* lse,
                  const float* dout, float* dq, float* dk, float* dv, float* dtables, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+
+// Operand packing shared by the product forward / backward kernels (rpe_xattn_fwd.cu):
+//   qp   bf16 [rows][64]   MQA rows = (b*nQp + q)*4 + h        MHA rows = (b*4 + h)*nQp + q     (zero padded)
+//   dop  bf16, same layout as qp (backward only)
+//   kp   bf16 [B][kvh][nKp][64]           vp bf16 same layout (backward only)
+//   vtp  bf16 [B][kvh][64][nKp]   (V transposed: keys contiguous)
+//   xyz4 f32  [B][nKp] float4
+//   geo  f32  [B][nQp][9] float4: (x+,y+,z+,fast flag) (x-,y-,z-,0) 24 vertex floats (cos,sin,0,0)
+struct VdetrPack {
+  int B, nQ, nK, nQp, nKp, kvh, has_bias;
+  const float *q, *k, *v, *xyz, *ref, *ang, *dout;
+  __nv_bfloat16 *qp, *kp, *vtp, *vp, *dop;
+  float4* xyz4;
+  float4* geo;
+};
+__global__ void vdetr_pack_kernel(VdetrPack K);

@@ -1,5 +1,653 @@
-#include "common.cuh"
+// Fused Vertex-RPE attention forward for sm_100a (impl = 0, the product path).
+//
+//   O = softmax_k( Q K^T + rpe(ref_pts, xyz, tables) ) V          /root/reference/models/vdetr_transformer.py:708-753
+//
+// One persistent CTA per SM.  A work item is (scene, 128-row query tile, key split):
+//   * MQA (cross attention, ShareSelfAttention): the 4 query heads share K/V, so the 128 MMA rows are
+//     32 queries x 4 heads and ONE geometry evaluation per (query, key) pair feeds all four heads (float4 cell);
+//   * MHA (decoder self attention): 128 queries of one head, no bias.
+// Per 64-key tile:
+//   TMA      K tile [64 x 64] bf16 (128B swizzle), V^T tile [64 d x 64 keys], key xyz (1-D bulk copy)
+//   tcgen05  S = Q K^T  -> TMEM (double buffered), issued one tile ahead by the control warp
+//   CUDA     all 16 compute warps: Vertex-RPE bias of the 32 x 64 (query,key) pairs (lanes = 32 consecutive
+//            keys, so table reads broadcast), staged through shared memory;
+//            then every thread owns (row, 16 key columns): tcgen05.ld S, + bias, online softmax (row max via a
+//            4-way smem exchange), P -> shared memory in the UMMA K-major swizzled layout
+//   tcgen05  O += P V   (accumulator stays in TMEM for the whole item; rescaled in place when the max moves)
+// Nothing of size nQ x nK ever reaches global memory.
 #include "rpe_internal.h"
-size_t tc_xattn_fwd_workspace(const VdetrXattnShape*) { return 0; }
-int tc_xattn_fwd(const VdetrXattnShape*, const float*, const float*, const float*, const float*, const float*, const float*,
-                 const float*, float*, float*, void*, size_t, cudaStream_t) { return VDETR_ERR_UNSUPPORTED; }
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int NCOMPUTE_WARPS = 16;
+constexpr int NCOMPUTE = NCOMPUTE_WARPS * 32;     // 512
+constexpr int NTHREADS = NCOMPUTE + 32;           // + control warp
+constexpr int BM = 128;                           // MMA rows per item
+constexpr int BN = 64;                            // keys per tile
+constexpr int HD = 64;
+constexpr int QT = 32;                            // queries per MQA tile
+constexpr int GEO_F4 = 9;                         // float4 per query geometry record
+constexpr int BIAS_STRIDE_F4 = BN + 1;            // padded row (per query) of the bias staging buffer
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int TMEM_COLS = 256;                    // S0 [0,64) S1 [64,128) O [128,192)
+constexpr float MAGIC = 12582912.0f;              // 1.5 * 2^23
+constexpr int MAGIC_BITS = 0x4B400000;
+
+struct FwdParams {
+  int B, nQ, nK, nQp, nKp, kvh;
+  int mtiles;             // per scene
+  int splits, tiles_per_split;
+  int items;              // B * mtiles * splits
+  int grid_n;
+  float log_scale, c1, c0;      // p = copysign(lg2(|d|*ls+1) * c1, d) + c0
+  const float4* xyz4;           // [B][nKp]
+  const float4* geo;            // [B][nQp][GEO_F4]
+  const float4* tables;         // [8][n^3]
+  float* out;                   // [B,nQ,4,64]
+  float* lse;                   // [B,4,nQ]
+  float* part_o;                // [items][128][64]   (splits > 1)
+  float2* part_ml;              // [items][128] (m in log2 units, l)
+};
+
+struct SmemLayout {
+  uint32_t tables, q, k, vt, p, bias, xyz, geo, smax, bars, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.q = o;      o += BM * 128;                       // 16 KB  (1024-aligned: o == 0)
+  L.k = o;      o += BN * 128;                       //  8 KB
+  L.vt = o;     o += HD * 128;                       //  8 KB
+  L.p = o;      o += BM * 128;                       // 16 KB
+  L.tables = o; o += (uint32_t)((table_bytes + 1023) / 1024 * 1024);
+  L.bias = o;   o += QT * BIAS_STRIDE_F4 * 16;       // 33,280 B
+  L.xyz = o;    o += 2 * BN * 16;
+  L.geo = o;    o += QT * GEO_F4 * 16;
+  L.smax = o;   o += BM * 4 * 4;
+  L.bars = o;   o += 128;
+  L.total = o;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------ bias maths
+struct Axis {
+  float w0, w1;
+  int o0, o1;       // byte offsets of the two cells along this axis
+};
+template <int STRIDE_SHIFT_UNUSED = 0>
+__device__ __forceinline__ Axis rpe_axis_fast(float d, float ls, float c1, float c0, int n, int stride_bytes) {
+  Axis a;
+  float t = lg2_approx(fmaf(fabsf(d), ls, 1.0f)) * c1;
+  float ts = copysignf(t, d);
+  ts = fminf(fmaxf(ts, -c0 - 1.5f), (float)n - c0 + 0.5f);     // p in [-1.5, n+0.5]: outside both corners are padding
+  float p = ts + c0;
+  float r = (p - 0.5f) + MAGIC;                                 // round-to-nearest(p - 0.5) == floor(p) (ties are harmless)
+  float fl = r - MAGIC;
+  float f = p - fl;
+  int n0 = __float_as_int(r) - MAGIC_BITS;
+  a.w0 = ((unsigned)n0 < (unsigned)n) ? 1.0f - f : 0.0f;
+  a.w1 = ((unsigned)(n0 + 1) < (unsigned)n) ? f : 0.0f;
+  a.o0 = min(max(n0, 0), n - 1) * stride_bytes;
+  a.o1 = min(max(n0 + 1, 0), n - 1) * stride_bytes;
+  return a;
+}
+
+__device__ __forceinline__ void corner8(float4& acc, const char* tab, const Axis& ax, const Axis& ay, const Axis& az) {
+#pragma unroll
+  for (int cz = 0; cz < 2; ++cz) {
+    const int oz = cz ? az.o1 : az.o0;
+    const float wz = cz ? az.w1 : az.w0;
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy) {
+      const int ozy = oz + (cy ? ay.o1 : ay.o0);
+      const float wzy = wz * (cy ? ay.w1 : ay.w0);
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx) {
+        const float w = wzy * (cx ? ax.w1 : ax.w0);
+        const float4 t = *reinterpret_cast<const float4*>(tab + ozy + (cx ? ax.o1 : ax.o0));
+        acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y);
+        acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
+      }
+    }
+  }
+}
+
+// Bias of one (query,key) pair for the 4 heads.  geo: the query's record in shared memory (see pack kernel).
+__device__ __forceinline__ float4 rpe_bias_pair(const float4* __restrict__ geo, float kx, float ky, float kz,
+                                                const char* __restrict__ tab, int n, float ls, float c1, float c0) {
+  const int sx = 16, sy = 16 * n, sz = 16 * n * n, st = 16 * n * n * n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 hi = geo[0];
+  if (__float_as_int(hi.w) != 0) {
+    // axis-aligned box: 2 distinct coordinates per axis -> 6 transforms instead of 24
+    const float4 lo = geo[1];
+    const Axis xp = rpe_axis_fast(hi.x - kx, ls, c1, c0, n, sx), xm = rpe_axis_fast(lo.x - kx, ls, c1, c0, n, sx);
+    const Axis yp = rpe_axis_fast(hi.y - ky, ls, c1, c0, n, sy), ym = rpe_axis_fast(lo.y - ky, ls, c1, c0, n, sy);
+    const Axis zp = rpe_axis_fast(hi.z - kz, ls, c1, c0, n, sz), zm = rpe_axis_fast(lo.z - kz, ls, c1, c0, n, sz);
+    // vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4:(+,+,+) 5:(+,-,+) 6:(-,-,+) 7:(-,+,+)
+    corner8(acc, tab + 0 * st, xp, yp, zm);
+    corner8(acc, tab + 1 * st, xp, ym, zm);
+    corner8(acc, tab + 2 * st, xm, ym, zm);
+    corner8(acc, tab + 3 * st, xm, yp, zm);
+    corner8(acc, tab + 4 * st, xp, yp, zp);
+    corner8(acc, tab + 5 * st, xp, ym, zp);
+    corner8(acc, tab + 6 * st, xm, ym, zp);
+    corner8(acc, tab + 7 * st, xm, yp, zp);
+  } else {
+    const float4 rot = geo[8];
+    const float* v = reinterpret_cast<const float*>(geo + 2);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      float dx = v[i * 3 + 0] - kx, dy = v[i * 3 + 1] - ky, dz = v[i * 3 + 2] - kz;
+      const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;     // identity when not rotated
+      const Axis ax = rpe_axis_fast(tx, ls, c1, c0, n, sx), ay = rpe_axis_fast(ty, ls, c1, c0, n, sy),
+                 az = rpe_axis_fast(dz, ls, c1, c0, n, sz);
+      corner8(acc, tab + i * st, ax, ay, az);
+    }
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <bool HAS_BIAS, bool MQA>
+__global__ void __launch_bounds__(NTHREADS, 1)
+rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmVt, const FwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
+  const SmemLayout L = smem_layout(HAS_BIAS ? 8 * P.grid_n * P.grid_n * P.grid_n * 16 : 0);
+  uint8_t* sQ = smem + L.q;
+  uint8_t* sK = smem + L.k;
+  uint8_t* sVt = smem + L.vt;
+  uint8_t* sP = smem + L.p;
+  const char* sTab = reinterpret_cast<const char*>(smem + L.tables);
+  float4* sBias = reinterpret_cast<float4*>(smem + L.bias);
+  float4* sXyz = reinterpret_cast<float4*>(smem + L.xyz);
+  float4* sGeo = reinterpret_cast<float4*>(smem + L.geo);
+  float* sMax = reinterpret_cast<float*>(smem + L.smax);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_kfree = bars + 3;
+  uint64_t* bar_s = bars + 4;       // [2]
+  uint64_t* bar_p = bars + 6;
+  uint64_t* bar_pv = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_control = warp == NCOMPUTE_WARPS;
+
+  if (is_control) {
+    if (lane == 0) {
+      mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_kfree, 1);
+      mbar_init(bar_s + 0, 1); mbar_init(bar_s + 1, 1);
+      mbar_init(bar_p, NCOMPUTE); mbar_init(bar_pv, 1);
+      fence_barrier_init();
+      prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
+    }
+    __syncwarp();
+    tmem_alloc<TMEM_COLS>(tmem_slot);
+  } else if (HAS_BIAS) {
+    // tables -> shared memory, once per (persistent) CTA
+    const int n4 = 8 * P.grid_n * P.grid_n * P.grid_n;
+    float4* dst = reinterpret_cast<float4*>(smem + L.tables);
+    for (int i = tid; i < n4; i += NCOMPUTE) dst[i] = __ldg(P.tables + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 128;
+
+  const uint32_t idesc_s = umma_idesc_bf16(BM, BN);
+  const uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+
+  uint32_t g = 0;          // tiles processed by this CTA so far (phase bookkeeping)
+  uint32_t it = 0;         // items processed by this CTA so far
+
+  for (int item = blockIdx.x; item < P.items; item += gridDim.x, ++it) {
+    const int split = item % P.splits;
+    const int mt = (item / P.splits) % P.mtiles;
+    const int b = item / (P.splits * P.mtiles);
+    const int tile_begin = split * P.tiles_per_split;
+    const int total_tiles = P.nKp / BN;
+    const int T = min(P.tiles_per_split, total_tiles - tile_begin);
+    int q0, hsel;
+    if (MQA) { q0 = mt * QT; hsel = 0; } else { q0 = (mt >> 2) * BM; hsel = mt & 3; }
+    const int hk = MQA ? 0 : hsel;
+    const int qrow0 = MQA ? (b * P.nQp + q0) * 4 : ((b * 4 + hsel) * P.nQp + q0);
+    const int krow0 = (b * P.kvh + hk) * P.nKp;
+    const int vrow0 = (b * P.kvh + hk) * HD;
+
+    if (is_control) {
+      // ======================================================================== control warp (one lane)
+      if (lane == 0) {
+        if (it > 0) mbar_wait(bar_pv, (g - 1) & 1);       // last PV of the previous item: sVt / sQ are free
+        mbar_arrive_expect_tx(bar_q, BM * 128);
+        tma_load_2d(sQ, &tmQ, 0, qrow0, bar_q);
+        mbar_arrive_expect_tx(bar_k, BN * 128 + (HAS_BIAS ? BN * 16 : 0));
+        tma_load_2d(sK, &tmK, 0, krow0 + tile_begin * BN, bar_k);
+        if (HAS_BIAS) bulk_load_1d(sXyz + (g & 1) * BN, P.xyz4 + (size_t)b * P.nKp + tile_begin * BN, BN * 16, bar_k);
+        mbar_arrive_expect_tx(bar_v, HD * 128);
+        tma_load_2d(sVt, &tmVt, tile_begin * BN, vrow0, bar_v);
+        mbar_wait(bar_q, it & 1);
+        mbar_wait(bar_k, g & 1);
+        tc_fence_after();
+        {
+          const uint64_t da = umma_desc_sw128(smem_u32(sQ)), db = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk)
+            umma_bf16(tS0 + (g & 1) * BN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc_s, kk > 0);
+          umma_commit(bar_s + (g & 1));
+          umma_commit(bar_kfree);
+        }
+        for (int j = 0; j < T; ++j) {
+          const uint32_t gj = g + j;
+          if (j + 1 < T) {
+            mbar_wait(bar_kfree, gj & 1);
+            mbar_arrive_expect_tx(bar_k, BN * 128 + (HAS_BIAS ? BN * 16 : 0));
+            tma_load_2d(sK, &tmK, 0, krow0 + (tile_begin + j + 1) * BN, bar_k);
+            if (HAS_BIAS)
+              bulk_load_1d(sXyz + ((gj + 1) & 1) * BN, P.xyz4 + (size_t)b * P.nKp + (tile_begin + j + 1) * BN, BN * 16, bar_k);
+            mbar_wait(bar_k, (gj + 1) & 1);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(sQ)), db = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk)
+              umma_bf16(tS0 + ((gj + 1) & 1) * BN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc_s, kk > 0);
+            umma_commit(bar_s + ((gj + 1) & 1));
+            umma_commit(bar_kfree);
+          }
+          mbar_wait(bar_p, gj & 1);
+          mbar_wait(bar_v, gj & 1);
+          tc_fence_after();
+          {
+            const uint64_t da = umma_desc_sw128(smem_u32(sP)), db = umma_desc_sw128(smem_u32(sVt));
+#pragma unroll
+            for (int kk = 0; kk < BN / 16; ++kk)
+              umma_bf16(tO, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc_o, (j > 0) || (kk > 0));
+            umma_commit(bar_pv);
+          }
+          if (j + 1 < T) {
+            mbar_wait(bar_pv, gj & 1);
+            mbar_arrive_expect_tx(bar_v, HD * 128);
+            tma_load_2d(sVt, &tmVt, (tile_begin + j + 1) * BN, vrow0, bar_v);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      // ======================================================================== compute warps
+      const int quarter = warp & 3, slice = warp >> 2;
+      const int row = quarter * 32 + lane;                 // TMEM lane == MMA row
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      if (HAS_BIAS) {
+        // query geometry records of this tile -> smem (previous item's readers are past their last barrier)
+        const float4* src = P.geo + ((size_t)b * P.nQp + q0) * GEO_F4;
+        for (int i = tid; i < QT * GEO_F4; i += NCOMPUTE) sGeo[i] = __ldg(src + i);
+        named_bar_sync(1, NCOMPUTE);
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < T; ++j) {
+        const uint32_t gj = g + j;
+        const int key0 = (tile_begin + j) * BN;
+        if (HAS_BIAS) {
+          mbar_wait(bar_k, gj & 1);                          // key xyz of this tile has landed
+          const int kg = warp & 1;                           // key group (32 consecutive keys), lane = key
+          const float4 kx = sXyz[(gj & 1) * BN + kg * 32 + lane];
+#pragma unroll 1
+          for (int u = 0; u < 4; ++u) {
+            const int q = (warp >> 1) + 8 * u;
+            const float4 bias = rpe_bias_pair(sGeo + q * GEO_F4, kx.x, kx.y, kx.z, sTab, P.grid_n, P.log_scale, P.c1, P.c0);
+            sBias[q * BIAS_STRIDE_F4 + kg * 32 + lane] = bias;
+          }
+        }
+        named_bar_sync(1, NCOMPUTE);                         // (a) bias tile complete (and previous smax reads done)
+        mbar_wait(bar_s + (gj & 1), (gj >> 1) & 1);          // S tile is in TMEM
+        tc_fence_after();
+        uint32_t sr[16];
+        tmem_ld16(tS0 + (gj & 1) * BN + lane_addr + slice * 16, sr);
+        tmem_ld_wait();
+        float x[16];
+        float pmax = -INFINITY;
+        {
+          const float* brow = nullptr;
+          if (HAS_BIAS) brow = reinterpret_cast<const float*>(sBias + (row >> 2) * BIAS_STRIDE_F4 + slice * 16) + (row & 3);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float s = __uint_as_float(sr[c]);
+            if (HAS_BIAS) s += brow[c * 4];
+            s *= LOG2E;
+            if (key0 + slice * 16 + c >= P.nK) s = -INFINITY;
+            x[c] = s;
+            pmax = fmaxf(pmax, s);
+          }
+        }
+        sMax[row * 4 + slice] = pmax;
+        named_bar_sync(2, NCOMPUTE);                         // (b)
+        const float4 pm = *reinterpret_cast<const float4*>(sMax + row * 4);
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(pm.x, pm.y), fmaxf(pm.z, pm.w)));
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = ex2_approx(m_run - m_use);       // m_run = -inf -> 0
+        float psum = 0.f;
+        uint32_t pk[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          const float p0 = ex2_approx(x[c] - m_use), p1 = ex2_approx(x[c + 1] - m_use);
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+          // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
+          const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&pk[c >> 1]);
+          psum += __bfloat162float(rb.x) + __bfloat162float(rb.y);
+        }
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
+        if (j > 0) {
+          mbar_wait(bar_pv, (gj - 1) & 1);                   // PV of the previous tile done: O readable, sP free
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {      // rescale this thread's 16 O columns in place
+            uint32_t o[16];
+            tmem_ld16(tO + lane_addr + slice * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(tO + lane_addr + slice * 16, o);
+            tmem_st_wait();
+          }
+        }
+        {
+          // P[row][16*slice .. +15] -> sP, K-major rows of 128 B with the 128-byte swizzle (chunk ^= row % 8)
+          uint8_t* prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
+          const int ch0 = slice * 2, ch1 = slice * 2 + 1;
+          *reinterpret_cast<uint4*>(prow + ((ch0 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(prow + ((ch1 ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
+      // ------------------------------------------------------------------ item epilogue
+      mbar_wait(bar_pv, (g + T - 1) & 1);
+      tc_fence_after();
+      sMax[row * 4 + slice] = l_run;
+      named_bar_sync(2, NCOMPUTE);
+      const float4 pl = *reinterpret_cast<const float4*>(sMax + row * 4);
+      const float l_tot = (pl.x + pl.y) + (pl.z + pl.w);
+      uint32_t o[16];
+      tmem_ld16(tO + lane_addr + slice * 16, o);
+      tmem_ld_wait();
+      const int q = MQA ? q0 + (row >> 2) : q0 + row;
+      const int h = MQA ? (row & 3) : hsel;
+      if (P.splits == 1) {
+        if (q < P.nQ) {
+          const float inv = 1.0f / l_tot;
+          float4* dst = reinterpret_cast<float4*>(P.out + (((size_t)b * P.nQ + q) * 4 + h) * HD + slice * 16);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            dst[c] = make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv,
+                                 __uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv);
+          if (slice == 0) P.lse[((size_t)b * 4 + h) * P.nQ + q] = (m_run + log2f(l_tot)) * LN2;
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(P.part_o + ((size_t)item * BM + row) * HD + slice * 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_float4(__uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]), __uint_as_float(o[4 * c + 2]),
+                               __uint_as_float(o[4 * c + 3]));
+        if (slice == 0) P.part_ml[(size_t)item * BM + row] = make_float2(m_run, l_tot);
+      }
+      tc_fence_before();
+      named_bar_sync(1, NCOMPUTE);     // sMax / sGeo / TMEM O reads are done before the next item starts
+    }
+    g += (uint32_t)T;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (is_control) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ split combine
+__global__ void fwd_combine_kernel(FwdParams P, int mqa) {
+  // one thread per (b, mtile, row, 16-column slice)
+  const size_t total = (size_t)P.B * P.mtiles * BM * 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int slice = (int)(i & 3);
+    const int row = (int)((i >> 2) % BM);
+    const size_t bm = (i >> 2) / BM;                        // b * mtiles + mt
+    const int mt = (int)(bm % P.mtiles), b = (int)(bm / P.mtiles);
+    int q, h;
+    if (mqa) { q = mt * QT + (row >> 2); h = row & 3; } else { q = (mt >> 2) * BM + row; h = mt & 3; }
+    if (q >= P.nQ) continue;
+    float m = -INFINITY;
+    for (int s = 0; s < P.splits; ++s) m = fmaxf(m, P.part_ml[(bm * P.splits + s) * BM + row].x);
+    float lsum = 0.f, acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int s = 0; s < P.splits; ++s) {
+      const float2 ml = P.part_ml[(bm * P.splits + s) * BM + row];
+      const float w = exp2f(ml.x - m);
+      lsum += ml.y * w;
+      const float4* src = reinterpret_cast<const float4*>(P.part_o + ((bm * P.splits + s) * BM + row) * HD + slice * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = src[c];
+        acc[4 * c] += v.x * w; acc[4 * c + 1] += v.y * w; acc[4 * c + 2] += v.z * w; acc[4 * c + 3] += v.w * w;
+      }
+    }
+    const float inv = 1.0f / lsum;
+    float4* dst = reinterpret_cast<float4*>(P.out + (((size_t)b * P.nQ + q) * 4 + h) * HD + slice * 16);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+    if (slice == 0) P.lse[((size_t)b * 4 + h) * P.nQ + q] = (m + log2f(lsum)) * LN2;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ packing (shared with bwd)
+__global__ void vdetr_pack_kernel(VdetrPack K) {
+  const size_t nq = (size_t)K.B * K.nQp * 4 * 64;           // destination elements of Qp
+  const size_t nk = (size_t)K.B * K.kvh * K.nKp * 64;
+  const size_t nx = K.has_bias ? (size_t)K.B * K.nKp : 0;
+  const size_t ng = K.has_bias ? (size_t)K.B * K.nQp : 0;
+  const size_t total = nq + 2 * nk + nx + ng;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nq) {
+      // destination row-major [rows][64]; MQA rows = (b*nQp + q)*4 + h ; MHA rows = (b*4 + h)*nQp + q
+      const int d = (int)(i & 63);
+      const size_t r = i >> 6;
+      int b, q, h;
+      if (K.kvh == 1) { h = (int)(r & 3); q = (int)((r >> 2) % K.nQp); b = (int)((r >> 2) / K.nQp); }
+      else { q = (int)(r % K.nQp); h = (int)((r / K.nQp) & 3); b = (int)(r / ((size_t)K.nQp * 4)); }
+      float val = 0.f;
+      if (q < K.nQ) val = K.q[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
+      K.qp[i] = __float2bfloat16_rn(val);
+      if (K.dout) {
+        float dv = 0.f;
+        if (q < K.nQ) dv = K.dout[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
+        K.dop[i] = __float2bfloat16_rn(dv);
+      }
+    } else if (i < nq + nk) {
+      const size_t e = i - nq;                               // Kp [b][hk][key][d]
+      const int d = (int)(e & 63);
+      const size_t r = e >> 6;
+      const int key = (int)(r % K.nKp);
+      const int hk = (int)((r / K.nKp) % K.kvh), b = (int)(r / ((size_t)K.nKp * K.kvh));
+      float val = 0.f;
+      if (key < K.nK) val = K.k[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
+      K.kp[e] = __float2bfloat16_rn(val);
+      if (K.vp) {                                            // row-major V as well (backward: dP = dO V^T)
+        float vv = 0.f;
+        if (key < K.nK) vv = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
+        K.vp[e] = __float2bfloat16_rn(vv);
+      }
+    } else if (i < nq + 2 * nk) {
+      const size_t e = i - nq - nk;                          // Vtp [b][hk][d][key]
+      const int key = (int)(e % K.nKp);
+      const size_t r = e / K.nKp;
+      const int d = (int)(r & 63);
+      const int hk = (int)((r >> 6) % K.kvh), b = (int)((r >> 6) / K.kvh);
+      float val = 0.f;
+      if (key < K.nK) val = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
+      K.vtp[e] = __float2bfloat16_rn(val);
+    } else if (i < nq + 2 * nk + nx) {
+      const size_t e = i - nq - 2 * nk;
+      const int key = (int)(e % K.nKp), b = (int)(e / K.nKp);
+      float4 o = make_float4(1e9f, 1e9f, 1e9f, 0.f);
+      if (key < K.nK) {
+        const float* s = K.xyz + ((size_t)b * K.nK + key) * 3;
+        o = make_float4(s[0], s[1], s[2], 0.f);
+      }
+      K.xyz4[e] = o;
+    } else {
+      const size_t e = i - nq - 2 * nk - nx;
+      const int q = (int)(e % K.nQp), b = (int)(e / K.nQp);
+      float v[24];
+#pragma unroll
+      for (int t = 0; t < 24; ++t) v[t] = 0.f;
+      float c = 1.f, s = 0.f;
+      if (q < K.nQ) {
+        const float* src = K.ref + ((size_t)b * K.nQ + q) * 24;
+#pragma unroll
+        for (int t = 0; t < 24; ++t) v[t] = src[t];
+        if (K.ang) { const float a = K.ang[(size_t)b * K.nQ + q]; c = cosf(a); s = sinf(a); }
+      }
+      // axis aligned?  vertex i = centre + (sx,sy,sz) * half (SURVEY Appendix A sign table)
+      const float xp = v[0], yp = v[1], zm = v[2], ym = v[4], xm = v[6], zp = v[14];
+      bool fast = (K.ang == nullptr);
+      const float sxp[8] = {1, 1, 0, 0, 1, 1, 0, 0}, syp[8] = {1, 0, 0, 1, 1, 0, 0, 1}, szp[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        fast = fast && (v[t * 3 + 0] == (sxp[t] != 0.f ? xp : xm)) && (v[t * 3 + 1] == (syp[t] != 0.f ? yp : ym)) &&
+               (v[t * 3 + 2] == (szp[t] != 0.f ? zp : zm));
+      }
+      float4* dst = K.geo + e * 9;
+      dst[0] = make_float4(xp, yp, zp, __int_as_float(fast ? 1 : 0));
+      dst[1] = make_float4(xm, ym, zm, 0.f);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) dst[2 + t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+      dst[8] = make_float4(c, s, 0.f, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+namespace {
+
+struct FwdPlan {
+  int nQp, nKp, mtiles, splits, tiles_per_split, items;
+  size_t off_qp, off_kp, off_vtp, off_xyz, off_geo, off_po, off_pml, total;
+};
+
+FwdPlan make_plan(const VdetrXattnShape* s) {
+  FwdPlan p;
+  const bool mqa = s->kv_heads == 1;
+  p.nQp = mqa ? (s->nQ + QT - 1) / QT * QT : (s->nQ + BM - 1) / BM * BM;
+  p.nKp = (s->nK + BN - 1) / BN * BN;
+  p.mtiles = mqa ? p.nQp / QT : (p.nQp / BM) * 4;
+  const int ktiles = p.nKp / BN;
+  const int sms = vdetr_num_sms();
+  const long base = (long)s->B * p.mtiles;
+  int best = 1;
+  double best_eff = -1.0;
+  for (int sp = 1; sp <= 16; ++sp) {
+    if (sp > 1 && ktiles / sp < 4) break;                 // keep >= 4 key tiles per split
+    const int tps = (ktiles + sp - 1) / sp;
+    const int real = (ktiles + tps - 1) / tps;
+    if (real != sp) continue;
+    const double waves = (double)(base * sp) / sms;
+    const double eff = waves / (double)((long)((base * sp + sms - 1) / sms));
+    if (eff > best_eff + 0.04) { best_eff = eff; best = sp; }
+    if (eff >= 0.93) { best = sp; break; }
+  }
+  p.splits = best;
+  p.tiles_per_split = (ktiles + best - 1) / best;
+  p.items = (int)(base * best);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += vdetr_align_up(bytes, 1024); return r; };
+  p.off_qp = take((size_t)s->B * p.nQp * 4 * 64 * 2);
+  p.off_kp = take((size_t)s->B * s->kv_heads * p.nKp * 64 * 2);
+  p.off_vtp = take((size_t)s->B * s->kv_heads * p.nKp * 64 * 2);
+  p.off_xyz = take(s->has_bias ? (size_t)s->B * p.nKp * 16 : 0);
+  p.off_geo = take(s->has_bias ? (size_t)s->B * p.nQp * GEO_F4 * 16 : 0);
+  p.off_po = take(best > 1 ? (size_t)p.items * BM * HD * 4 : 0);
+  p.off_pml = take(best > 1 ? (size_t)p.items * BM * 8 : 0);
+  p.total = o;
+  return p;
+}
+
+}  // namespace
+
+size_t tc_xattn_fwd_workspace(const VdetrXattnShape* s) { return make_plan(s).total; }
+
+int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
+                 const float* ref, const float* ang, const float* tables, float* out, float* lse, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  const bool mqa = s->kv_heads == 1;
+  if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
+  const FwdPlan pl = make_plan(s);
+  if (!ws || ws_bytes < pl.total) return VDETR_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return VDETR_ERR_WORKSPACE;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+
+  VdetrPack pk = {};
+  pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = pl.nQp; pk.nKp = pl.nKp; pk.kvh = s->kv_heads; pk.has_bias = s->has_bias;
+  pk.q = q; pk.k = k; pk.v = v; pk.xyz = xyz; pk.ref = ref; pk.ang = (s->has_bias && s->rotate) ? ang : nullptr;
+  pk.qp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_qp);
+  pk.kp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_kp);
+  pk.vtp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_vtp);
+  pk.xyz4 = reinterpret_cast<float4*>(w + pl.off_xyz);
+  pk.geo = reinterpret_cast<float4*>(w + pl.off_geo);
+  vdetr_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(pk);
+  VDETR_LAUNCH_CHECK();
+
+  CUtensorMap tmQ, tmK, tmVt;
+  int rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, (uint64_t)s->B * pl.nQp * 4, BM))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, (uint64_t)s->B * s->kv_heads * pl.nKp, BN))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_2d(&tmVt, pk.vtp, (uint64_t)s->B * s->kv_heads * HD, (uint64_t)pl.nKp, HD))) return rc;
+
+  FwdParams P = {};
+  P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = pl.nQp; P.nKp = pl.nKp; P.kvh = s->kv_heads;
+  P.mtiles = pl.mtiles; P.splits = pl.splits; P.tiles_per_split = pl.tiles_per_split; P.items = pl.items;
+  P.grid_n = s->has_bias ? s->grid_n : 0;
+  P.log_scale = s->log_scale;
+  P.c1 = s->has_bias ? (float)s->grid_n / (2.0f * 3.0f * s->max_value) : 0.f;
+  P.c0 = s->has_bias ? 0.5f * (float)(s->grid_n - 1) : 0.f;
+  P.xyz4 = pk.xyz4; P.geo = pk.geo; P.tables = reinterpret_cast<const float4*>(tables);
+  P.out = out; P.lse = lse;
+  P.part_o = reinterpret_cast<float*>(w + pl.off_po);
+  P.part_ml = reinterpret_cast<float2*>(w + pl.off_pml);
+
+  const int table_bytes = s->has_bias ? 8 * s->grid_n * s->grid_n * s->grid_n * 16 : 0;
+  const SmemLayout L = smem_layout(table_bytes);
+  if (L.total + 1024 > 232448) return VDETR_ERR_UNSUPPORTED;
+  const size_t smem = L.total + 1024;     // slack for the manual 1024-B alignment
+  const int grid = pl.items < vdetr_num_sms() ? pl.items : vdetr_num_sms();
+  if (s->has_bias) {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_fwd_kernel<true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);
+  } else if (mqa) {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_fwd_kernel<false, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);
+  } else {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_fwd_kernel<false, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);
+  }
+  VDETR_LAUNCH_CHECK();
+  if (pl.splits > 1) {
+    const size_t total = (size_t)s->B * pl.mtiles * BM * 4;
+    int blocks = (int)((total + 255) / 256);
+    fwd_combine_kernel<<<blocks, 256, 0, st>>>(P, mqa ? 1 : 0);
+    VDETR_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -30,7 +30,7 @@ def _shape(q, k, tables, log_scale, max_value, rotate, has_bias):
 
 class _RpeAttention(Function):
     @staticmethod
-    def forward(ctx, q, k, v, xyz, ref_pts, ref_angle, tables, log_scale, max_value, impl):
+    def forward(ctx, q, k, v, xyz, ref_pts, ref_angle, tables, log_scale, max_value, impl, impl_bwd):
         has_bias = tables is not None
         for name, t in (("q", q), ("k", k), ("v", v)):
             _C.require_cuda(name, t, torch.float32)
@@ -49,7 +49,7 @@ class _RpeAttention(Function):
             _C.check(L.vdetr_xattn_fwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
                                        _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
         ctx.save_for_backward(q, k, v, xyz, ref_pts, ref_angle, tables, out, lse)
-        ctx.meta = (log_scale, max_value, impl, has_bias)
+        ctx.meta = (log_scale, max_value, impl_bwd, has_bias)
         return out
 
     @staticmethod
@@ -67,11 +67,11 @@ class _RpeAttention(Function):
             _C.check(L.vdetr_xattn_bwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
                                        _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(dout), _C.ptr(dq), _C.ptr(dk),
                                        _C.ptr(dv), _C.ptr(dtab), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
-        return dq, dk, dv, None, None, None, dtab, None, None, None
+        return dq, dk, dv, None, None, None, dtab, None, None, None, None
 
 
 def rpe_attention(q, k, v, xyz=None, ref_pts=None, ref_angle=None, tables=None, log_scale=512.0, max_value=4.0,
-                  impl=None):
+                  impl=None, impl_bwd=None):
     """softmax_k(q k^T + rpe(ref_pts, xyz, tables)) v.
 
     q [B,nQ,H,hd] (pre-scaled by hd^-0.5), k/v [B,nK,kvh,hd] (kvh = 1: shared K/V head, kvh = H: per head),
@@ -79,11 +79,12 @@ def rpe_attention(q, k, v, xyz=None, ref_pts=None, ref_angle=None, tables=None, 
     Returns [B,nQ,H,hd].  Gradients: q, k, v, tables (xyz / ref_pts are detached in the reference).
     """
     impl = default_impl() if impl is None else impl
+    impl_bwd = int(os.environ.get("VDETR_B200_IMPL_BWD", impl)) if impl_bwd is None else impl_bwd
     return _RpeAttention.apply(q.contiguous(), k.contiguous(), v.contiguous(),
                                None if xyz is None else xyz.contiguous(),
                                None if ref_pts is None else ref_pts.contiguous(),
                                None if ref_angle is None else ref_angle.contiguous(),
-                               None if tables is None else tables.contiguous(), log_scale, max_value, impl)
+                               None if tables is None else tables.contiguous(), log_scale, max_value, impl, impl_bwd)
 
 
 def rpe_bias(xyz, ref_pts, tables, ref_angle=None, log_scale=512.0, max_value=4.0):
