@@ -117,6 +117,13 @@ int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, co
 int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
                    const float* tables, float* rpe, void* stream);
 
+/* Adjoint of vdetr_rpe_bias w.r.t. the tables: dtables[8,n,n,n,H] = sum_{b,q,k} dbias[b,q,k,h] * w_corner
+ * (what autograd of F.grid_sample returns for its input at vdetr_transformer.py:727-731).
+ * dbias is given pair-major: [B,nQ,nK,H] f32.  dtables is fully overwritten. */
+size_t vdetr_rpe_dtables_workspace_bytes(const VdetrXattnShape* s);
+int vdetr_rpe_dtables(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
+                      const float* dbias, float* dtables, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

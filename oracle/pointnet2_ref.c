@@ -27,9 +27,11 @@ static int opt_n_threads(int work_size) {
   return t;
 }
 
-/* nvcc (-fmad=true) contracts  a*a + b*b + c*c  (left-assoc) into fma(c,c, fma(b,b, a*a));
- * SASS of the rebuilt reference: FMUL, FFMA, FFMA (SURVEY.md 2.3 [probe]). */
-static inline float sumsq3(float a, float b, float c) { return fmaf(c, c, fmaf(b, b, a * a)); }
+/* nvcc (-fmad=true) contracts  x*x + y*y + z*z  into  fma(z,z, fma(x,x, y*y)):  the SASS of the rebuilt
+ * reference (oracle/_ref, cuobjdump) is  FMUL y,y ; FFMA x,x ; FFMA z,z  in the FPS kernel (both for |p|^2 and
+ * for the distance) and in query_ball_point_kernel.  Verified on a B200: with any other order the indices
+ * diverge from the reference after a few dozen rounds on lattice data. */
+static inline float sumsq3(float x, float y, float z) { return fmaf(z, z, fmaf(x, x, y * y)); }
 
 /* src/sampling_gpu.cu:72-176 + host init src/sampling.cpp:67-88 */
 void pn2_ref_fps(int b, int n, int m, const float* dataset, int32_t* idxs) {

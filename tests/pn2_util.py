@@ -75,9 +75,9 @@ def fps_slot_order_numpy(xyz, m):
         mag = (z * z + (y * y + (x * x).astype(f)).astype(f)).astype(f)      # not fma-exact; only used for the skip rule
         mag64 = x.astype(np.float64) ** 2 + y.astype(np.float64) ** 2 + z.astype(np.float64) ** 2
         # exact fma emulation in float64: fma(c,c,fma(b,b,a*a)) -- a*a rounded to f32, then each fma rounded once
-        def sumsq3(a, bb, c):
-            t = (a.astype(np.float64) * a.astype(np.float64)).astype(f)
-            t = (bb.astype(np.float64) * bb.astype(np.float64) + t.astype(np.float64)).astype(f)
+        def sumsq3(a, bb, c):      # fma(z,z, fma(x,x, y*y)): the contraction nvcc emits for the reference
+            t = (bb.astype(np.float64) * bb.astype(np.float64)).astype(f)
+            t = (a.astype(np.float64) * a.astype(np.float64) + t.astype(np.float64)).astype(f)
             return (c.astype(np.float64) * c.astype(np.float64) + t.astype(np.float64)).astype(f)
         mag = sumsq3(x, y, z)
         _ = mag64

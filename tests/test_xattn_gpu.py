@@ -134,3 +134,41 @@ def test_tc_forward_matches_oracle(seed, B, nQ, nK, kvh, rot):
     _cmp(got, want_b["o"], 2e-3, 1e-4, "out vs oracle on bf16-rounded operands")
     _cmp(got, want["o"], 6e-3, 1e-4, "out vs fp64 oracle")
     _cmp(got, ref_simt.cpu().numpy(), 6e-3, 1e-4, "out vs SIMT kernel")
+
+
+TC_BWD_CASES = [(21, 1, 32, 64, 1, False), (22, 2, 24, 80, 1, False), (23, 1, 16, 48, 1, True), (24, 2, 70, 333, 1, False),
+                (25, 1, 40, 200, 4, False), (26, 1, 130, 260, 4, False)]
+
+
+@pytest.mark.parametrize("seed,B,nQ,nK,kvh,rot", TC_BWD_CASES)
+def test_tc_backward_matches_oracle(seed, B, nQ, nK, kvh, rot):
+    has_bias = kvh == 1
+    I = _core_inputs(seed, B, nQ, nK, kvh, rot)
+    Ib = dict(I, q=_bf16_round(I["q"]), k=_bf16_round(I["k"]), v=_bf16_round(I["v"]), do=_bf16_round(I["do"]))
+    want = _oracle(Ib, has_bias)
+    got = _run(I, impl=0, has_bias=has_bias)
+    for name, tol in (("o", 3e-3), ("dq", 1e-2), ("dk", 1e-2), ("dv", 1e-2)):
+        assert np.isfinite(got[name]).all(), name
+        _cmp(got[name], want[name], tol, 1e-4, name)        # bf16 P / dS operands in the GEMMs: 1e-2 of max
+    if has_bias:
+        assert np.isfinite(got["dT"]).all()
+        _cmp(got["dT"], want["dT"], 1e-2, 1e-4, "dtables")
+
+
+def test_dtables_op_matches_oracle():
+    """dTables kernel alone (fp32 dS in): tight tolerance against the fp64 oracle."""
+    from vdetr_b200 import ops
+    I = _core_inputs(31, 2, 37, 150, 1, False, far=0.2)
+    rs = np.random.RandomState(5)
+    ds = (rs.standard_normal((2, 4, 37, 150)) * np.exp(rs.standard_normal((2, 4, 37, 150)) * 2)).astype(np.float32)
+    want = ora.rpe_bias_backward_tables(I["ref"], I["xyz"], I["tables"].shape, ds.astype(np.float64))
+    got = ops.rpe_bias_grad_tables(torch.from_numpy(I["xyz"]).cuda(), torch.from_numpy(I["ref"]).cuda(), None,
+                                   torch.from_numpy(I["tables"]).cuda(), torch.from_numpy(ds).cuda()).cpu().numpy()
+    _cmp(got, want, 2e-4, 1e-6, "dtables")
+    Ir = _core_inputs(32, 1, 20, 90, 1, True)
+    ds = rs.standard_normal((1, 4, 20, 90)).astype(np.float32)
+    want = ora.rpe_bias_backward_tables(Ir["ref"], Ir["xyz"], Ir["tables"].shape, ds.astype(np.float64), Ir["angle"])
+    got = ops.rpe_bias_grad_tables(torch.from_numpy(Ir["xyz"]).cuda(), torch.from_numpy(Ir["ref"]).cuda(),
+                                   torch.from_numpy(Ir["angle"]).cuda(), torch.from_numpy(Ir["tables"]).cuda(),
+                                   torch.from_numpy(ds).cuda()).cpu().numpy()
+    _cmp(got, want, 2e-4, 1e-6, "dtables rotated")

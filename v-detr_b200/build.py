@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvdetr_b200.so")
-SOURCES = ["api.cu", "pointnet2.cu", "rpe_simt.cu", "rpe_xattn_fwd.cu", "rpe_xattn_bwd.cu"]
+SOURCES = ["api.cu", "pointnet2.cu", "rpe_simt.cu", "rpe_xattn_fwd.cu", "rpe_xattn_bwd.cu", "rpe_dtables.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         raise RuntimeError(f"nvcc failed on {failed}")
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs)
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcublas"])
     open(stamp, "w").write(dig)
     return LIB
 

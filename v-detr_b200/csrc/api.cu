@@ -67,4 +67,17 @@ int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_
   return rpe_bias_launch(s, xyz, ref_pts, ref_angle, tables, rpe, (cudaStream_t)stream);
 }
 
+size_t vdetr_rpe_dtables_workspace_bytes(const VdetrXattnShape* s) {
+  if (vdetr_check_shape(s) != 0 || !s->has_bias) return 0;
+  return rpe_dtables_workspace(s);
+}
+
+int vdetr_rpe_dtables(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
+                      const float* dbias, float* dtables, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = vdetr_check_shape(s);
+  if (rc) return rc;
+  if (!s->has_bias || !xyz || !ref_pts || !dbias || !dtables) return VDETR_ERR_BAD_ARG;
+  return rpe_dtables_dense(s, xyz, ref_pts, ref_angle, dbias, dtables, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -23,6 +23,8 @@
 //    Here the CTA streams xyz through shared memory in tiles (broadcast LDS.128) with block-wide early exit.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -114,7 +116,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int32_t* __restrict__ idxs, Fp
       int k = slot_to_k(s, g);
       if (k < g.n) {
         x = pts[k * 3 + 0]; y = pts[k * 3 + 1]; z = pts[k * 3 + 2];
-        float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));   // FMA-contracted as nvcc does (:103)
+        float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));   // nvcc contracts as FMUL y,y; FFMA x,x; FFMA z,z (:103)
         if (!((double)mag <= 1e-3)) valid |= 1u << p;                    // :104 (double literal)
       }
     }
@@ -133,7 +135,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int32_t* __restrict__ idxs, Fp
     for (int p = 0; p < PPT; ++p) {
       if (valid & (1u << p)) {
         float dx = __fsub_rn(px[p], ox), dy = __fsub_rn(py[p], oy), dz = __fsub_rn(pz[p], oz);
-        float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // :107-108
+        float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));   // :107-108
         float d2 = fminf(d, pt[p]);                                           // :110
         pt[p] = d2;
         if (d2 > best) { best = d2; bp = p; }                                 // :111-112
@@ -198,10 +200,10 @@ fps_generic_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int3
     Cand c; c.key = 0ull; c.x = c.y = c.z = c.pad = 0.f;
     for (int k = tid; k < g.n; k += 1024) {
       float x = pts[k * 3], y = pts[k * 3 + 1], z = pts[k * 3 + 2];
-      float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
       if ((double)mag <= 1e-3) continue;
       float dx = __fsub_rn(x, ox), dy = __fsub_rn(y, oy), dz = __fsub_rn(z, oz);
-      float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+      float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
       float d2 = fminf(d, tmp[k]);
       tmp[k] = d2;
       if (d2 > -1.f) {
@@ -340,7 +342,7 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
       for (int t = 0; t < len && cnt < nsample; ++t) {
         const float4 p = tile[t];
         const float dx = __fsub_rn(cx, p.x), dy = __fsub_rn(cy, p.y), dz = __fsub_rn(cz, p.z);
-        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));     // :33-35, FMA-contracted
+        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));     // :33-35, FMA-contracted
         if (d2 < radius2) {                                                        // strict, :36
           const int k = base + t;
           if (cnt == 0) for (int l = 0; l < nsample; ++l) row[l] = k;              // :37-41
@@ -376,6 +378,10 @@ int vdetr_pn2_fps(const float* xyz, int B, int N, int M, int32_t* idx, void* wor
     // 16-CTA clusters need 16 free SMs in one GPC: use them only while all scenes can be co-resident.
     const bool allow16 = (attempt == 0) && (B * 16 <= vdetr_num_sms());
     FpsPlan p = fps_plan(g, allow16);
+    if (const char* dbg = getenv("VDETR_FPS_PLAN")) {          // debug override "cluster,ppt" (tests only)
+      int c = 0, pp = 0;
+      if (sscanf(dbg, "%d,%d", &c, &pp) == 2 && (long long)c * FPS_THREADS * pp >= g.slots) p = FpsPlan{c, pp};
+    }
     if (p.cluster == 0) {
       if (!workspace || workspace_bytes < (size_t)B * N * sizeof(float)) return VDETR_ERR_WORKSPACE;
       fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, (float*)workspace, idx, g);

@@ -41,3 +41,10 @@ struct VdetrPack {
   float4* geo;
 };
 __global__ void vdetr_pack_kernel(VdetrPack K);
+
+// dTables (rpe_dtables.cu)
+int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const float4* ds4,
+                       float* dtables, cudaStream_t st);
+size_t rpe_dtables_workspace(const VdetrXattnShape* s);
+int rpe_dtables_dense(const VdetrXattnShape* s, const float* xyz, const float* ref, const float* ang, const float* ds4,
+                      float* dtables, void* ws, size_t ws_bytes, cudaStream_t st);

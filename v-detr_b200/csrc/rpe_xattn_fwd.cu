@@ -17,10 +17,12 @@
 // Nothing of size nQ x nK ever reaches global memory.
 #include "rpe_internal.h"
 #include "tc_common.cuh"
+#include "rpe_fast.cuh"
 
 namespace {
 
 using namespace tc;
+using rpe::rpe_bias_pair;
 
 constexpr int NCOMPUTE_WARPS = 16;
 constexpr int NCOMPUTE = NCOMPUTE_WARPS * 32;     // 512
@@ -34,8 +36,6 @@ constexpr int BIAS_STRIDE_F4 = BN + 1;            // padded row (per query) of t
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int TMEM_COLS = 256;                    // S0 [0,64) S1 [64,128) O [128,192)
-constexpr float MAGIC = 12582912.0f;              // 1.5 * 2^23
-constexpr int MAGIC_BITS = 0x4B400000;
 
 struct FwdParams {
   int B, nQ, nK, nQp, nKp, kvh;
@@ -73,85 +73,6 @@ __host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
   return L;
 }
 
-// ------------------------------------------------------------------------------------------------ bias maths
-struct Axis {
-  float w0, w1;
-  int o0, o1;       // byte offsets of the two cells along this axis
-};
-template <int STRIDE_SHIFT_UNUSED = 0>
-__device__ __forceinline__ Axis rpe_axis_fast(float d, float ls, float c1, float c0, int n, int stride_bytes) {
-  Axis a;
-  float t = lg2_approx(fmaf(fabsf(d), ls, 1.0f)) * c1;
-  float ts = copysignf(t, d);
-  ts = fminf(fmaxf(ts, -c0 - 1.5f), (float)n - c0 + 0.5f);     // p in [-1.5, n+0.5]: outside both corners are padding
-  float p = ts + c0;
-  float r = (p - 0.5f) + MAGIC;                                 // round-to-nearest(p - 0.5) == floor(p) (ties are harmless)
-  float fl = r - MAGIC;
-  float f = p - fl;
-  int n0 = __float_as_int(r) - MAGIC_BITS;
-  a.w0 = ((unsigned)n0 < (unsigned)n) ? 1.0f - f : 0.0f;
-  a.w1 = ((unsigned)(n0 + 1) < (unsigned)n) ? f : 0.0f;
-  a.o0 = min(max(n0, 0), n - 1) * stride_bytes;
-  a.o1 = min(max(n0 + 1, 0), n - 1) * stride_bytes;
-  return a;
-}
-
-__device__ __forceinline__ void corner8(float4& acc, const char* tab, const Axis& ax, const Axis& ay, const Axis& az) {
-#pragma unroll
-  for (int cz = 0; cz < 2; ++cz) {
-    const int oz = cz ? az.o1 : az.o0;
-    const float wz = cz ? az.w1 : az.w0;
-#pragma unroll
-    for (int cy = 0; cy < 2; ++cy) {
-      const int ozy = oz + (cy ? ay.o1 : ay.o0);
-      const float wzy = wz * (cy ? ay.w1 : ay.w0);
-#pragma unroll
-      for (int cx = 0; cx < 2; ++cx) {
-        const float w = wzy * (cx ? ax.w1 : ax.w0);
-        const float4 t = *reinterpret_cast<const float4*>(tab + ozy + (cx ? ax.o1 : ax.o0));
-        acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y);
-        acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
-      }
-    }
-  }
-}
-
-// Bias of one (query,key) pair for the 4 heads.  geo: the query's record in shared memory (see pack kernel).
-__device__ __forceinline__ float4 rpe_bias_pair(const float4* __restrict__ geo, float kx, float ky, float kz,
-                                                const char* __restrict__ tab, int n, float ls, float c1, float c0) {
-  const int sx = 16, sy = 16 * n, sz = 16 * n * n, st = 16 * n * n * n;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 hi = geo[0];
-  if (__float_as_int(hi.w) != 0) {
-    // axis-aligned box: 2 distinct coordinates per axis -> 6 transforms instead of 24
-    const float4 lo = geo[1];
-    const Axis xp = rpe_axis_fast(hi.x - kx, ls, c1, c0, n, sx), xm = rpe_axis_fast(lo.x - kx, ls, c1, c0, n, sx);
-    const Axis yp = rpe_axis_fast(hi.y - ky, ls, c1, c0, n, sy), ym = rpe_axis_fast(lo.y - ky, ls, c1, c0, n, sy);
-    const Axis zp = rpe_axis_fast(hi.z - kz, ls, c1, c0, n, sz), zm = rpe_axis_fast(lo.z - kz, ls, c1, c0, n, sz);
-    // vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4:(+,+,+) 5:(+,-,+) 6:(-,-,+) 7:(-,+,+)
-    corner8(acc, tab + 0 * st, xp, yp, zm);
-    corner8(acc, tab + 1 * st, xp, ym, zm);
-    corner8(acc, tab + 2 * st, xm, ym, zm);
-    corner8(acc, tab + 3 * st, xm, yp, zm);
-    corner8(acc, tab + 4 * st, xp, yp, zp);
-    corner8(acc, tab + 5 * st, xp, ym, zp);
-    corner8(acc, tab + 6 * st, xm, ym, zp);
-    corner8(acc, tab + 7 * st, xm, yp, zp);
-  } else {
-    const float4 rot = geo[8];
-    const float* v = reinterpret_cast<const float*>(geo + 2);
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-      float dx = v[i * 3 + 0] - kx, dy = v[i * 3 + 1] - ky, dz = v[i * 3 + 2] - kz;
-      const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;     // identity when not rotated
-      const Axis ax = rpe_axis_fast(tx, ls, c1, c0, n, sx), ay = rpe_axis_fast(ty, ls, c1, c0, n, sy),
-                 az = rpe_axis_fast(dz, ls, c1, c0, n, sz);
-      corner8(acc, tab + i * st, ax, ay, az);
-    }
-  }
-  return acc;
-}
-
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool HAS_BIAS, bool MQA>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -171,20 +92,20 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* sMax = reinterpret_cast<float*>(smem + L.smax);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
-  uint64_t* bar_v = bars + 2;
-  uint64_t* bar_kfree = bars + 3;
-  uint64_t* bar_s = bars + 4;       // [2]
-  uint64_t* bar_p = bars + 6;
-  uint64_t* bar_pv = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_k = bars + 1;       // [2] one per key-xyz buffer: waiters can never fall two phases behind
+  uint64_t* bar_v = bars + 3;
+  uint64_t* bar_kfree = bars + 4;
+  uint64_t* bar_s = bars + 5;       // [2]
+  uint64_t* bar_p = bars + 7;
+  uint64_t* bar_pv = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_control = warp == NCOMPUTE_WARPS;
 
   if (is_control) {
     if (lane == 0) {
-      mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_kfree, 1);
+      mbar_init(bar_q, 1); mbar_init(bar_k + 0, 1); mbar_init(bar_k + 1, 1); mbar_init(bar_v, 1); mbar_init(bar_kfree, 1);
       mbar_init(bar_s + 0, 1); mbar_init(bar_s + 1, 1);
       mbar_init(bar_p, NCOMPUTE); mbar_init(bar_pv, 1);
       fence_barrier_init();
@@ -230,13 +151,14 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (it > 0) mbar_wait(bar_pv, (g - 1) & 1);       // last PV of the previous item: sVt / sQ are free
         mbar_arrive_expect_tx(bar_q, BM * 128);
         tma_load_2d(sQ, &tmQ, 0, qrow0, bar_q);
-        mbar_arrive_expect_tx(bar_k, BN * 128 + (HAS_BIAS ? BN * 16 : 0));
-        tma_load_2d(sK, &tmK, 0, krow0 + tile_begin * BN, bar_k);
-        if (HAS_BIAS) bulk_load_1d(sXyz + (g & 1) * BN, P.xyz4 + (size_t)b * P.nKp + tile_begin * BN, BN * 16, bar_k);
+        mbar_arrive_expect_tx(bar_k + (g & 1), BN * 128 + (HAS_BIAS ? BN * 16 : 0));
+        tma_load_2d(sK, &tmK, 0, krow0 + tile_begin * BN, bar_k + (g & 1));
+        if (HAS_BIAS)
+          bulk_load_1d(sXyz + (g & 1) * BN, P.xyz4 + (size_t)b * P.nKp + tile_begin * BN, BN * 16, bar_k + (g & 1));
         mbar_arrive_expect_tx(bar_v, HD * 128);
         tma_load_2d(sVt, &tmVt, tile_begin * BN, vrow0, bar_v);
         mbar_wait(bar_q, it & 1);
-        mbar_wait(bar_k, g & 1);
+        mbar_wait(bar_k + (g & 1), (g >> 1) & 1);
         tc_fence_after();
         {
           const uint64_t da = umma_desc_sw128(smem_u32(sQ)), db = umma_desc_sw128(smem_u32(sK));
@@ -250,11 +172,12 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t gj = g + j;
           if (j + 1 < T) {
             mbar_wait(bar_kfree, gj & 1);
-            mbar_arrive_expect_tx(bar_k, BN * 128 + (HAS_BIAS ? BN * 16 : 0));
-            tma_load_2d(sK, &tmK, 0, krow0 + (tile_begin + j + 1) * BN, bar_k);
+            uint64_t* bk = bar_k + ((gj + 1) & 1);
+            mbar_arrive_expect_tx(bk, BN * 128 + (HAS_BIAS ? BN * 16 : 0));
+            tma_load_2d(sK, &tmK, 0, krow0 + (tile_begin + j + 1) * BN, bk);
             if (HAS_BIAS)
-              bulk_load_1d(sXyz + ((gj + 1) & 1) * BN, P.xyz4 + (size_t)b * P.nKp + (tile_begin + j + 1) * BN, BN * 16, bar_k);
-            mbar_wait(bar_k, (gj + 1) & 1);
+              bulk_load_1d(sXyz + ((gj + 1) & 1) * BN, P.xyz4 + (size_t)b * P.nKp + (tile_begin + j + 1) * BN, BN * 16, bk);
+            mbar_wait(bk, ((gj + 1) >> 1) & 1);
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(sQ)), db = umma_desc_sw128(smem_u32(sK));
 #pragma unroll
@@ -297,7 +220,7 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t gj = g + j;
         const int key0 = (tile_begin + j) * BN;
         if (HAS_BIAS) {
-          mbar_wait(bar_k, gj & 1);                          // key xyz of this tile has landed
+          mbar_wait(bar_k + (gj & 1), (gj >> 1) & 1);        // key xyz of this tile has landed
           const int kg = warp & 1;                           // key group (32 consecutive keys), lane = key
           const float4 kx = sXyz[(gj & 1) * BN + kg * 32 + lane];
 #pragma unroll 1
@@ -454,8 +377,8 @@ __global__ void fwd_combine_kernel(FwdParams P, int mqa) {
 
 // ------------------------------------------------------------------------------------------------ packing (shared with bwd)
 __global__ void vdetr_pack_kernel(VdetrPack K) {
-  const size_t nq = (size_t)K.B * K.nQp * 4 * 64;           // destination elements of Qp
-  const size_t nk = (size_t)K.B * K.kvh * K.nKp * 64;
+  const size_t nq = K.qp ? (size_t)K.B * K.nQp * 4 * 64 : 0;           // destination elements of Qp
+  const size_t nk = K.kp ? (size_t)K.B * K.kvh * K.nKp * 64 : 0;
   const size_t nx = K.has_bias ? (size_t)K.B * K.nKp : 0;
   const size_t ng = K.has_bias ? (size_t)K.B * K.nQp : 0;
   const size_t total = nq + 2 * nk + nx + ng;
@@ -595,7 +518,7 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
   const FwdPlan pl = make_plan(s);
   if (!ws || ws_bytes < pl.total) return VDETR_ERR_WORKSPACE;
-  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return VDETR_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return VDETR_ERR_WORKSPACE;      // cudaMalloc / torch give >= 256 B
   uint8_t* w = reinterpret_cast<uint8_t*>(ws);
 
   VdetrPack pk = {};

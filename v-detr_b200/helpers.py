@@ -1,0 +1,88 @@
+"""Small building blocks of the decoder (drop-in for /root/reference/models/helpers.py:17-145).
+
+Same class names, constructor arguments and state_dict keys as the reference so that checkpoints load
+unchanged; these layers are plain PyTorch (cuBLAS / cuDNN) -- SURVEY.md 8(a) rows a7-a10 keep them outside
+the hand-written kernels.
+"""
+from __future__ import annotations
+
+import copy
+from functools import partial
+
+import torch.nn as nn
+
+
+class PositionEmbeddingLearned(nn.Module):
+    """Learned absolute position embedding: Conv1d - BN - ReLU - Conv1d on [B, N, C_in] (helpers.py:17-33)."""
+
+    def __init__(self, input_channel, num_pos_feats=288):
+        super().__init__()
+        self.position_embedding_head = nn.Sequential(
+            nn.Conv1d(input_channel, num_pos_feats, kernel_size=1),
+            nn.BatchNorm1d(num_pos_feats),
+            nn.ReLU(inplace=True),
+            nn.Conv1d(num_pos_feats, num_pos_feats, kernel_size=1))
+
+    def forward(self, xyz):
+        return self.position_embedding_head(xyz.transpose(1, 2).contiguous())
+
+
+class BatchNormDim1Swap(nn.BatchNorm1d):
+    """BatchNorm over the channel dim of an [HW, N, C] tensor (helpers.py:36-53)."""
+
+    def forward(self, x):
+        return super().forward(x.permute(1, 2, 0)).permute(2, 0, 1)
+
+
+NORM_DICT = {"bn": BatchNormDim1Swap, "bn1d": nn.BatchNorm1d, "id": nn.Identity, "ln": nn.LayerNorm}
+ACTIVATION_DICT = {"relu": nn.ReLU, "gelu": nn.GELU, "leakyrelu": partial(nn.LeakyReLU, negative_slope=0.1)}
+WEIGHT_INIT_DICT = {"xavier_uniform": nn.init.xavier_uniform_}
+
+
+class GenericMLP(nn.Module):
+    """helpers.py:74-141: [Linear|Conv1d(k=1) - norm - act - dropout] x len(hidden_dims) + output layer."""
+
+    def __init__(self, input_dim, hidden_dims, output_dim, norm_fn_name=None, activation="relu", use_conv=False,
+                 dropout=None, hidden_use_bias=False, output_use_bias=True, output_use_activation=False,
+                 output_use_norm=False, weight_init_name=None):
+        super().__init__()
+        act = ACTIVATION_DICT[activation]
+        norm = NORM_DICT[norm_fn_name] if norm_fn_name is not None else None
+        if norm_fn_name == "ln" and use_conv:
+            norm = lambda c: nn.GroupNorm(1, c)  # noqa: E731  (LayerNorm over channels of a conv feature map)
+        if dropout is not None and not isinstance(dropout, list):
+            dropout = [dropout] * len(hidden_dims)
+
+        def dense(i, o, bias):
+            return nn.Conv1d(i, o, 1, bias=bias) if use_conv else nn.Linear(i, o, bias=bias)
+
+        mods, width = [], input_dim
+        for li, h in enumerate(hidden_dims):
+            mods.append(dense(width, h, hidden_use_bias))
+            if norm:
+                mods.append(norm(h))
+            mods.append(act())
+            if dropout is not None:
+                mods.append(nn.Dropout(p=dropout[li]))
+            width = h
+        mods.append(dense(width, output_dim, output_use_bias))
+        if output_use_norm:
+            mods.append(norm(output_dim))
+        if output_use_activation:
+            mods.append(act())
+        self.layers = nn.Sequential(*mods)
+        if weight_init_name is not None:
+            self.do_weight_init(weight_init_name)
+
+    def do_weight_init(self, weight_init_name):
+        init = WEIGHT_INIT_DICT[weight_init_name]
+        for _, p in self.named_parameters():
+            if p.dim() > 1:
+                init(p)
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+def get_clones(module, N):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])

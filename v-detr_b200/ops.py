@@ -99,3 +99,20 @@ def rpe_bias(xyz, ref_pts, tables, ref_angle=None, log_scale=512.0, max_value=4.
         _C.check(_C.lib().vdetr_rpe_bias(s, _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle), _C.ptr(tables), _C.ptr(out),
                                          _C.stream_ptr()))
     return out
+
+
+def rpe_bias_grad_tables(xyz, ref_pts, ref_angle, tables, dbias, log_scale=512.0, max_value=4.0):
+    """dTables [8,n,n,n,H] from a dense d(bias) [B,H,nQ,nK] (adjoint of ``rpe_bias``)."""
+    B, nK = xyz.shape[:2]
+    nQ = ref_pts.shape[1]
+    s = _C.XattnShape(B, nQ, nK, 4, 64, tables.shape[1], float(log_scale), float(max_value), int(ref_angle is not None), 1, 1)
+    ds4 = dbias.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty_like(tables)
+    L = _C.lib()
+    with torch.cuda.device(xyz.device):
+        nbytes = L.vdetr_rpe_dtables_workspace_bytes(s)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+        _C.check(L.vdetr_rpe_dtables(s, _C.ptr(xyz.contiguous()), _C.ptr(ref_pts.contiguous()),
+                                     _C.ptr(None if ref_angle is None else ref_angle.contiguous()), _C.ptr(ds4), _C.ptr(out),
+                                     _C.ptr(ws), nbytes, _C.stream_ptr()))
+    return out

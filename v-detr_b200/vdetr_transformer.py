@@ -1,0 +1,621 @@
+"""Drop-in for /root/reference/models/vdetr_transformer.py on top of the sm_100a kernels.
+
+Same public classes, constructor arguments, ``forward`` signatures and state_dict keys:
+``TransformerDecoder`` (:105-452), ``GlobalDecoderLayer`` (:455-582), ``FFNLayer`` (:585-606),
+``ShareSelfAttention`` (:609-653), ``GlobalShareCrossAttention`` (:656-758), ``BoxProcessor`` (:20-90),
+``convert_corners_camera2lidar`` (:98-102).
+
+What is different underneath:
+  * cross attention never materialises the [B,4,nQ,nK] bias or probability tensors: the eight vertex tables
+    (cpb_mlps evaluated on the 10^3 lattice, stays PyTorch so autograd reaches the MLP weights through
+    dTables) are handed to ``ops.rpe_attention`` -- one fused kernel forward, one backward;
+  * decoder self attention (``nn.MultiheadAttention`` in the reference, :468) is ``MultiheadSelfAttention``:
+    identical parameter names, the same fused kernel without bias;
+  * key tokens are visited in Morton order (attention is permutation invariant over keys) so that the 32 keys a
+    warp handles for one query fall into the same table cells and the table reads broadcast.
+There is no CPU path: modules raise if their inputs are not CUDA tensors.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from functools import partial
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import ops
+from .helpers import ACTIVATION_DICT, NORM_DICT, WEIGHT_INIT_DICT, GenericMLP, PositionEmbeddingLearned, get_clones
+
+
+# ------------------------------------------------------------------------------------------------- geometry
+def shift_scale_points(pred_xyz, src_range, dst_range=None):
+    """utils/pc_util.py:38-66 (only the default dst_range=[0,1] use of the decoder)."""
+    lo, hi = src_range
+    if dst_range is None:
+        return (pred_xyz - lo[:, None, :]) / (hi[:, None, :] - lo[:, None, :])
+    dlo, dhi = dst_range
+    return (pred_xyz - lo[:, None, :]) * (dhi - dlo)[:, None, :] / (hi - lo)[:, None, :] + dlo[:, None, :]
+
+
+def scale_points(pred_xyz, mult_factor):
+    """utils/pc_util.py:69-73."""
+    return pred_xyz * mult_factor[:, None, :]
+
+
+def box_corners_camera(center, size, angle):
+    """dataset_config.box_parametrization_to_corners for ScanNet (datasets/scannet.py:168-171 ->
+    utils/box_util.py:294-358): 8 corners in the camera frame, reference vertex order."""
+    cam = torch.stack((center[..., 0], -center[..., 2], center[..., 1]), dim=-1)
+    hl, hw, hh = size[..., 0:1] * 0.5, size[..., 1:2] * 0.5, size[..., 2:3] * 0.5
+    sx = size.new_tensor([1., 1., -1., -1., 1., 1., -1., -1.])
+    sy = size.new_tensor([1., 1., 1., 1., -1., -1., -1., -1.])
+    sz = size.new_tensor([1., -1., -1., 1., 1., -1., -1., 1.])
+    local = torch.stack((hl * sx, hh * sy, hw * sz), dim=-1)
+    c, s = torch.cos(angle), torch.sin(angle)
+    zero, one = torch.zeros_like(c), torch.ones_like(c)
+    rot = torch.stack((torch.stack((c, zero, s), -1), torch.stack((zero, one, zero), -1),
+                       torch.stack((-s, zero, c), -1)), -2)
+    return torch.matmul(local, rot.transpose(-1, -2)) + cam.unsqueeze(-2)
+
+
+class ScanNetBoxConfig:
+    """The part of ScannetDatasetConfig the decoder reads (datasets/scannet.py:38-41,168-171).  The reference's
+    own config object can be passed instead; only these attributes are used."""
+
+    def __init__(self, num_semcls=18, num_angle_bin=1):
+        self.num_semcls = num_semcls
+        self.num_angle_bin = num_angle_bin
+
+    @staticmethod
+    def box_parametrization_to_corners(center, size, angle):
+        return box_corners_camera(center, size, angle)
+
+
+def convert_corners_camera2lidar(corners_camera):
+    """(x_c, y_c, z_c) -> (x_c, z_c, -y_c); in place like the reference (:98-102)."""
+    y = corners_camera[..., 1].clone()
+    corners_camera[..., 1] = corners_camera[..., 2]
+    corners_camera[..., 2] = -y
+    return corners_camera
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def roty_batch_tensor(t):
+    c, s = torch.cos(t), torch.sin(t)
+    out = torch.zeros(tuple(t.shape) + (3, 3), dtype=torch.float32, device=t.device)
+    out[..., 0, 0] = c; out[..., 0, 2] = s; out[..., 1, 1] = 1; out[..., 2, 0] = -s; out[..., 2, 2] = c
+    return out
+
+
+def rotz_batch_tensor(t):
+    c, s = torch.cos(t), torch.sin(t)
+    out = torch.zeros(tuple(t.shape) + (3, 3), dtype=torch.float32, device=t.device)
+    out[..., 0, 0] = c; out[..., 0, 1] = -s; out[..., 1, 0] = s; out[..., 1, 1] = c; out[..., 2, 2] = 1
+    return out
+
+
+def morton_order(xyz: Tensor) -> Tensor:
+    """Permutation that sorts the key tokens of every scene along a 30-bit Morton curve.  xyz [B,N,3] -> [B,N]."""
+    lo = xyz.amin(dim=1, keepdim=True)
+    span = (xyz.amax(dim=1, keepdim=True) - lo).clamp_min(1e-6)
+    g = ((xyz - lo) / span * 1023.0).long().clamp_(0, 1023)
+
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(g[..., 0]) | (spread(g[..., 1]) << 1) | (spread(g[..., 2]) << 2)
+    return torch.argsort(code, dim=1)
+
+
+class BoxProcessor(object):
+    """Turns MLP head outputs into boxes (:20-90)."""
+
+    def __init__(self, dataset_config, cls_loss="celoss"):
+        self.dataset_config = dataset_config
+        self.cls_loss = cls_loss
+
+    def compute_predicted_center(self, center_offset, query_xyz, point_cloud_dims):
+        center_unnormalized = query_xyz + center_offset
+        return shift_scale_points(center_unnormalized, src_range=point_cloud_dims), center_unnormalized
+
+    def compute_predicted_class_size(self, size_normalized_offset, logits):
+        class_idx = logits.sigmoid().max(dim=-1)[1]
+        per_class = torch.tensor(self.dataset_config.mean_size_arr, device=logits.device).float()[class_idx]
+        return per_class + size_normalized_offset * per_class, size_normalized_offset * per_class
+
+    def compute_predicted_size(self, size_normalized, point_cloud_dims):
+        scene = torch.clamp(point_cloud_dims[1] - point_cloud_dims[0], min=1e-1)
+        return scale_points(size_normalized, mult_factor=scene)
+
+    def compute_predicted_angle(self, angle_logits, angle_residual, zero_angle=False):
+        nbin = angle_logits.shape[-1]
+        if nbin == 1 or zero_angle:
+            # keep the heads in the autograd graph (DDP), value is identically zero (:49-59)
+            if nbin == 1:
+                angle = (angle_logits * 0 + angle_residual * 0).squeeze(-1).clamp(min=0)
+            else:
+                angle = (angle_logits.sum(-1) * 0 + angle_residual.sum(-1) * 0).squeeze(-1).clamp(min=0)
+            return angle, angle
+        per_bin = 2 * np.pi / self.dataset_config.num_angle_bin
+        prob, cls = F.softmax(angle_logits, dim=-1).max(dim=-1)
+        cls = cls.detach()
+        angle = per_bin * cls + angle_residual.gather(2, cls.unsqueeze(-1)).squeeze(-1)
+        angle = torch.where(angle > np.pi, angle - 2 * np.pi, angle)
+        return angle, prob
+
+    def compute_objectness_and_cls_prob(self, cls_logits):
+        if self.cls_loss.split("_")[0] == "focalloss":
+            return cls_logits, cls_logits.sigmoid().max(dim=-1)[0]
+        assert cls_logits.shape[-1] == self.dataset_config.num_semcls + 1
+        prob = F.softmax(cls_logits, dim=-1)
+        return prob[..., :-1], 1 - prob[..., -1]
+
+    def box_parametrization_to_corners(self, box_center_unnorm, box_size_unnorm, box_angle):
+        return self.dataset_config.box_parametrization_to_corners(box_center_unnorm, box_size_unnorm, box_angle)
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def _dense_attention(q, k, v, bias, drop):
+    """Materialising attention used only for return_attn_weights / attn_mask / train-time attention dropout
+    (the fused kernels implement none of the three).  q [B,nQ,H,hd], k/v [B,nK,kvh,hd], bias [B,H,nQ,nK] or None."""
+    qh, kh, vh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2)
+    if bias is not None:
+        s = s + bias
+    p = torch.softmax(s, dim=-1)
+    o = (drop(p) @ vh).permute(0, 2, 1, 3)
+    return o, p
+
+
+class MultiheadSelfAttention(nn.Module):
+    """Stand-in for ``nn.MultiheadAttention(d_model, nhead, dropout)`` as used at :468/:541: same parameter
+    names (in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias), sequence-first tensors,
+    returns (output, None)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0):
+        super().__init__()
+        assert embed_dim % num_heads == 0
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        self.dropout = dropout
+        self.attn_drop = nn.Dropout(dropout)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+    def forward(self, query, key, value, attn_mask=None, key_padding_mask=None, need_weights=False):
+        L, B, D = query.shape
+        H, hd = self.num_heads, self.head_dim
+        wq, wk, wv = self.in_proj_weight.chunk(3)
+        bq, bk, bv = self.in_proj_bias.chunk(3)
+        if key is query:
+            qk = F.linear(query, self.in_proj_weight[: 2 * D], self.in_proj_bias[: 2 * D])
+            q, k = qk[..., :D], qk[..., D:]
+        else:
+            q, k = F.linear(query, wq, bq), F.linear(key, wk, bk)
+        v = F.linear(value, wv, bv)
+        q = (q * (hd ** -0.5)).reshape(L, B, H, hd).transpose(0, 1)
+        k = k.reshape(-1, B, H, hd).transpose(0, 1)
+        v = v.reshape(-1, B, H, hd).transpose(0, 1)
+        plain = attn_mask is None and key_padding_mask is None and not need_weights and \
+            not (self.training and self.dropout > 0)
+        weights = None
+        if plain:
+            o = ops.rpe_attention(q, k, v)
+        else:
+            bias = None
+            if attn_mask is not None:
+                bias = torch.zeros_like(attn_mask, dtype=q.dtype).masked_fill(attn_mask, float("-inf")) \
+                    if attn_mask.dtype == torch.bool else attn_mask
+            if key_padding_mask is not None:
+                pad = torch.zeros(B, 1, 1, k.shape[1], dtype=q.dtype, device=q.device).masked_fill(
+                    key_padding_mask[:, None, None, :], float("-inf"))
+                bias = pad if bias is None else bias + pad
+            o, weights = _dense_attention(q, k, v, bias, self.attn_drop)
+            weights = weights.mean(dim=1) if need_weights else None
+        o = o.transpose(0, 1).reshape(L, B, D)
+        return self.out_proj(o), weights
+
+
+class ShareSelfAttention(nn.Module):
+    """Self attention with one K/V head shared by all query heads (:609-653)."""
+
+    def __init__(self, dim, num_heads, qkv_bias=True, dropout=0.0, args=None):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.q = nn.Linear(dim, dim, bias=qkv_bias)
+        self.k = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.v = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(dropout)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(dropout)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def forward(self, query, key, value=None, attn_mask=None, key_padding_mask=None):
+        assert attn_mask is None and key_padding_mask is None
+        L, B, D = query.shape
+        H = self.num_heads
+        q = (self.q(query) * self.scale).reshape(L, B, H, D // H).transpose(0, 1)
+        k = self.k(key).transpose(0, 1).unsqueeze(2)
+        v = self.v(value).transpose(0, 1).unsqueeze(2)
+        if self.training and self.attn_drop.p > 0:
+            o, _ = _dense_attention(q, k, v, None, self.attn_drop)
+        else:
+            o = ops.rpe_attention(q, k, v)
+        x = self.proj(o.transpose(0, 1).reshape(L, B, D))
+        return self.proj_drop(x), None
+
+
+class GlobalShareCrossAttention(nn.Module):
+    """Cross attention with the 3-D Vertex relative position bias (:656-758)."""
+
+    def __init__(self, dim, num_heads, qkv_bias=True, attn_drop=0.0, proj_drop=0.0, args=None):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.log_scale = args.log_scale
+        self.rpe_quant = args.rpe_quant
+        self.angle_type = args.angle_type
+        self.interp_method, max_value, num_points = self.rpe_quant.split("_")
+        max_value, num_points = float(max_value), int(num_points)
+        lin = torch.linspace(-max_value, max_value, num_points, dtype=torch.float32)
+        self.register_buffer("relative_coords_table",
+                             torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), dim=-1).unsqueeze(0))
+        self.max_value = max_value
+        self.cpb_mlps = get_clones(self.build_cpb_mlp(3, args.rpe_dim, num_heads), 8)
+        self.q = nn.Linear(dim, dim, bias=qkv_bias)
+        self.k = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.v = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.softmax = nn.Softmax(dim=-1)
+        self.need_weights = False       # set True to get the [B,H,nQ,nK] probabilities back (debug path)
+
+    def build_cpb_mlp(self, in_dim, hidden_dim, out_dim):
+        return nn.Sequential(nn.Linear(in_dim, hidden_dim, bias=True), nn.ReLU(inplace=False),
+                             nn.Linear(hidden_dim, out_dim, bias=False))
+
+    def vertex_tables(self):
+        """[8, n, n, n, H]: the eight per-vertex MLPs evaluated on the lattice (:725).  Kernel input; its
+        gradient (dTables) is the kernel output that autograd carries on into the MLP weights."""
+        return torch.stack([mlp(self.relative_coords_table)[0] for mlp in self.cpb_mlps])
+
+    def forward(self, query, key, reference_point, reference_angle, xyz, attn_mask=None, key_padding_mask=None):
+        # query [nQ,B,D]  key [nK,B,D]  reference_point [B,nQ,8,3]  xyz [B,nK,3]
+        nQ, B, D = query.shape
+        H = self.num_heads
+        if self.interp_method != "bilinear":
+            raise NotImplementedError("only rpe_quant='bilinear_<max>_<n>' is implemented")
+        rotate = self.angle_type == "object_coords" and reference_angle is not None
+        tables = self.vertex_tables()
+        q = (self.q(query) * self.scale).reshape(nQ, B, H, D // H).transpose(0, 1)
+        k = self.k(key).transpose(0, 1).unsqueeze(2)
+        v = self.v(key).transpose(0, 1).unsqueeze(2)
+        ref = reference_point.detach().float()
+        ang = reference_angle.detach().float() if rotate else None
+        pts = xyz.detach().float()
+        fused = attn_mask is None and not self.need_weights and not (self.training and self.attn_drop.p > 0)
+        attn = None
+        if fused:
+            o = ops.rpe_attention(q, k, v, pts, ref, ang, tables, self.log_scale, self.max_value)
+        else:
+            bias = _RpeBiasFn.apply(pts, ref, ang, tables, self.log_scale, self.max_value)
+            if attn_mask is not None:
+                m = attn_mask.unsqueeze(1)
+                bias = bias.masked_fill(m, -100.0) if m.dtype == torch.bool else bias + m
+                # (the reference fills the *logits* with -100; filling the bias differs by q.k only where masked)
+            o, attn = _dense_attention(q, k, v, bias, self.attn_drop)
+        x = self.proj(o.transpose(0, 1).reshape(nQ, B, D))
+        return self.proj_drop(x), attn
+
+
+class _RpeBiasFn(torch.autograd.Function):
+    """Materialised bias with a table gradient (debug / mask / attention-dropout path only)."""
+
+    @staticmethod
+    def forward(ctx, xyz, ref, ang, tables, log_scale, max_value):
+        ctx.save_for_backward(xyz, ref, ang, tables)
+        ctx.meta = (log_scale, max_value)
+        return ops.rpe_bias(xyz.contiguous(), ref.contiguous(), tables.contiguous(),
+                            None if ang is None else ang.contiguous(), log_scale, max_value)
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz, ref, ang, tables = ctx.saved_tensors
+        return None, None, None, ops.rpe_bias_grad_tables(xyz, ref, ang, tables, g.contiguous(), *ctx.meta), None, None
+
+
+# ------------------------------------------------------------------------------------------------- layers
+class FFNLayer(nn.Module):
+    """Pre-norm feed forward block applied to the encoder tokens (:585-606)."""
+
+    def __init__(self, d_model, dim_feedforward=256, dropout=0.1, norm_fn_name="ln", activation="relu",
+                 normalize_before=True):
+        super().__init__()
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout, inplace=False)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm = NORM_DICT[norm_fn_name](d_model)
+        self.activation = ACTIVATION_DICT[activation]()
+        self.normalize_before = normalize_before
+
+    def forward_pre(self, memory):
+        memory = self.norm(memory)
+        return memory + self.dropout(self.linear2(self.dropout(self.activation(self.linear1(memory)))))
+
+    def forward(self, memory):
+        return self.forward_pre(memory)
+
+
+class GlobalDecoderLayer(nn.Module):
+    """Self attention over the queries, Vertex-RPE cross attention to the point tokens, FFN (:455-582)."""
+
+    def __init__(self, d_model, nhead=4, dim_feedforward=256, dropout=0.1, dropout_attn=None, activation="relu",
+                 normalize_before=True, norm_fn_name="ln", pos_for_key=False, args=None):
+        super().__init__()
+        if dropout_attn is None:
+            dropout_attn = dropout
+        self.pos_for_key = pos_for_key
+        if args.share_selfattn:
+            self.self_attn = ShareSelfAttention(d_model, nhead, dropout=dropout)
+        else:
+            self.self_attn = MultiheadSelfAttention(d_model, nhead, dropout=dropout)
+        self.multihead_attn = GlobalShareCrossAttention(d_model, nhead, attn_drop=dropout, proj_drop=dropout, args=args)
+        self.norm1 = NORM_DICT[norm_fn_name](d_model)
+        self.norm2 = NORM_DICT[norm_fn_name](d_model)
+        self.norm3 = NORM_DICT[norm_fn_name](d_model)
+        self.dropout1 = nn.Dropout(dropout, inplace=False)
+        self.dropout2 = nn.Dropout(dropout, inplace=False)
+        self.dropout3 = nn.Dropout(dropout, inplace=False)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout, inplace=False)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.activation = ACTIVATION_DICT[activation]()
+        self.normalize_before = normalize_before
+
+    @staticmethod
+    def with_pos_embed(tensor, pos: Optional[Tensor]):
+        return tensor if pos is None else tensor + pos
+
+    def _cross(self, tgt, memory, reference_point, reference_angle, enc_xyz, memory_mask, memory_key_padding_mask, pos,
+               query_pos):
+        key = self.with_pos_embed(memory, pos) if self.pos_for_key else memory
+        return self.multihead_attn(query=self.with_pos_embed(tgt, query_pos), key=key, reference_point=reference_point,
+                                   reference_angle=reference_angle, xyz=enc_xyz, attn_mask=memory_mask,
+                                   key_padding_mask=memory_key_padding_mask)
+
+    def forward_post(self, tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask=None,
+                     memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None,
+                     return_attn_weights=False):
+        qk = self.with_pos_embed(tgt, query_pos)
+        tgt = self.norm1(tgt + self.dropout1(self.self_attn(qk, qk, value=tgt, attn_mask=tgt_mask,
+                                                            key_padding_mask=tgt_key_padding_mask)[0]))
+        x, attn = self._cross(tgt, memory, reference_point, reference_angle, enc_xyz, memory_mask,
+                              memory_key_padding_mask, pos, query_pos)
+        tgt = self.norm2(tgt + self.dropout2(x))
+        tgt = self.norm3(tgt + self.dropout3(self.linear2(self.dropout(self.activation(self.linear1(tgt))))))
+        return (tgt, attn) if return_attn_weights else (tgt, None)
+
+    def forward_pre(self, tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask=None,
+                    memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None,
+                    return_attn_weights=False):
+        t2 = self.norm1(tgt)
+        qk = self.with_pos_embed(t2, query_pos)
+        tgt = tgt + self.dropout1(self.self_attn(qk, qk, value=t2, attn_mask=tgt_mask,
+                                                 key_padding_mask=tgt_key_padding_mask)[0])
+        t2 = self.norm2(tgt)
+        x, attn = self._cross(t2, memory, reference_point, reference_angle, enc_xyz, memory_mask,
+                              memory_key_padding_mask, pos, query_pos)
+        tgt = tgt + self.dropout2(x)
+        t2 = self.norm3(tgt)
+        tgt = tgt + self.dropout3(self.linear2(self.dropout(self.activation(self.linear1(t2)))))
+        return (tgt, attn) if return_attn_weights else (tgt, None)
+
+    def forward(self, tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask=None,
+                memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None,
+                return_attn_weights=False):
+        fn = self.forward_pre if self.normalize_before else self.forward_post
+        if return_attn_weights:
+            self.multihead_attn.need_weights = True
+        try:
+            return fn(tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask, memory_mask,
+                      tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos, return_attn_weights)
+        finally:
+            if return_attn_weights:
+                self.multihead_attn.need_weights = False
+
+
+class TransformerDecoder(nn.Module):
+    """Proposal stage on the encoder tokens + ``num_layers`` refinement layers with box heads (:105-452)."""
+
+    def __init__(self, first_layer, decoder_layer, dataset_config, num_layers, decoder_dim=256, mlp_dropout=0.3,
+                 mlp_norm="bn1d", mlp_act="relu", mlp_sep=False, pos_for_key=False, num_queries=256, cls_loss="celoss",
+                 norm_fn_name="ln", is_bilable=False, q_content="sample", return_intermediate=False,
+                 weight_init_name="xavier_uniform", args=None):
+        super().__init__()
+        self.first_layer = first_layer
+        self.layers = get_clones(decoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.dec_output_dim = self.layers[0].linear2.out_features
+        self.norm = NORM_DICT[norm_fn_name](self.dec_output_dim) if norm_fn_name is not None else None
+        self.is_bilable = is_bilable
+        self.pos_for_key = pos_for_key
+        self.num_queries = num_queries
+        self.q_content = q_content
+        self.query_pos_projection = nn.ModuleList(
+            [PositionEmbeddingLearned(6, self.dec_output_dim) for _ in range(num_layers)])
+        if pos_for_key:
+            self.key_pos_projection = nn.ModuleList(
+                [PositionEmbeddingLearned(3, self.dec_output_dim) for _ in range(num_layers)])
+        if q_content in ("random", "random_add"):
+            self.query_embed = nn.Embedding(num_queries, self.dec_output_dim)
+        self.return_intermediate = return_intermediate
+        self._reset_parameters(weight_init_name)
+        self.mlp_norm, self.mlp_act, self.mlp_sep, self.cls_loss = mlp_norm, mlp_act, mlp_sep, cls_loss
+        self.build_mlp_heads(dataset_config, decoder_dim, mlp_dropout)
+        self.build_pointcls_heads(dataset_config, decoder_dim, mlp_dropout)
+        head_sets = list(self.mlp_heads) if mlp_sep else [self.mlp_heads]
+        if cls_loss.split("_")[0] == "focalloss":
+            prior = -math.log((1 - 0.01) / 0.01)
+            for hs in head_sets:
+                last = hs["sem_cls_head"].layers[-1]
+                last.bias.data = torch.ones(last.bias.shape[0]) * prior
+        for hs in head_sets:
+            for name in ("center_head", "size_head"):
+                nn.init.constant_(hs[name].layers[-1].weight.data, 0.0)
+                nn.init.constant_(hs[name].layers[-1].bias.data, 0.0)
+        self.box_processor = BoxProcessor(dataset_config, cls_loss=cls_loss)
+        self.sort_keys = True       # Morton-order the key tokens once per forward (see module docstring)
+
+    def _head_factory(self, decoder_dim, mlp_dropout):
+        return partial(GenericMLP, norm_fn_name=self.mlp_norm, activation=self.mlp_act, use_conv=True,
+                       hidden_dims=[decoder_dim, decoder_dim], dropout=mlp_dropout, input_dim=decoder_dim)
+
+    def build_pointcls_heads(self, dataset_config, decoder_dim, mlp_dropout):
+        extra = 0 if self.cls_loss.split("_")[0] == "focalloss" else 1
+        self.pointcls_heads = self._head_factory(decoder_dim, mlp_dropout)(output_dim=dataset_config.num_semcls + extra)
+
+    def build_mlp_heads(self, dataset_config, decoder_dim, mlp_dropout):
+        mk = self._head_factory(decoder_dim, mlp_dropout)
+        extra = 0 if self.cls_loss.split("_")[0] == "focalloss" else 1
+        heads = [("sem_cls_head", mk(output_dim=dataset_config.num_semcls + extra)),
+                 ("center_head", mk(output_dim=3)), ("size_head", mk(output_dim=3)),
+                 ("angle_cls_head", mk(output_dim=dataset_config.num_angle_bin)),
+                 ("angle_residual_head", mk(output_dim=dataset_config.num_angle_bin))]
+        if not self.mlp_sep:
+            self.mlp_heads = nn.ModuleDict(heads)
+        elif self.is_bilable:
+            self.mlp_heads = get_clones(nn.ModuleDict(heads), self.num_layers)
+            first = copy.deepcopy(heads)
+            first[0] = ("sem_cls_head", mk(output_dim=1))
+            self.mlp_heads.insert(0, nn.ModuleDict(first))
+        else:
+            self.mlp_heads = get_clones(nn.ModuleDict(heads), self.num_layers + 1)
+
+    def _reset_parameters(self, weight_init_name):
+        init = WEIGHT_INIT_DICT[weight_init_name]
+        for _, p in self.named_parameters():
+            if p.dim() > 1:
+                init(p)
+
+    def get_proposal_box_predictions_refine(self, idx, query_xyz, point_cloud_dims, box_features,
+                                            pre_center_normalized=None, pre_size_normalized=None):
+        """box_features [nQ,B,C] -> dict of box predictions (:244-333)."""
+        assert pre_center_normalized is not None and pre_size_normalized is not None
+        feats = box_features.permute(1, 2, 0)
+        heads = self.mlp_heads[idx] if self.mlp_sep else self.mlp_heads
+        lo, hi = point_cloud_dims
+        scene = (hi - lo).unsqueeze(1)
+        origin = lo.unsqueeze(1)
+        cls_logits = heads["sem_cls_head"](feats).transpose(1, 2)
+        pre_center = pre_center_normalized * scene + origin
+        pre_size = pre_size_normalized * scene
+        center_reg = heads["center_head"](feats).transpose(1, 2).contiguous()
+        center = center_reg * pre_size + pre_center
+        center_norm = (center - origin) / scene
+        size_reg = heads["size_head"](feats).transpose(1, 2).contiguous()
+        size = torch.exp(size_reg) * pre_size
+        size_norm = size / scene
+        angle_logits = heads["angle_cls_head"](feats).transpose(1, 2)
+        angle_res_norm = heads["angle_residual_head"](feats).transpose(1, 2)
+        angle_res = angle_res_norm * (np.pi / angle_res_norm.shape[-1])
+        angle, angle_prob = self.box_processor.compute_predicted_angle(angle_logits, angle_res)
+        corners = self.box_processor.box_parametrization_to_corners(center, size, angle)
+        angle0, _ = self.box_processor.compute_predicted_angle(angle_logits, angle_res, zero_angle=True)
+        corners0 = self.box_processor.box_parametrization_to_corners(center, size, angle0)
+        with torch.no_grad():
+            semcls_prob, objectness = self.box_processor.compute_objectness_and_cls_prob(cls_logits)
+        return {"sem_cls_logits": cls_logits, "center_normalized": center_norm.contiguous(),
+                "center_unnormalized": center, "size_normalized": size_norm, "size_unnormalized": size,
+                "angle_logits": angle_logits, "angle_prob": angle_prob, "angle_residual": angle_res,
+                "angle_residual_normalized": angle_res_norm, "angle_continuous": angle,
+                "objectness_prob": objectness, "sem_cls_prob": semcls_prob, "box_corners": corners,
+                "box_corners_axis_align": corners0, "pre_box_center_unnormalized": pre_center,
+                "center_reg": center_reg, "pre_box_size_unnormalized": pre_size, "size_reg": size_reg}
+
+    def forward(self, tgt, memory, query_xyz, enc_xyz, point_cloud_dims, tgt_mask=None, memory_mask=None,
+                tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None, transpose_swap=False,
+                return_attn_weights=False, enc_box_predictions=None, enc_box_features=None):
+        preds, attns = [], []
+        output = self.first_layer(enc_box_features)
+        pred = self.get_proposal_box_predictions_refine(
+            0, query_xyz, point_cloud_dims, self.norm(output),
+            pre_center_normalized=enc_box_predictions["center_normalized"],
+            pre_size_normalized=enc_box_predictions["size_normalized"])
+        if self.return_intermediate:
+            preds.append(pred)
+        score = pred["objectness_prob"].clone().detach()
+        B, nprop = score.shape
+        if nprop >= self.num_queries:
+            top = torch.topk(score, self.num_queries, dim=1)[1]
+        else:
+            top = torch.arange(nprop, device=score.device).unsqueeze(0).repeat(B, 1)
+
+        def pick(t):
+            idx = top.reshape(top.shape + (1,) * (t.dim() - 2)).expand(top.shape + t.shape[2:])
+            return torch.gather(t.clone().detach(), 1, idx)
+        reference_point = convert_corners_camera2lidar(pick(pred["box_corners"]))
+        reference_center = pick(pred["center_unnormalized"])
+        query_xyz = reference_center.clone().detach()
+        reference_size = pick(pred["size_unnormalized"])
+        reference_angle = pick(pred["angle_continuous"])
+        proposal_center_normalized = pick(pred["center_normalized"])
+        proposal_size_normalized = pick(pred["size_normalized"])
+        output = torch.gather(output.permute(1, 0, 2), 1, top.unsqueeze(-1).expand(-1, -1, output.shape[-1])) \
+            .permute(1, 0, 2).contiguous()
+        if self.q_content == "zero":
+            output = torch.zeros_like(output)
+        elif self.q_content == "random":
+            output = self.query_embed.weight.unsqueeze(1).repeat(1, output.shape[1], 1)
+        elif self.q_content == "random_add":
+            output = output + self.query_embed.weight.unsqueeze(1).repeat(1, output.shape[1], 1)
+
+        # keys in Morton order for the cross-attention kernels (results are permutation invariant over keys)
+        mem_l, xyz_l, perm = memory, enc_xyz, None
+        if self.sort_keys and memory_mask is None and not return_attn_weights and not self.pos_for_key:
+            perm = morton_order(enc_xyz.detach())
+            xyz_l = torch.gather(enc_xyz, 1, perm.unsqueeze(-1).expand(-1, -1, 3))
+            mem_l = torch.gather(memory, 0, perm.t().unsqueeze(-1).expand(-1, -1, memory.shape[-1]))
+
+        for idx, layer in enumerate(self.layers):
+            if idx > 0:
+                reference_point = convert_corners_camera2lidar(pred["box_corners"].clone().detach())
+                reference_center = pred["center_unnormalized"].clone().detach()
+                reference_size = pred["size_unnormalized"].clone().detach()
+                reference_angle = pred["angle_continuous"].clone().detach()
+            query_reference = torch.cat([reference_center, reference_size], dim=-1)
+            qpos = self.query_pos_projection[idx](query_reference).permute(2, 0, 1)
+            if self.pos_for_key:
+                pos = self.key_pos_projection[idx](enc_xyz).permute(2, 0, 1)
+            output, attn = layer(output, mem_l, reference_point, reference_angle, xyz_l, point_cloud_dims,
+                                 tgt_mask=tgt_mask, memory_mask=memory_mask, tgt_key_padding_mask=tgt_key_padding_mask,
+                                 memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=qpos,
+                                 return_attn_weights=return_attn_weights)
+            pred = self.get_proposal_box_predictions_refine(
+                idx + 1, query_xyz, point_cloud_dims, self.norm(output),
+                pre_center_normalized=proposal_center_normalized, pre_size_normalized=proposal_size_normalized)
+            if self.return_intermediate:
+                preds.append(pred)
+            if return_attn_weights:
+                attns.append(attn)
+        if return_attn_weights:
+            attns = torch.stack(attns)
+        if self.return_intermediate:
+            return {"outputs": preds[-1], "aux_outputs": preds[:-1]}, attns
+        return {"outputs": pred}, attns
