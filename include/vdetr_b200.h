@@ -117,6 +117,13 @@ int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, co
 int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
                    const float* tables, float* rpe, void* stream);
 
+/* Optional per-kernel timing for benchmarks: when enabled, CUDA events are recorded on the launch stream
+ * around [0] the fused forward kernel, [1] the backward pass-1 kernel, [2] the dTables kernel (at most 512
+ * launches each between reads).  vdetr_timing_read synchronises on the recorded events, returns the summed
+ * device time in ms and the launch counts, and resets the counters. */
+int vdetr_timing_enable(int enable);
+int vdetr_timing_read(float* total_ms /*[3]*/, int* launches /*[3]*/);
+
 /* Adjoint of vdetr_rpe_bias w.r.t. the tables: dtables[8,n,n,n,H] = sum_{b,q,k} dbias[b,q,k,h] * w_corner
  * (what autograd of F.grid_sample returns for its input at vdetr_transformer.py:727-731).
  * dbias is given pair-major: [B,nQ,nK,H] f32.  dtables is fully overwritten. */

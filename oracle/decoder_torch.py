@@ -194,6 +194,27 @@ def rpe_bias_torch(ref_pts, xyz, tables, ref_angle=None, log_scale=512.0, max_va
     return out.permute(0, 3, 1, 2)
 
 
+def rpe_bias_grid_sample(ref_pts, xyz, tables, ref_angle=None, log_scale=512.0, max_value=4.0):
+    """Same quantity through F.grid_sample, the primitive the reference itself calls
+    (models/vdetr_transformer.py:725-731).  Used for the CPU baseline timing (it is what the reference's CPU
+    path executes); tests/test_oracle_golden.py checks that it agrees with the explicit gather above."""
+    B, nQ = ref_pts.shape[:2]
+    nK = xyz.shape[1]
+    out = None
+    for i in range(8):
+        d = ref_pts[:, :, None, i, :] - xyz[:, None, :, :]
+        if ref_angle is not None:
+            c = torch.cos(ref_angle)[:, :, None]
+            s = torch.sin(ref_angle)[:, :, None]
+            d = torch.stack([c * d[..., 0] - s * d[..., 1], s * d[..., 0] + c * d[..., 1], d[..., 2]], -1)
+        g = torch.sign(d) * torch.log2(d.abs() * log_scale + 1.0) / 3.0 / max_value
+        tab = tables[i].permute(3, 0, 1, 2).unsqueeze(0)                              # [1,H,n,n,n]
+        r = F.grid_sample(tab, g.reshape(1, 1, 1, -1, 3), mode="bilinear", padding_mode="zeros", align_corners=False)
+        r = r.reshape(-1, B, nQ, nK).permute(1, 0, 2, 3)
+        out = r if out is None else out + r
+    return out
+
+
 class OracleVertexRPECrossAttention(nn.Module):
     """GlobalShareCrossAttention (models/vdetr_transformer.py:656-758)."""
 
@@ -217,6 +238,7 @@ class OracleVertexRPECrossAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
+        self.use_grid_sample = False
 
     def tables(self):
         return torch.stack([m(self.relative_coords_table)[0] for m in self.cpb_mlps])     # [8,N,N,N,H]
@@ -225,7 +247,8 @@ class OracleVertexRPECrossAttention(nn.Module):
         nQ, B, D = query.shape
         H = self.num_heads
         ang = reference_angle if (self.angle_type == "object_coords" and reference_angle is not None) else None
-        bias = rpe_bias_torch(reference_point, xyz, self.tables(), ang, self.log_scale, self.max_value)
+        fn = rpe_bias_grid_sample if self.use_grid_sample else rpe_bias_torch
+        bias = fn(reference_point, xyz, self.tables(), ang, self.log_scale, self.max_value)
         q = self.q(query).view(nQ, B, H, D // H).permute(1, 2, 0, 3) * self.scale
         k = self.k(key).permute(1, 0, 2).unsqueeze(1)
         v = self.v(key).permute(1, 0, 2).unsqueeze(1)

@@ -1,0 +1,118 @@
+"""Decoder-level GPU parity: the drop-in TransformerDecoder (vdetr_b200.vdetr_transformer) against
+  (1) golden vectors of the UNMODIFIED reference decoder (tests/golden/decoder_*.npz), and
+  (2) the CPU oracle port at a larger, ragged size, forward and backward.
+Weights come from tests/golden/recipe.py, so all three implementations hold the same state_dict."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import recipe
+from oracle import decoder_torch as odt
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+KEYS = ("sem_cls_logits", "center_normalized", "size_normalized", "angle_logits", "angle_residual_normalized",
+        "center_unnormalized", "size_unnormalized", "box_corners")
+
+
+def build_product_decoder(L, nq, dropout=0.1, mlp_dropout=0.3, share=False):
+    from vdetr_b200 import vdetr_transformer as vt
+    args = types.SimpleNamespace(log_scale=512.0, rpe_quant="bilinear_4_10", angle_type="", rpe_dim=128, share_selfattn=share)
+    first = vt.FFNLayer(d_model=256, dim_feedforward=256, dropout=dropout)
+    layer = vt.GlobalDecoderLayer(d_model=256, nhead=4, dim_feedforward=256, dropout=dropout, pos_for_key=False, args=args)
+    return vt.TransformerDecoder(first, layer, vt.ScanNetBoxConfig(), num_layers=L, decoder_dim=256, mlp_dropout=mlp_dropout,
+                                 mlp_norm="bn1d", mlp_act="relu", mlp_sep=True, pos_for_key=False, num_queries=nq,
+                                 cls_loss="focalloss_0.25", is_bilable=True, q_content="random", return_intermediate=True,
+                                 args=args)
+
+
+def _load(dec, seed):
+    sd = dec.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    for k, v in recipe.fill_state_dict(shapes, seed).items():
+        if v is not None:
+            sd[k] = torch.from_numpy(v)
+    dec.load_state_dict(sd)
+    return shapes
+
+
+def _run_product(dec, c, train):
+    dev = "cuda"
+    feat = torch.from_numpy(c["feat"]).to(dev).requires_grad_(train)
+    xyz = torch.from_numpy(c["xyz"]).to(dev)
+    dims = [torch.from_numpy(c["mins"]).to(dev), torch.from_numpy(c["maxs"]).to(dev)]
+    encp = {"center_normalized": torch.from_numpy(c["center_normalized"]).to(dev),
+            "size_normalized": torch.from_numpy(c["size_normalized"]).to(dev)}
+    with torch.set_grad_enabled(train):
+        out, _ = dec(None, feat, xyz, xyz, dims, query_pos=None, enc_box_predictions=encp, enc_box_features=feat)
+    return out, feat
+
+
+@pytest.mark.parametrize("name,seed,B,nK,nq,L,share", [("decoder_eval", 31, 2, 96, 32, 2, False),
+                                                       ("decoder_share_eval", 51, 1, 64, 16, 1, True)])
+def test_product_decoder_matches_reference_golden(name, seed, B, nK, nq, L, share):
+    gold = dict(np.load(os.path.join(G, name + ".npz")))
+    dec = build_product_decoder(L, nq, share=share)
+    shapes = _load(dec, seed)
+    assert sorted(shapes) == list(gold["shapes_keys"])                      # same state_dict surface as the reference
+    assert [str(shapes[k]) for k in sorted(shapes)] == list(gold["shapes_vals"])
+    dec = dec.cuda().eval()
+    out, _ = _run_product(dec, recipe.decoder_case(seed + 1, B, nK), False)
+    for li, d in enumerate(out["aux_outputs"] + [out["outputs"]]):
+        for k in KEYS:
+            want = gold[f"l{li}.{k}"]
+            got = d[k].float().cpu().numpy()
+            tol = 3e-3 * (np.abs(want).max() + 1e-6)                        # 3e-3 of the tensor's max (fp16 operands)
+            assert np.abs(got - want).max() <= tol, f"layer {li} {k}: {np.abs(got - want).max():.3e} > {tol:.3e}"
+
+
+def test_product_decoder_train_matches_reference_golden_gradients():
+    gold = dict(np.load(os.path.join(G, "decoder_train.npz")))
+    dec = build_product_decoder(2, 32, dropout=0.0, mlp_dropout=0.0)
+    _load(dec, 41)
+    dec = dec.cuda().train()
+    out, feat = _run_product(dec, recipe.decoder_case(42, 2, 96), True)
+    loss = odt.synthetic_loss(out)
+    loss.backward()
+    assert abs(loss.item() - float(gold["loss"])) <= 3e-3 * abs(float(gold["loss"])) + 1e-2
+    g = feat.grad.cpu().numpy()
+    assert np.abs(g - gold["dfeat"]).max() <= 2e-2 * np.abs(gold["dfeat"]).max()
+    for n, p in dec.named_parameters():
+        key = "grad." + n
+        if key in gold:
+            got = p.grad.cpu().numpy()
+            got = got[::16] if got.ndim == 2 and got.shape[0] > 64 else got
+            want = gold[key]
+            assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max() + 1e-6, n
+
+
+def test_product_decoder_vs_oracle_port_c1_size():
+    """BASELINE config C1 (512 keys x 128 queries x 1 layer) plus a ragged variant, product (GPU) vs oracle (CPU)."""
+    for (B, nK, nq, L, seed) in [(1, 512, 128, 1, 7), (2, 333, 70, 2, 9)]:
+        torch.manual_seed(0)
+        ora = odt.OracleDecoder(num_layers=L, num_queries=nq).eval()
+        shapes = {k: tuple(v.shape) for k, v in ora.state_dict().items()}
+        vals = recipe.fill_state_dict(shapes, seed)
+        sd = ora.state_dict()
+        for k, v in vals.items():
+            if v is not None:
+                sd[k] = torch.from_numpy(v)
+        ora.load_state_dict(sd)
+        dec = build_product_decoder(L, nq)
+        dec.load_state_dict(sd)
+        dec = dec.cuda().eval()
+        c = recipe.decoder_case(seed + 1, B, nK)
+        with torch.no_grad():
+            want, _ = ora(torch.from_numpy(c["feat"]), torch.from_numpy(c["xyz"]),
+                          [torch.from_numpy(c["mins"]), torch.from_numpy(c["maxs"])],
+                          torch.from_numpy(c["center_normalized"]), torch.from_numpy(c["size_normalized"]))
+        got, _ = _run_product(dec, c, False)
+        for li, (dg, dw) in enumerate(zip(got["aux_outputs"] + [got["outputs"]], want["aux_outputs"] + [want["outputs"]])):
+            for k in KEYS:
+                w = dw[k].numpy()
+                gg = dg[k].float().cpu().numpy()
+                tol = 3e-3 * (np.abs(w).max() + 1e-6)
+                assert np.abs(gg - w).max() <= tol, f"B{B} layer {li} {k}: {np.abs(gg - w).max():.3e} > {tol:.3e}"

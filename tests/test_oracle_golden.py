@@ -127,3 +127,15 @@ def test_torch_port_matches_reference_decoder(name, seed, B, nK, nq, L, train, s
                 g = p.grad.numpy()
                 g = g[::16] if g.ndim == 2 and g.shape[0] > 64 else g
                 np.testing.assert_allclose(g, gold[key], rtol=5e-3, atol=5e-4, err_msg=n)
+
+
+def test_grid_sample_variant_agrees_with_explicit_gather():
+    torch.manual_seed(3)
+    tables = torch.randn(8, 10, 10, 10, 4)
+    c = recipe.xattn_case(77, 2, 9, 31, True, 0.3)
+    ref = torch.from_numpy(ora.box_vertices(c["center"], c["size"]))
+    xyz, ang = torch.from_numpy(c["xyz"]), torch.from_numpy(c["angle"])
+    for a in (None, ang):
+        x = odt.rpe_bias_torch(ref, xyz, tables, a)
+        y = odt.rpe_bias_grid_sample(ref, xyz, tables, a)
+        torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-5)

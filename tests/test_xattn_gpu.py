@@ -100,14 +100,20 @@ def test_bias_kernel_matches_numpy_oracle_and_reference_golden():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Product kernels (impl = 0: tcgen05 + TMA, bf16 tensor-core operands, fp32 bias / softmax / accumulation).
-# Tolerance: bf16 operands carry 2^-9 relative rounding; against the fp64 oracle the attention output is
-# checked to 6e-3 of the tensor's max (north_star's 1e-3 is met by the fp32 validation kernels above; the
-# bf16 figure is what BASELINE.json's bf16 configs imply) and against the oracle evaluated on bf16-rounded
-# operands to 2e-3.
+# Product kernels (impl = 0: tcgen05 + TMA, fp32 bias / softmax / accumulation).  The S = QK^T and O = PV
+# products use FP16 tensor-core operands (2^-12 relative rounding, 8x tighter than the BF16 the configs name,
+# same cost); operands that carry gradients are BF16.  Tolerances, as a fraction of the tensor's max:
+#   forward  vs the oracle evaluated on fp16-rounded q/k/v : 1e-3   (what the kernel itself adds)
+#   forward  vs the fp64 oracle on the original fp32 inputs : 4e-3   (includes the fp16 rounding of the inputs at
+#            this deliberately harsh logit scale, |S| ~ 4; at the decoder's real scale see test_decoder_gpu.py)
+#   backward vs the oracle on bf16-rounded inputs           : 1e-2   (bf16 P / dS in the gradient GEMMs)
 # ---------------------------------------------------------------------------------------------------------
 def _bf16_round(a):
     return torch.from_numpy(a).bfloat16().float().numpy()
+
+
+def _fp16_round(a):
+    return torch.from_numpy(a).half().float().numpy()
 
 
 TC_FWD_CASES = [(11, 1, 32, 64, 1, False), (12, 2, 24, 80, 1, False), (13, 1, 16, 48, 1, True), (14, 2, 70, 333, 1, False),
@@ -120,7 +126,7 @@ def test_tc_forward_matches_oracle(seed, B, nQ, nK, kvh, rot):
     has_bias = kvh == 1
     I = _core_inputs(seed, B, nQ, nK, kvh, rot)
     want = _oracle(I, has_bias)
-    Ib = dict(I, q=_bf16_round(I["q"]), k=_bf16_round(I["k"]), v=_bf16_round(I["v"]))
+    Ib = dict(I, q=_fp16_round(I["q"]), k=_fp16_round(I["k"]), v=_fp16_round(I["v"]))
     want_b = _oracle(Ib, has_bias)
     t = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in I.items()}
     with torch.no_grad():
@@ -131,9 +137,9 @@ def test_tc_forward_matches_oracle(seed, B, nQ, nK, kvh, rot):
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     assert np.isfinite(got).all()
-    _cmp(got, want_b["o"], 2e-3, 1e-4, "out vs oracle on bf16-rounded operands")
-    _cmp(got, want["o"], 6e-3, 1e-4, "out vs fp64 oracle")
-    _cmp(got, ref_simt.cpu().numpy(), 6e-3, 1e-4, "out vs SIMT kernel")
+    _cmp(got, want_b["o"], 1e-3, 1e-5, "out vs oracle on fp16-rounded operands")
+    _cmp(got, want["o"], 4e-3, 1e-5, "out vs fp64 oracle")
+    _cmp(got, ref_simt.cpu().numpy(), 4e-3, 1e-5, "out vs SIMT kernel")
 
 
 TC_BWD_CASES = [(21, 1, 32, 64, 1, False), (22, 2, 24, 80, 1, False), (23, 1, 16, 48, 1, True), (24, 2, 70, 333, 1, False),

@@ -2,7 +2,59 @@
 #include "common.cuh"
 #include "rpe_internal.h"
 
+namespace {
+constexpr int TIMING_RING = 512;
+struct TimingState {
+  bool enabled = false;
+  cudaEvent_t start[VDETR_T_COUNT][TIMING_RING];
+  cudaEvent_t stop[VDETR_T_COUNT][TIMING_RING];
+  int n[VDETR_T_COUNT] = {0, 0, 0};
+  bool created = false;
+} g_timing;
+}  // namespace
+
+VdetrTimingScope::VdetrTimingScope(int k, cudaStream_t s) : kind(k), st(s), stop(nullptr), on(false) {
+  if (k < 0 || k >= VDETR_T_COUNT || !g_timing.enabled || g_timing.n[k] >= TIMING_RING) return;
+  const int i = g_timing.n[k]++;
+  cudaEventRecord(g_timing.start[k][i], st);
+  stop = g_timing.stop[k][i];
+  on = true;
+}
+VdetrTimingScope::~VdetrTimingScope() {
+  if (on) cudaEventRecord(stop, st);
+}
+
 extern "C" {
+
+int vdetr_timing_enable(int enable) {
+  if (enable && !g_timing.created) {
+    for (int k = 0; k < VDETR_T_COUNT; ++k)
+      for (int i = 0; i < TIMING_RING; ++i) {
+        VDETR_CUDA_TRY(cudaEventCreate(&g_timing.start[k][i]));
+        VDETR_CUDA_TRY(cudaEventCreate(&g_timing.stop[k][i]));
+      }
+    g_timing.created = true;
+  }
+  g_timing.enabled = enable != 0;
+  for (int k = 0; k < VDETR_T_COUNT; ++k) g_timing.n[k] = 0;
+  return 0;
+}
+
+int vdetr_timing_read(float* total_ms /*[3]*/, int* launches /*[3]*/) {
+  for (int k = 0; k < VDETR_T_COUNT; ++k) {
+    float sum = 0.f;
+    for (int i = 0; i < g_timing.n[k]; ++i) {
+      VDETR_CUDA_TRY(cudaEventSynchronize(g_timing.stop[k][i]));
+      float ms = 0.f;
+      VDETR_CUDA_TRY(cudaEventElapsedTime(&ms, g_timing.start[k][i], g_timing.stop[k][i]));
+      sum += ms;
+    }
+    total_ms[k] = sum;
+    launches[k] = g_timing.n[k];
+    g_timing.n[k] = 0;
+  }
+  return 0;
+}
 
 const char* vdetr_version(void) { return "vdetr_b200 0.1 sm_100a"; }
 

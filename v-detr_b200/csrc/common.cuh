@@ -28,3 +28,16 @@ static inline int vdetr_num_sms() {
   }
   return n;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Optional kernel timing (bench.py): CUDA events recorded on the launch stream around the three dominant
+// kernels.  Disabled by default; enabling costs two cudaEventRecord per launch.
+enum VdetrTimedKernel { VDETR_T_FWD = 0, VDETR_T_BWD = 1, VDETR_T_DTABLES = 2, VDETR_T_COUNT = 3 };
+struct VdetrTimingScope {
+  int kind;
+  cudaStream_t st;
+  cudaEvent_t stop;
+  bool on;
+  VdetrTimingScope(int kind, cudaStream_t st);
+  ~VdetrTimingScope();
+};

@@ -144,7 +144,10 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   const long tasks = (long)s->B * s->nQ * 8;
   long want = (tasks + DT_WARPS - 1) / DT_WARPS;
   int grid = (int)(want < vdetr_num_sms() ? want : vdetr_num_sms());
-  rpe_dtables_kernel<<<grid, DT_THREADS, smem, st>>>(P);
+  {
+    VdetrTimingScope timing(VDETR_T_DTABLES, st);
+    rpe_dtables_kernel<<<grid, DT_THREADS, smem, st>>>(P);
+  }
   VDETR_LAUNCH_CHECK();
   return 0;
 }

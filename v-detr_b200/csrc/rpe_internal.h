@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "../../include/vdetr_b200.h"
 
 int vdetr_check_shape(const VdetrXattnShape* s);
@@ -33,10 +34,14 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
 //   vtp  bf16 [B][kvh][64][nKp]   (V transposed: keys contiguous)
 //   xyz4 f32  [B][nKp] float4
 //   geo  f32  [B][nQp][9] float4: (x+,y+,z+,fast flag) (x-,y-,z-,0) 24 vertex floats (cos,sin,0,0)
+// Precision plan: the S = Q K^T and O = P V tensor-core products use FP16 operands (11-bit significand: 8x
+// tighter than BF16 at the same cost, and q/k/v/p are O(1) so range is no concern); everything that carries
+// gradients (dO, dS, and the copies of Q/K/V/P that meet them in a GEMM) is BF16.
 struct VdetrPack {
   int B, nQ, nK, nQp, nKp, kvh, has_bias;
   const float *q, *k, *v, *xyz, *ref, *ang, *dout;
-  __nv_bfloat16 *qp, *kp, *vtp, *vp, *dop;
+  __half *qp, *kp, *vtp;                 // fp16: forward operands (and the S recompute of the backward)
+  __nv_bfloat16 *qpb, *kpb, *vp, *dop;   // bf16: backward GEMM operands (null in the forward)
   float4* xyz4;
   float4* geo;
 };

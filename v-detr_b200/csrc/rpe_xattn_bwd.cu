@@ -105,7 +105,8 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS0 = tmem_base, tdP0 = tmem_base + 128;
-  const uint32_t idesc = umma_idesc_bf16(BM, BN);
+  const uint32_t idesc_s = umma_idesc_f16(BM, BN);     // S  = Q K^T : fp16 operands, exactly as the forward
+  const uint32_t idesc_d = umma_idesc_bf16(BM, BN);    // dP = dO V^T: bf16 operands (gradients need the range)
 
   uint32_t g = 0, it = 0;
   for (int item = blockIdx.x; item < P.items; item += gridDim.x, ++it) {
@@ -144,10 +145,10 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t ddo = umma_desc_sw128(smem_u32(sdO)), dv = umma_desc_sw128(smem_u32(sV));
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk)
-            umma_bf16(tS0 + (gj & 1) * BN, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc, kk > 0);
+            umma_bf16(tS0 + (gj & 1) * BN, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk > 0);
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk)
-            umma_bf16(tdP0 + (gj & 1) * BN, ddo + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc, kk > 0);
+            umma_bf16(tdP0 + (gj & 1) * BN, ddo + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_d, kk > 0);
           umma_commit(bar_s + (gj & 1));
           umma_commit(bar_kfree);
         }
@@ -283,7 +284,7 @@ __global__ void bwd_unpack_kernel(UnpackParams U) {
 
 struct BwdPlan {
   int nQp, nKp, mtiles, splits, tiles_per_split, items;
-  size_t off_qp, off_dop, off_kp, off_vp, off_vtp, off_xyz, off_geo, off_pb, off_dsb, off_ds4, off_dqp, off_dkp, off_dvp, total;
+  size_t off_qp, off_qpb, off_dop, off_kp, off_kpb, off_vp, off_vtp, off_xyz, off_geo, off_pb, off_dsb, off_ds4, off_dqp, off_dkp, off_dvp, total;
 };
 BwdPlan make_plan(const VdetrXattnShape* s) {
   BwdPlan p;
@@ -313,8 +314,10 @@ BwdPlan make_plan(const VdetrXattnShape* s) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += vdetr_align_up(bytes, 1024); return r; };
   p.off_qp = take(rows * 64 * 2);
+  p.off_qpb = take(rows * 64 * 2);
   p.off_dop = take(rows * 64 * 2);
   p.off_kp = take(krows * 64 * 2);
+  p.off_kpb = take(krows * 64 * 2);
   p.off_vp = take(krows * 64 * 2);
   p.off_vtp = take(krows * 64 * 2);
   p.off_xyz = take(s->has_bias ? (size_t)s->B * p.nKp * 16 : 0);
@@ -367,11 +370,13 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   VdetrPack pk = {};
   pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = pl.nQp; pk.nKp = pl.nKp; pk.kvh = s->kv_heads; pk.has_bias = s->has_bias;
   pk.q = q; pk.k = k; pk.v = v; pk.xyz = xyz; pk.ref = ref; pk.ang = (s->has_bias && s->rotate) ? ang : nullptr; pk.dout = dout;
-  pk.qp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_qp);
+  pk.qp = reinterpret_cast<__half*>(w + pl.off_qp);
+  pk.qpb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_qpb);
   pk.dop = reinterpret_cast<__nv_bfloat16*>(w + pl.off_dop);
-  pk.kp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_kp);
+  pk.kp = reinterpret_cast<__half*>(w + pl.off_kp);
+  pk.kpb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_kpb);
   pk.vp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_vp);
-  pk.vtp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_vtp);
+  pk.vtp = reinterpret_cast<__half*>(w + pl.off_vtp);
   pk.xyz4 = reinterpret_cast<float4*>(w + pl.off_xyz);
   pk.geo = reinterpret_cast<float4*>(w + pl.off_geo);
   vdetr_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(pk);
@@ -380,9 +385,9 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   const uint64_t rows = (uint64_t)s->B * pl.nQp * 4, krows = (uint64_t)s->B * s->kv_heads * pl.nKp;
   CUtensorMap tmQ, tmdO, tmK, tmV;
   int rc;
-  if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, rows, BM))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, rows, BM, true))) return rc;
   if ((rc = vdetr_make_tmap_bf16_rows64(&tmdO, pk.dop, rows, BM))) return rc;
-  if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, krows, BN))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, krows, BN, true))) return rc;
   if ((rc = vdetr_make_tmap_bf16_rows64(&tmV, pk.vp, krows, BN))) return rc;
 
   BwdParams P = {};
@@ -403,6 +408,8 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   if (L.total + 1024 > 232448) return VDETR_ERR_UNSUPPORTED;
   const size_t smem = L.total + 1024;
   const int grid = pl.items < vdetr_num_sms() ? pl.items : vdetr_num_sms();
+  {
+  VdetrTimingScope timing(s->has_bias ? VDETR_T_BWD : VDETR_T_COUNT, st);
   if (s->has_bias) {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rpe_xattn_bwd_kernel<true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
@@ -412,6 +419,7 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   } else {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rpe_xattn_bwd_kernel<false, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
+  }
   }
   VDETR_LAUNCH_CHECK();
 
@@ -425,8 +433,8 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   const int batch = mqa ? s->B : s->B * 4;
   const int rpb = mqa ? pl.nQp * 4 : pl.nQp;              // attention rows per batch entry
   const long long sRows = (long long)rpb * pl.nKp, sRow64 = (long long)rpb * 64, sK64 = (long long)pl.nKp * 64;
-  if ((rc = gemm_rm(hnd, false, false, rpb, 64, pl.nKp, P.dsb, pl.nKp, sRows, pk.kp, 64, sK64, dqp, 64, sRow64, batch))) return rc;
-  if ((rc = gemm_rm(hnd, true, false, pl.nKp, 64, rpb, P.dsb, pl.nKp, sRows, pk.qp, 64, sRow64, dkp, 64, sK64, batch))) return rc;
+  if ((rc = gemm_rm(hnd, false, false, rpb, 64, pl.nKp, P.dsb, pl.nKp, sRows, pk.kpb, 64, sK64, dqp, 64, sRow64, batch))) return rc;
+  if ((rc = gemm_rm(hnd, true, false, pl.nKp, 64, rpb, P.dsb, pl.nKp, sRows, pk.qpb, 64, sRow64, dkp, 64, sK64, batch))) return rc;
   if ((rc = gemm_rm(hnd, true, false, pl.nKp, 64, rpb, P.pb, pl.nKp, sRows, pk.dop, 64, sRow64, dvp, 64, sK64, batch))) return rc;
   UnpackParams U = {s->B, s->nQ, s->nK, pl.nQp, pl.nKp, s->kv_heads, dqp, dkp, dvp, dq, dk, dv};
   bwd_unpack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(U);

@@ -7,7 +7,7 @@
 //     32 queries x 4 heads and ONE geometry evaluation per (query, key) pair feeds all four heads (float4 cell);
 //   * MHA (decoder self attention): 128 queries of one head, no bias.
 // Per 64-key tile:
-//   TMA      K tile [64 x 64] bf16 (128B swizzle), V^T tile [64 d x 64 keys], key xyz (1-D bulk copy)
+//   TMA      K tile [64 x 64] fp16 (128B swizzle), V^T tile [64 d x 64 keys], key xyz (1-D bulk copy)
 //   tcgen05  S = Q K^T  -> TMEM (double buffered), issued one tile ahead by the control warp
 //   CUDA     all 16 compute warps: Vertex-RPE bias of the 32 x 64 (query,key) pairs (lanes = 32 consecutive
 //            keys, so table reads broadcast), staged through shared memory;
@@ -125,8 +125,8 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS0 = tmem_base, tO = tmem_base + 128;
 
-  const uint32_t idesc_s = umma_idesc_bf16(BM, BN);
-  const uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+  const uint32_t idesc_s = umma_idesc_f16(BM, BN);
+  const uint32_t idesc_o = umma_idesc_f16(BM, HD);
 
   uint32_t g = 0;          // tiles processed by this CTA so far (phase bookkeeping)
   uint32_t it = 0;         // items processed by this CTA so far
@@ -262,10 +262,10 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
           const float p0 = ex2_approx(x[c] - m_use), p1 = ex2_approx(x[c + 1] - m_use);
-          pk[c >> 1] = pack_bf16x2(p0, p1);
-          // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
-          const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&pk[c >> 1]);
-          psum += __bfloat162float(rb.x) + __bfloat162float(rb.y);
+          pk[c >> 1] = pack_f16x2(p0, p1);
+          // accumulate the row sum from the fp16-rounded values that the PV MMA will actually use
+          const float2 rb = __half22float2(*reinterpret_cast<const __half2*>(&pk[c >> 1]));
+          psum += rb.x + rb.y;
         }
         l_run = l_run * alpha + psum;
         m_run = m_new;
@@ -392,7 +392,8 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       else { q = (int)(r % K.nQp); h = (int)((r / K.nQp) & 3); b = (int)(r / ((size_t)K.nQp * 4)); }
       float val = 0.f;
       if (q < K.nQ) val = K.q[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
-      K.qp[i] = __float2bfloat16_rn(val);
+      K.qp[i] = __float2half_rn(val);
+      if (K.qpb) K.qpb[i] = __float2bfloat16_rn(val);
       if (K.dout) {
         float dv = 0.f;
         if (q < K.nQ) dv = K.dout[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
@@ -406,7 +407,8 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       const int hk = (int)((r / K.nKp) % K.kvh), b = (int)(r / ((size_t)K.nKp * K.kvh));
       float val = 0.f;
       if (key < K.nK) val = K.k[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-      K.kp[e] = __float2bfloat16_rn(val);
+      K.kp[e] = __float2half_rn(val);
+      if (K.kpb) K.kpb[e] = __float2bfloat16_rn(val);
       if (K.vp) {                                            // row-major V as well (backward: dP = dO V^T)
         float vv = 0.f;
         if (key < K.nK) vv = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
@@ -420,7 +422,7 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       const int hk = (int)((r >> 6) % K.kvh), b = (int)((r >> 6) / K.kvh);
       float val = 0.f;
       if (key < K.nK) val = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-      K.vtp[e] = __float2bfloat16_rn(val);
+      K.vtp[e] = __float2half_rn(val);
     } else if (i < nq + 2 * nk + nx) {
       const size_t e = i - nq - 2 * nk;
       const int key = (int)(e % K.nKp), b = (int)(e / K.nKp);
@@ -524,9 +526,9 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   VdetrPack pk = {};
   pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = pl.nQp; pk.nKp = pl.nKp; pk.kvh = s->kv_heads; pk.has_bias = s->has_bias;
   pk.q = q; pk.k = k; pk.v = v; pk.xyz = xyz; pk.ref = ref; pk.ang = (s->has_bias && s->rotate) ? ang : nullptr;
-  pk.qp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_qp);
-  pk.kp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_kp);
-  pk.vtp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_vtp);
+  pk.qp = reinterpret_cast<__half*>(w + pl.off_qp);
+  pk.kp = reinterpret_cast<__half*>(w + pl.off_kp);
+  pk.vtp = reinterpret_cast<__half*>(w + pl.off_vtp);
   pk.xyz4 = reinterpret_cast<float4*>(w + pl.off_xyz);
   pk.geo = reinterpret_cast<float4*>(w + pl.off_geo);
   vdetr_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(pk);
@@ -534,9 +536,9 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
 
   CUtensorMap tmQ, tmK, tmVt;
   int rc;
-  if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, (uint64_t)s->B * pl.nQp * 4, BM))) return rc;
-  if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, (uint64_t)s->B * s->kv_heads * pl.nKp, BN))) return rc;
-  if ((rc = vdetr_make_tmap_bf16_2d(&tmVt, pk.vtp, (uint64_t)s->B * s->kv_heads * HD, (uint64_t)pl.nKp, HD))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, (uint64_t)s->B * pl.nQp * 4, BM, true))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, (uint64_t)s->B * s->kv_heads * pl.nKp, BN, true))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_2d(&tmVt, pk.vtp, (uint64_t)s->B * s->kv_heads * HD, (uint64_t)pl.nKp, HD, true))) return rc;
 
   FwdParams P = {};
   P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = pl.nQp; P.nKp = pl.nKp; P.kvh = s->kv_heads;
@@ -555,6 +557,7 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   if (L.total + 1024 > 232448) return VDETR_ERR_UNSUPPORTED;
   const size_t smem = L.total + 1024;     // slack for the manual 1024-B alignment
   const int grid = pl.items < vdetr_num_sms() ? pl.items : vdetr_num_sms();
+  VdetrTimingScope timing(s->has_bias ? VDETR_T_FWD : VDETR_T_COUNT, st);
   if (s->has_bias) {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rpe_xattn_fwd_kernel<true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);

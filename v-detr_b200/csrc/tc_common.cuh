@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace tc {
@@ -119,6 +120,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17)    // n_dim
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
+// Same for FP16 x FP16 -> F32 (format code 0).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -134,6 +139,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float lg2_approx(float x) {
@@ -167,27 +176,29 @@ static inline PFN_tmapEncodeTiled vdetr_get_tmap_encoder() {
 }
 
 // bf16 matrix [rows, 64] row-major (128 B rows), box = [box_rows x 64], 128-B swizzle, OOB rows -> zeros
-static inline int vdetr_make_tmap_bf16_rows64(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+static inline int vdetr_make_tmap_bf16_rows64(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows,
+                                              bool fp16 = false) {
   PFN_tmapEncodeTiled enc = vdetr_get_tmap_encoder();
   if (!enc) return VDETR_ERR_NO_DRIVER;
   cuuint64_t dims[2] = {64, rows};
   cuuint64_t strides[1] = {128};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : VDETR_ERR_BAD_ARG;
 }
 // bf16 matrix [rows, cols] row-major (cols*2 B rows, cols % 8 == 0), box = [box_rows x 64 cols]
-static inline int vdetr_make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static inline int vdetr_make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                          bool fp16 = false) {
   PFN_tmapEncodeTiled enc = vdetr_get_tmap_encoder();
   if (!enc) return VDETR_ERR_NO_DRIVER;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : VDETR_ERR_BAD_ARG;
