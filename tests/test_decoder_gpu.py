@@ -13,6 +13,18 @@ import recipe
 from oracle import decoder_torch as odt
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    """The decoder picks its queries with a top-k over proposal scores: the 1e-3 noise of TF32 convolutions
+    (cuDNN's default) is enough to swap near-tied proposals and thereby permute the per-query outputs, so the
+    PyTorch layers around the kernels run in true fp32 here."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 G = os.path.join(os.path.dirname(__file__), "golden")
 KEYS = ("sem_cls_logits", "center_normalized", "size_normalized", "angle_logits", "angle_residual_normalized",
         "center_unnormalized", "size_unnormalized", "box_corners")

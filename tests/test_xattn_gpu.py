@@ -150,10 +150,10 @@ TC_BWD_CASES = [(21, 1, 32, 64, 1, False), (22, 2, 24, 80, 1, False), (23, 1, 16
 def test_tc_backward_matches_oracle(seed, B, nQ, nK, kvh, rot):
     has_bias = kvh == 1
     I = _core_inputs(seed, B, nQ, nK, kvh, rot)
-    Ib = dict(I, q=_bf16_round(I["q"]), k=_bf16_round(I["k"]), v=_bf16_round(I["v"]), do=_bf16_round(I["do"]))
+    Ib = dict(I, q=_fp16_round(I["q"]), k=_fp16_round(I["k"]), v=_fp16_round(I["v"]), do=_bf16_round(I["do"]))
     want = _oracle(Ib, has_bias)
     got = _run(I, impl=0, has_bias=has_bias)
-    for name, tol in (("o", 3e-3), ("dq", 1e-2), ("dk", 1e-2), ("dv", 1e-2)):
+    for name, tol in (("o", 1e-3), ("dq", 1e-2), ("dk", 1e-2), ("dv", 1e-2)):
         assert np.isfinite(got[name]).all(), name
         _cmp(got[name], want[name], tol, 1e-4, name)        # bf16 P / dS operands in the GEMMs: 1e-2 of max
     if has_bias:
