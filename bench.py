@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="scenes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of one step to this file and exit")
     a = ap.parse_args()
 
     import torch
@@ -246,6 +247,15 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step(resident, False)
     torch.cuda.synchronize()
+    if a.profile:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step(resident, False)
+            torch.cuda.synchronize()
+        os.makedirs(os.path.dirname(os.path.abspath(a.profile)), exist_ok=True)
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        return
     sampler = ClockSampler(local)
     sampler.start()
     C.lib().vdetr_timing_enable(1)

@@ -18,7 +18,7 @@ namespace {
 
 constexpr int DT_WARPS = 16;
 constexpr int DT_THREADS = DT_WARPS * 32;
-constexpr int CACHE = 4;
+constexpr int CACHE = 8;                       // warp-level cache entries (bins held in registers)
 
 struct DtParams {
   int B, nQ, nK, nQp, nKp, n;
@@ -36,6 +36,20 @@ __device__ __forceinline__ void flush_slot(float* stab, int tag, float acc, int 
   const int x = n0x + (corner & 1), y = n0y + ((corner >> 1) & 1), z = n0z + (corner >> 2);
   if ((unsigned)x < (unsigned)n && (unsigned)y < (unsigned)n && (unsigned)z < (unsigned)n && acc != 0.f)
     atomicAdd(stab + ((((size_t)vert * n + z) * n + y) * n + x) * 4 + h, acc);
+}
+
+// sum of column `lane` of the 32x33 scratch tile over the rows selected by `mask` (fully unrolled: the 32
+// predicated loads are independent, so their latency overlaps)
+__device__ __forceinline__ float column_sum(const float* my, int lane, unsigned mask) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int l = 0; l < 32; l += 4) {
+    if (mask & (1u << l)) s0 += my[l * 33 + lane];
+    if (mask & (2u << l)) s1 += my[(l + 1) * 33 + lane];
+    if (mask & (4u << l)) s2 += my[(l + 2) * 33 + lane];
+    if (mask & (8u << l)) s3 += my[(l + 3) * 33 + lane];
+  }
+  return (s0 + s1) + (s2 + s3);
 }
 
 __global__ void __launch_bounds__(DT_THREADS, 1) rpe_dtables_kernel(DtParams P) {
@@ -62,59 +76,58 @@ __global__ void __launch_bounds__(DT_THREADS, 1) rpe_dtables_kernel(DtParams P) 
     const float4* xrow = P.xyz4 + (size_t)b * P.nKp;
     const float4* drow = P.ds4 + ((size_t)b * P.nQp + q) * P.nKp;
 
-    int tag0 = -1, tag1 = -1, tag2 = -1, tag3 = -1, victim = 0;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int tag[CACHE];
+    float acc[CACHE];
+#pragma unroll
+    for (int c = 0; c < CACHE; ++c) { tag[c] = -1; acc[c] = 0.f; }
+    int victim = 0;
 
+    // software prefetch of the next step's inputs
+    float4 kx_n = make_float4(0.f, 0.f, 0.f, 0.f), ds_n = kx_n;
+    if (lane < P.nK) { kx_n = __ldg(xrow + lane); ds_n = __ldg(drow + lane); }
     for (int k0 = 0; k0 < P.nK; k0 += 32) {
       const int key = k0 + lane;
+      const float4 kx = kx_n, ds = ds_n;
+      if (key + 32 < P.nK) { kx_n = __ldg(xrow + key + 32); ds_n = __ldg(drow + key + 32); }
       int bin = -1;
-      if (key < P.nK) {
-        const float4 kx = __ldg(xrow + key);
-        const float4 ds = __ldg(drow + key);
-        if (ds.x != 0.f || ds.y != 0.f || ds.z != 0.f || ds.w != 0.f) {
-          const float dx = vx - kx.x, dy = vy - kx.y, dz = vz - kx.z;
-          const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-          const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
-          const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
-          const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
-          bin = ((az.n0 + 2) << 10) | ((ay.n0 + 2) << 5) | (ax.n0 + 2);
-          float* row = my + lane * 33;
+      if (key < P.nK && (ds.x != 0.f || ds.y != 0.f || ds.z != 0.f || ds.w != 0.f)) {
+        const float dx = vx - kx.x, dy = vy - kx.y, dz = vz - kx.z;
+        const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+        const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
+        const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
+        const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
+        bin = ((az.n0 + 2) << 10) | ((ay.n0 + 2) << 5) | (ax.n0 + 2);
+        float* row = my + lane * 33;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float w = ((c & 4) ? az.w1 : az.w0) * ((c & 2) ? ay.w1 : ay.w0) * ((c & 1) ? ax.w1 : ax.w0);
-            row[c * 4 + 0] = w * ds.x; row[c * 4 + 1] = w * ds.y; row[c * 4 + 2] = w * ds.z; row[c * 4 + 3] = w * ds.w;
-          }
+        for (int c = 0; c < 8; ++c) {
+          const float w = ((c & 4) ? az.w1 : az.w0) * ((c & 2) ? ay.w1 : ay.w0) * ((c & 1) ? ax.w1 : ax.w0);
+          row[c * 4 + 0] = w * ds.x; row[c * 4 + 1] = w * ds.y; row[c * 4 + 2] = w * ds.z; row[c * 4 + 3] = w * ds.w;
         }
       }
       __syncwarp();
       unsigned rem = __ballot_sync(0xffffffffu, bin >= 0);
+      // 1. bins already cached: one masked column sum per cache entry that is hit
+#pragma unroll
+      for (int c = 0; c < CACHE; ++c) {
+        const unsigned hit = __ballot_sync(0xffffffffu, bin == tag[c]) & rem;   // tag -1 never matches a live bin
+        if (hit) { acc[c] += column_sum(my, lane, hit); rem &= ~hit; }
+      }
+      // 2. new bins: evict round-robin
       while (rem) {
         const int leader = __ffs(rem) - 1;
         const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, bin == bsel);
+        const unsigned grp = __ballot_sync(0xffffffffu, bin == bsel) & rem;
         rem &= ~grp;
-        float s = 0.f;
-        for (unsigned m = grp; m; m &= m - 1) s += my[(__ffs(m) - 1) * 33 + lane];
-        if (bsel == tag0) acc0 += s;
-        else if (bsel == tag1) acc1 += s;
-        else if (bsel == tag2) acc2 += s;
-        else if (bsel == tag3) acc3 += s;
-        else {
-          switch (victim) {
-            case 0: flush_slot(stab, tag0, acc0, lane, vert, P.n); tag0 = bsel; acc0 = s; break;
-            case 1: flush_slot(stab, tag1, acc1, lane, vert, P.n); tag1 = bsel; acc1 = s; break;
-            case 2: flush_slot(stab, tag2, acc2, lane, vert, P.n); tag2 = bsel; acc2 = s; break;
-            default: flush_slot(stab, tag3, acc3, lane, vert, P.n); tag3 = bsel; acc3 = s; break;
-          }
-          victim = (victim + 1) & (CACHE - 1);
-        }
+        const float s = column_sum(my, lane, grp);
+#pragma unroll
+        for (int c = 0; c < CACHE; ++c)
+          if (c == victim) { flush_slot(stab, tag[c], acc[c], lane, vert, P.n); tag[c] = bsel; acc[c] = s; }
+        victim = (victim + 1) & (CACHE - 1);
       }
       __syncwarp();
     }
-    flush_slot(stab, tag0, acc0, lane, vert, P.n);
-    flush_slot(stab, tag1, acc1, lane, vert, P.n);
-    flush_slot(stab, tag2, acc2, lane, vert, P.n);
-    flush_slot(stab, tag3, acc3, lane, vert, P.n);
+#pragma unroll
+    for (int c = 0; c < CACHE; ++c) flush_slot(stab, tag[c], acc[c], lane, vert, P.n);
   }
   __syncthreads();
   for (int i = tid; i < ncell4; i += DT_THREADS) {
