@@ -169,7 +169,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     config = {"workload": f"C3/C4: {a.batch} scenes per GPU x {NK} keys x {NQ} queries x {NLAYERS} decoder layers, "
-                          "fwd+bwd+AdamW, train mode (BN batch stats per GPU, dropout 0)",
+                          "fwd+bwd+AdamW, train mode (BN batch stats per GPU, dropout 0), TF32 Linear/Conv layers",
               "global_batch": a.batch * world, "parallelism": f"dp{world}",
               "l2": "per-step working set (> 2 GB of attention scratch + activations) >> 126 MB L2; no explicit flush"}
 
@@ -195,6 +195,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (vdetr_b200 has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # the nn.Linear / Conv1d layers around the kernels run on the TF32 tensor-core path (the configs name bf16)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
     ddp = world > 1
     if ddp:
         import torch.distributed as dist

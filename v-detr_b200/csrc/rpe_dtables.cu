@@ -13,6 +13,7 @@
 //     tables in shared memory (CAS atomics, rare), which is added to global memory once per CTA at the end.
 #include "rpe_internal.h"
 #include "rpe_fast.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -138,6 +139,245 @@ __global__ void __launch_bounds__(DT_THREADS, 1) rpe_dtables_kernel(DtParams P) 
 
 }  // namespace
 
+// =====================================================================================================
+// Version 2: bucket the evaluations by table cell first, then accumulate in registers.
+//
+// A unit is (scene b, vertex i, block of 32 queries, chunk of 1024 keys) = 32,768 evaluations.
+//   phase 1  every thread computes the bin (floor of the 3 pixel coordinates) of its evaluations, stores it and
+//            counts it in a shared-memory histogram (native integer atomics);
+//   phase 2  exclusive scan of the histogram, then a counting-sort scatter of the evaluation ids;
+//   phase 3  each warp walks a contiguous range of the sorted list, 32 evaluations per step (lane = evaluation).
+//            Sorted order means a whole step normally belongs to ONE bin, so every lane simply accumulates its
+//            8 corners x 4 heads into 32 private registers; only when the bin changes are the 32x32 partial sums
+//            reduced across lanes (transpose through a scratch tile) and added to a per-CTA fp32 copy of table i.
+// Per evaluation this costs ~4 warp-instructions instead of ~35 for the cache-based version above.
+namespace v2 {
+
+constexpr int QB = 32, KC = 1024, UNIT = QB * KC;          // evaluations per unit
+constexpr int THREADS = 512, WARPS = THREADS / 32;
+
+struct Params {
+  int B, nQ, nK, nQp, nKp, n, R;     // R = n + 1 values of n0 per axis that can contribute: [-1, n-1]
+  int qblocks, kchunks, units;
+  float log_scale, c1, c0;
+  const float4* xyz4;
+  const float4* geo;
+  const float4* ds4;
+  float* dtables;
+};
+
+__device__ __forceinline__ int axis_n0(float d, float ls, float c1, float c0, int n) {
+  float t = tc::lg2_approx(fmaf(fabsf(d), ls, 1.0f)) * c1;
+  float ts = copysignf(t, d);
+  ts = fminf(fmaxf(ts, -c0 - 1.5f), (float)n - c0 + 0.5f);
+  float r = ((ts + c0) - 0.5f) + rpe::MAGIC;
+  return __float_as_int(r) - rpe::MAGIC_BITS;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int nbins = P.R * P.R * P.R;
+  const int nbins_pad = (2 * nbins + 1 + 3) & ~3;                           // ints, keeps what follows 16-B aligned
+  uint16_t* binbuf = reinterpret_cast<uint16_t*>(sm);                       // [UNIT]
+  uint16_t* sorted = binbuf + UNIT;                                         // [UNIT]
+  int* hist = reinterpret_cast<int*>(sorted + UNIT);                        // [nbins]  counts, then cursors
+  int* offs = hist + nbins;                                                 // [nbins + 1] exclusive scan
+  float* stab = reinterpret_cast<float*>(hist + nbins_pad);                 // [n^3 * 4] table of the current vertex
+  float4* sgeo = reinterpret_cast<float4*>(stab + P.n * P.n * P.n * 4);     // [QB][2]: (vx,vy,vz,valid) (cos,sin,0,0)
+  float* scratch = reinterpret_cast<float*>(sgeo + QB * 2);                 // [WARPS][32][33]
+  __shared__ int s_total;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncell4 = P.n * P.n * P.n * 4;
+  float* my = scratch + warp * 32 * 33;
+  const int sx = 16, sy = 16 * P.n, sz = 16 * P.n * P.n;
+
+  // contiguous range of units per CTA, vertex-major, so that the shared table is flushed only a few times
+  const int per = (P.units + gridDim.x - 1) / gridDim.x;
+  const int u_begin = blockIdx.x * per, u_end = min(P.units, u_begin + per);
+  int cur_vert = -1;
+
+  for (int u = u_begin; u < u_end; ++u) {
+    // unit -> (vert, b, qblock, kchunk)
+    int r = u;
+    const int kc = r % P.kchunks; r /= P.kchunks;
+    const int qb = r % P.qblocks; r /= P.qblocks;
+    const int b = r % P.B;
+    const int vert = r / P.B;
+    const int q0 = qb * QB, k0 = kc * KC;
+
+    if (vert != cur_vert) {
+      __syncthreads();
+      if (cur_vert >= 0)
+        for (int i = tid; i < ncell4; i += THREADS) {
+          const float v = stab[i];
+          if (v != 0.f) atomicAdd(P.dtables + (size_t)cur_vert * ncell4 + i, v);
+        }
+      __syncthreads();
+      for (int i = tid; i < ncell4; i += THREADS) stab[i] = 0.f;
+      cur_vert = vert;
+    }
+    for (int i = tid; i < nbins; i += THREADS) hist[i] = 0;
+    if (tid < QB) {
+      const int q = q0 + tid;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = make_float4(1.f, 0.f, 0.f, 0.f);
+      if (q < P.nQ) {
+        const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
+        const float* vv = reinterpret_cast<const float*>(g + 2);
+        a = make_float4(__ldg(vv + vert * 3), __ldg(vv + vert * 3 + 1), __ldg(vv + vert * 3 + 2), 1.f);
+        c = __ldg(g + 8);
+      }
+      sgeo[tid * 2] = a; sgeo[tid * 2 + 1] = c;
+    }
+    __syncthreads();
+
+    // ---- phase 1: bins + histogram.  e = ql * KC + kl ; a warp covers 32 consecutive keys of one query
+    const float4* xrow = P.xyz4 + (size_t)b * P.nKp + k0;
+    for (int e = tid; e < UNIT; e += THREADS) {
+      const int ql = e >> 10, kl = e & (KC - 1);
+      const float4 vq = sgeo[ql * 2], rot = sgeo[ql * 2 + 1];
+      int bin = 0xFFFF;
+      if (vq.w != 0.f && k0 + kl < P.nK) {
+        const float4 kx = __ldg(xrow + kl);
+        const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
+        const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+        const int nx = axis_n0(tx, P.log_scale, P.c1, P.c0, P.n) + 1;
+        const int ny = axis_n0(ty, P.log_scale, P.c1, P.c0, P.n) + 1;
+        const int nz = axis_n0(dz, P.log_scale, P.c1, P.c0, P.n) + 1;
+        if ((unsigned)nx < (unsigned)P.R && (unsigned)ny < (unsigned)P.R && (unsigned)nz < (unsigned)P.R) {
+          bin = (nz * P.R + ny) * P.R + nx;
+          atomicAdd(&hist[bin], 1);
+        }
+      }
+      binbuf[e] = (uint16_t)bin;
+    }
+    __syncthreads();
+    // ---- phase 2a: exclusive scan (warp 0), cursors = offsets
+    if (warp == 0) {
+      int run = 0;
+      for (int base = 0; base < nbins; base += 32) {
+        const int i = base + lane;
+        const int c = i < nbins ? hist[i] : 0;
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += y;
+        }
+        if (i < nbins) { offs[i] = run + x - c; hist[i] = run + x - c; }
+        run += __shfl_sync(0xffffffffu, x, 31);
+      }
+      if (lane == 0) { offs[nbins] = run; s_total = run; }
+    }
+    __syncthreads();
+    // ---- phase 2b: scatter
+    for (int e = tid; e < UNIT; e += THREADS) {
+      const int bin = binbuf[e];
+      if (bin != 0xFFFF) sorted[atomicAdd(&hist[bin], 1)] = (uint16_t)e;
+    }
+    __syncthreads();
+    // sorted[] no longer needs binbuf's bins except to find segment ends: re-use offs[] for that.
+
+    // ---- phase 3: accumulate
+    const int total = s_total;
+    const int span = ((total + WARPS - 1) / WARPS + 31) & ~31;     // entries per warp, multiple of 32
+    const int p_begin = warp * span, p_end = min(total, p_begin + span);
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    int cur_bin = -1;
+    const float4* dbase = P.ds4 + ((size_t)b * P.nQp + q0) * P.nKp + k0;
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+      const int p = p0 + lane;
+      const bool live = p < p_end;
+      int e = 0, bin = -1;
+      if (live) { e = sorted[p]; bin = binbuf[e]; }
+      // segments inside this step (normally exactly one)
+      unsigned todo = __ballot_sync(0xffffffffu, live);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
+        todo &= ~grp;
+        if (bsel != cur_bin) {
+          if (cur_bin >= 0) {
+            // epilogue of the previous bin: transpose-reduce the 32x32 partial sums, add to the shared table
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { my[lane * 33 + j] = acc[j]; acc[j] = 0.f; }
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int l = 0; l < 32; l += 4) {
+              s0 += my[l * 33 + lane]; s1 += my[(l + 1) * 33 + lane];
+              s2 += my[(l + 2) * 33 + lane]; s3 += my[(l + 3) * 33 + lane];
+            }
+            __syncwarp();
+            const float tot = (s0 + s1) + (s2 + s3);
+            const int bx = cur_bin % P.R - 1, by = (cur_bin / P.R) % P.R - 1, bz = cur_bin / (P.R * P.R) - 1;
+            const int corner = lane >> 2, h = lane & 3;
+            const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
+            if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && tot != 0.f)
+              atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + h, tot);
+          }
+          cur_bin = bsel;
+        }
+        if (grp & (1u << lane)) {
+          const int ql = e >> 10, kl = e & (KC - 1);
+          const float4 vq = sgeo[ql * 2], rot = sgeo[ql * 2 + 1];
+          const float4 kx = __ldg(xrow + kl);
+          const float4 ds = __ldg(dbase + (size_t)ql * P.nKp + kl);
+          const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
+          const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+          const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
+          const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
+          const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float w = ((c & 4) ? az.w1 : az.w0) * ((c & 2) ? ay.w1 : ay.w0) * ((c & 1) ? ax.w1 : ax.w0);
+            acc[c * 4 + 0] = fmaf(w, ds.x, acc[c * 4 + 0]); acc[c * 4 + 1] = fmaf(w, ds.y, acc[c * 4 + 1]);
+            acc[c * 4 + 2] = fmaf(w, ds.z, acc[c * 4 + 2]); acc[c * 4 + 3] = fmaf(w, ds.w, acc[c * 4 + 3]);
+          }
+        }
+      }
+    }
+    if (cur_bin >= 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) my[lane * 33 + j] = acc[j];
+      __syncwarp();
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; l += 4) {
+        s0 += my[l * 33 + lane]; s1 += my[(l + 1) * 33 + lane];
+        s2 += my[(l + 2) * 33 + lane]; s3 += my[(l + 3) * 33 + lane];
+      }
+      __syncwarp();
+      const float tot = (s0 + s1) + (s2 + s3);
+      const int bx = cur_bin % P.R - 1, by = (cur_bin / P.R) % P.R - 1, bz = cur_bin / (P.R * P.R) - 1;
+      const int corner = lane >> 2, h = lane & 3;
+      const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
+      if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && tot != 0.f)
+        atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + h, tot);
+    }
+    __syncthreads();     // before the next unit overwrites hist / binbuf / sorted / sgeo
+  }
+  __syncthreads();
+  if (cur_vert >= 0)
+    for (int i = tid; i < ncell4; i += THREADS) {
+      const float v = stab[i];
+      if (v != 0.f) atomicAdd(P.dtables + (size_t)cur_vert * ncell4 + i, v);
+    }
+}
+
+size_t smem_bytes(int n) {
+  const int R = n + 1, nbins = R * R * R;
+  size_t o = (size_t)UNIT * 2 * 2;
+  o += (size_t)((2 * nbins + 1 + 3) & ~3) * 4;
+  o += (size_t)n * n * n * 16 + QB * 2 * 16 + (size_t)WARPS * 32 * 33 * 4;
+  return o;
+}
+
+}  // namespace v2
+
 // ds4 [B][nQp][nKp] float4, xyz4 / geo as produced by vdetr_pack_kernel.  dtables is zeroed here.
 int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const float4* ds4,
                        float* dtables, cudaStream_t st) {
@@ -151,6 +391,25 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   P.c1 = (float)n / (2.0f * 3.0f * s->max_value);
   P.c0 = 0.5f * (float)(n - 1);
   P.xyz4 = xyz4; P.geo = geo; P.ds4 = ds4; P.dtables = dtables;
+  const char* force = getenv("VDETR_DT_IMPL");
+  const size_t smem2 = v2::smem_bytes(n);
+  if (smem2 <= 232448 && (n + 1) * (n + 1) * (n + 1) < 0xFFFF && !(force && force[0] == '1')) {
+    v2::Params Q = {};
+    Q.B = s->B; Q.nQ = s->nQ; Q.nK = s->nK; Q.nQp = nQp; Q.nKp = nKp; Q.n = n; Q.R = n + 1;
+    Q.qblocks = (s->nQ + v2::QB - 1) / v2::QB;
+    Q.kchunks = (s->nK + v2::KC - 1) / v2::KC;
+    Q.units = 8 * s->B * Q.qblocks * Q.kchunks;
+    Q.log_scale = P.log_scale; Q.c1 = P.c1; Q.c0 = P.c0;
+    Q.xyz4 = xyz4; Q.geo = geo; Q.ds4 = ds4; Q.dtables = dtables;
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(v2::rpe_dtables_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const int grid2 = Q.units < vdetr_num_sms() ? Q.units : vdetr_num_sms();
+    {
+      VdetrTimingScope timing(VDETR_T_DTABLES, st);
+      v2::rpe_dtables_sorted_kernel<<<grid2, v2::THREADS, smem2, st>>>(Q);
+    }
+    VDETR_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = tbytes + (size_t)DT_WARPS * 32 * 33 * sizeof(float);
   if (smem > 232448) return VDETR_ERR_UNSUPPORTED;
   VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_dtables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
