@@ -244,36 +244,42 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
         const int nx = axis_n0(tx, P.log_scale, P.c1, P.c0, P.n) + 1;
         const int ny = axis_n0(ty, P.log_scale, P.c1, P.c0, P.n) + 1;
         const int nz = axis_n0(dz, P.log_scale, P.c1, P.c0, P.n) + 1;
-        if ((unsigned)nx < (unsigned)P.R && (unsigned)ny < (unsigned)P.R && (unsigned)nz < (unsigned)P.R) {
+        if ((unsigned)nx < (unsigned)P.R && (unsigned)ny < (unsigned)P.R && (unsigned)nz < (unsigned)P.R)
           bin = (nz * P.R + ny) * P.R + nx;
-          atomicAdd(&hist[bin], 1);
-        }
       }
       binbuf[e] = (uint16_t)bin;
+      // warp-aggregated histogram update: the 32 keys of a warp mostly share a bin, and same-address shared
+      // atomics serialise, so one lane per distinct bin adds the group's population
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xFFFF && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
     }
     __syncthreads();
-    // ---- phase 2a: exclusive scan (warp 0), cursors = offsets
+    // ---- phase 2a: exclusive scan (warp 0: each lane owns a contiguous slice of bins), cursors = offsets
     if (warp == 0) {
-      int run = 0;
-      for (int base = 0; base < nbins; base += 32) {
-        const int i = base + lane;
-        const int c = i < nbins ? hist[i] : 0;
-        int x = c;
+      const int per_lane = (nbins + 31) / 32;
+      const int lo = lane * per_lane, hi = min(nbins, lo + per_lane);
+      int mine = 0;
+      for (int i = lo; i < hi; ++i) mine += hist[i];
+      int x = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(0xffffffffu, x, o);
-          if (lane >= o) x += y;
-        }
-        if (i < nbins) { offs[i] = run + x - c; hist[i] = run + x - c; }
-        run += __shfl_sync(0xffffffffu, x, 31);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
       }
-      if (lane == 0) { offs[nbins] = run; s_total = run; }
+      int run = x - mine;
+      for (int i = lo; i < hi; ++i) { const int c = hist[i]; hist[i] = run; offs[i] = run; run += c; }
+      if (lane == 31) { offs[nbins] = x; s_total = x; }
     }
     __syncthreads();
     // ---- phase 2b: scatter
     for (int e = tid; e < UNIT; e += THREADS) {
       const int bin = binbuf[e];
-      if (bin != 0xFFFF) sorted[atomicAdd(&hist[bin], 1)] = (uint16_t)e;
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (bin != 0xFFFF && lane == leader) base = atomicAdd(&hist[bin], __popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (bin != 0xFFFF) sorted[base + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)e;
     }
     __syncthreads();
     // sorted[] no longer needs binbuf's bins except to find segment ends: re-use offs[] for that.
@@ -287,62 +293,12 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
     int cur_bin = -1;
     const float4* dbase = P.ds4 + ((size_t)b * P.nQp + q0) * P.nKp + k0;
-    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-      const int p = p0 + lane;
-      const bool live = p < p_end;
-      int e = 0, bin = -1;
-      if (live) { e = sorted[p]; bin = binbuf[e]; }
-      // segments inside this step (normally exactly one)
-      unsigned todo = __ballot_sync(0xffffffffu, live);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
-        todo &= ~grp;
-        if (bsel != cur_bin) {
-          if (cur_bin >= 0) {
-            // epilogue of the previous bin: transpose-reduce the 32x32 partial sums, add to the shared table
+    const int corner = lane >> 2, hsel = lane & 3;
+
+    // reduce the 32 lanes' private partial sums of bin `bin` (transpose through the scratch tile) into the table
+    auto flush = [&](int bin) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { my[lane * 33 + j] = acc[j]; acc[j] = 0.f; }
-            __syncwarp();
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int l = 0; l < 32; l += 4) {
-              s0 += my[l * 33 + lane]; s1 += my[(l + 1) * 33 + lane];
-              s2 += my[(l + 2) * 33 + lane]; s3 += my[(l + 3) * 33 + lane];
-            }
-            __syncwarp();
-            const float tot = (s0 + s1) + (s2 + s3);
-            const int bx = cur_bin % P.R - 1, by = (cur_bin / P.R) % P.R - 1, bz = cur_bin / (P.R * P.R) - 1;
-            const int corner = lane >> 2, h = lane & 3;
-            const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
-            if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && tot != 0.f)
-              atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + h, tot);
-          }
-          cur_bin = bsel;
-        }
-        if (grp & (1u << lane)) {
-          const int ql = e >> 10, kl = e & (KC - 1);
-          const float4 vq = sgeo[ql * 2], rot = sgeo[ql * 2 + 1];
-          const float4 kx = __ldg(xrow + kl);
-          const float4 ds = __ldg(dbase + (size_t)ql * P.nKp + kl);
-          const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
-          const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-          const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
-          const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
-          const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float w = ((c & 4) ? az.w1 : az.w0) * ((c & 2) ? ay.w1 : ay.w0) * ((c & 1) ? ax.w1 : ax.w0);
-            acc[c * 4 + 0] = fmaf(w, ds.x, acc[c * 4 + 0]); acc[c * 4 + 1] = fmaf(w, ds.y, acc[c * 4 + 1]);
-            acc[c * 4 + 2] = fmaf(w, ds.z, acc[c * 4 + 2]); acc[c * 4 + 3] = fmaf(w, ds.w, acc[c * 4 + 3]);
-          }
-        }
-      }
-    }
-    if (cur_bin >= 0) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) my[lane * 33 + j] = acc[j];
+      for (int j = 0; j < 32; ++j) { my[lane * 33 + j] = acc[j]; acc[j] = 0.f; }
       __syncwarp();
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -352,12 +308,74 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
       }
       __syncwarp();
       const float tot = (s0 + s1) + (s2 + s3);
-      const int bx = cur_bin % P.R - 1, by = (cur_bin / P.R) % P.R - 1, bz = cur_bin / (P.R * P.R) - 1;
-      const int corner = lane >> 2, h = lane & 3;
+      const int bx = bin % P.R - 1, by = (bin / P.R) % P.R - 1, bz = bin / (P.R * P.R) - 1;
       const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
       if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && tot != 0.f)
-        atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + h, tot);
+        atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, tot);
+    };
+
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+      const int p = p0 + lane;
+      const bool live = p < p_end;
+      int bin = -1;
+      float c[32];
+      int cz0 = 0, cy0 = 0, cx0 = 0;
+      if (live) {
+        const int e = sorted[p];
+        bin = binbuf[e];
+        const int ql = e >> 10, kl = e & (KC - 1);
+        const float4 vq = sgeo[ql * 2], rot = sgeo[ql * 2 + 1];
+        const float4 kx = __ldg(xrow + kl);
+        const float4 ds = __ldg(dbase + (size_t)ql * P.nKp + kl);
+        const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
+        const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+        const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
+        const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
+        const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
+        cz0 = az.n0; cy0 = ay.n0; cx0 = ax.n0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
+          c[k * 4 + 0] = w * ds.x; c[k * 4 + 1] = w * ds.y; c[k * 4 + 2] = w * ds.z; c[k * 4 + 3] = w * ds.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) c[k] = 0.f;
+      }
+      // segments of this step, in sorted (= lane) order
+      unsigned todo = __ballot_sync(0xffffffffu, live);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
+        todo &= ~grp;
+        const bool mine = (grp >> lane) & 1u;
+        if (bsel == cur_bin || __popc(grp) >= 12) {
+          // long segment: private register accumulation, reduced across lanes only when the bin changes
+          if (bsel != cur_bin) {
+            if (cur_bin >= 0) flush(cur_bin);
+            cur_bin = bsel;
+          }
+          if (mine) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc[k] += c[k];
+          }
+        } else if (mine) {
+          // short segment (the long tail of nearly empty cells): add this evaluation's 32 products directly
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int x = cx0 + (k & 1), y = cy0 + ((k >> 1) & 1), z = cz0 + (k >> 2);
+            if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n) {
+              float* cell = stab + (((z * P.n + y) * P.n + x) << 2);
+#pragma unroll
+              for (int h = 0; h < 4; ++h)
+                if (c[k * 4 + h] != 0.f) atomicAdd(cell + h, c[k * 4 + h]);
+            }
+          }
+        }
+      }
     }
+    if (cur_bin >= 0) flush(cur_bin);
     __syncthreads();     // before the next unit overwrites hist / binbuf / sorted / sgeo
   }
   __syncthreads();

@@ -34,18 +34,29 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
 //   vtp  bf16 [B][kvh][64][nKp]   (V transposed: keys contiguous)
 //   xyz4 f32  [B][nKp] float4
 //   geo  f32  [B][nQp][9] float4: (x+,y+,z+,fast flag) (x-,y-,z-,0) 24 vertex floats (cos,sin,0,0)
-// Precision plan: the S = Q K^T and O = P V tensor-core products use FP16 operands (11-bit significand: 8x
-// tighter than BF16 at the same cost, and q/k/v/p are O(1) so range is no concern); everything that carries
-// gradients (dO, dS, and the copies of Q/K/V/P that meet them in a GEMM) is BF16.
+// Precision plan: every tensor-core operand is FP16 (11-bit significand: 8x tighter than BF16 at the same
+// cost).  q/k/v/p are O(1), so range is no concern for them; gradients (dO, and dS which is proportional to it)
+// are multiplied by a power of two chosen per call from max|dO| so that they sit in [2^-20, 16] of fp16's range
+// ("scaled fp16"), and the results are divided by the same power of two (exact).
 struct VdetrPack {
   int B, nQ, nK, nQp, nKp, kvh, has_bias;
   const float *q, *k, *v, *xyz, *ref, *ang, *dout;
-  __half *qp, *kp, *vtp;                 // fp16: forward operands (and the S recompute of the backward)
-  __nv_bfloat16 *qpb, *kpb, *vp, *dop;   // bf16: backward GEMM operands (null in the forward)
+  const unsigned* dout_absmax_bits;      // device: bits of max|dout| (backward only)
+  __half *qp, *kp, *vtp;                 // forward operands (and the S recompute of the backward)
+  __half *vp, *dop;                      // backward: row-major V, scaled dO (null in the forward)
   float4* xyz4;
   float4* geo;
 };
 __global__ void vdetr_pack_kernel(VdetrPack K);
+__global__ void vdetr_absmax_kernel(const float* x, size_t n, unsigned* out_bits);
+// power-of-two gradient scale derived from max|dout| (same formula on every device thread that needs it)
+__device__ __forceinline__ float vdetr_grad_scale(unsigned absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
+  float e = floorf(log2f(16.f / m));
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
 
 // dTables (rpe_dtables.cu)
 int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const float4* ds4,

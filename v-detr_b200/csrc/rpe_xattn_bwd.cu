@@ -3,8 +3,9 @@
 // Pass 1 (this file's kernel, tcgen05 + TMA, same tiling / warp roles as the forward):
 //     S  = Q K^T + rpe            (bias recomputed, never read from memory)
 //     P  = exp(S - LSE)           dP = dO V^T          dS = P * (dP - D),   D = rowsum(dO * O)
-//   written once as  P (bf16), dS (bf16) [rows][nKp]  and  dS4 (fp32, 4 heads of a (query,key) pair together).
-// Pass 2: the three plain GEMMs   dQ = dS K,  dK = dS^T Q,  dV = P^T dO   (cuBLAS, bf16 in / fp32 out).
+//   written once as  P (fp16), g*dS (fp16) [rows][nKp]  and  dS4 (fp32, 4 heads of a (query,key) pair together);
+//   g is the per-call power-of-two gradient scale (rpe_internal.h).
+// Pass 2: the three plain GEMMs   dQ = dS K,  dK = dS^T Q,  dV = P^T dO   (cuBLAS, fp16 in / fp32 out).
 // Pass 3: dTables from dS4 (rpe_dtables.cu).
 #include <cublas_v2.h>
 #include "rpe_internal.h"
@@ -34,8 +35,9 @@ struct BwdParams {
   const float* out;            // [B,nQ,4,64] forward output
   const float* dout;           // [B,nQ,4,64]
   const float* lse;            // [B,4,nQ]
-  __nv_bfloat16* pb;           // [rows][nKp]
-  __nv_bfloat16* dsb;          // [rows][nKp]
+  const unsigned* absmax_bits; // bits of max|dout| -> gradient scale
+  __half* pb;                  // [rows][nKp]  P
+  __half* dsb;                 // [rows][nKp]  g * dS
   float4* ds4;                 // [B][nQp][nKp]   (HAS_BIAS)
 };
 
@@ -106,7 +108,8 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS0 = tmem_base, tdP0 = tmem_base + 128;
   const uint32_t idesc_s = umma_idesc_f16(BM, BN);     // S  = Q K^T : fp16 operands, exactly as the forward
-  const uint32_t idesc_d = umma_idesc_bf16(BM, BN);    // dP = dO V^T: bf16 operands (gradients need the range)
+  const uint32_t idesc_d = umma_idesc_f16(BM, BN);     // g*dP = (g dO) V^T: scaled fp16
+  const float gscale = vdetr_grad_scale(*P.absmax_bits), ginv = 1.0f / gscale;
 
   uint32_t g = 0, it = 0;
   for (int item = blockIdx.x; item < P.items; item += gridDim.x, ++it) {
@@ -180,7 +183,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       sRow[row * 4 + slice] = dpart;
       named_bar_sync(1, NCOMPUTE);
       const float4 dp4 = *reinterpret_cast<const float4*>(sRow + row * 4);
-      const float Drow = (dp4.x + dp4.y) + (dp4.z + dp4.w);
+      const float Drow = ((dp4.x + dp4.y) + (dp4.z + dp4.w)) * gscale;
       const float lse2 = (q < P.nQ) ? __ldg(P.lse + ((size_t)b * 4 + h) * P.nQ + q) * LOG2E : INFINITY;
       const size_t grow = (size_t)(qrow0 + row) * P.nKp;
 
@@ -219,12 +222,12 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (HAS_BIAS) s += brow[(c + e) * 4];
             float p = ex2_approx(s * LOG2E - lse2);
             if (key0 + slice * 16 + c + e >= P.nK) p = 0.f;
-            const float ds = p * (__uint_as_float(dr[c + e]) - Drow);
-            if (HAS_BIAS) brow[(c + e) * 4] = ds;          // same slot the bias came from: owned by this thread
+            const float ds = p * (__uint_as_float(dr[c + e]) - Drow);        // = g * dS
+            if (HAS_BIAS) brow[(c + e) * 4] = ds * ginv;   // same slot the bias came from: owned by this thread
             pv[e] = p; dv[e] = ds;
           }
-          pk[c >> 1] = pack_bf16x2(pv[0], pv[1]);
-          dk_[c >> 1] = pack_bf16x2(dv[0], dv[1]);
+          pk[c >> 1] = pack_f16x2(pv[0], pv[1]);
+          dk_[c >> 1] = pack_f16x2(dv[0], dv[1]);
         }
         {
           uint4* dstp = reinterpret_cast<uint4*>(P.pb + grow + key0 + slice * 16);
@@ -259,8 +262,10 @@ struct UnpackParams {
   int B, nQ, nK, nQp, nKp, kvh;
   const float *dqp, *dkp, *dvp;
   float *dq, *dk, *dv;
+  const unsigned* absmax_bits;
 };
 __global__ void bwd_unpack_kernel(UnpackParams U) {
+  const float ginv = 1.0f / vdetr_grad_scale(*U.absmax_bits);
   const size_t nq = (size_t)U.B * U.nQ * 4 * 64, nk = (size_t)U.B * U.nK * U.kvh * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nq + 2 * nk; i += (size_t)gridDim.x * blockDim.x) {
     if (i < nq) {
@@ -268,7 +273,7 @@ __global__ void bwd_unpack_kernel(UnpackParams U) {
       const size_t bq = i >> 8;
       const int q = (int)(bq % U.nQ), b = (int)(bq / U.nQ);
       const size_t row = U.kvh == 1 ? ((size_t)b * U.nQp + q) * 4 + h : ((size_t)b * 4 + h) * U.nQp + q;
-      U.dq[i] = U.dqp[row * 64 + d];
+      U.dq[i] = U.dqp[row * 64 + d] * ginv;
     } else {
       const size_t e = (i - nq) % nk;
       const bool isv = (i - nq) >= nk;
@@ -277,14 +282,14 @@ __global__ void bwd_unpack_kernel(UnpackParams U) {
       const int hk = (int)(r % U.kvh);
       const int key = (int)((r / U.kvh) % U.nK), b = (int)(r / ((size_t)U.kvh * U.nK));
       const size_t src = (((size_t)b * U.kvh + hk) * U.nKp + key) * 64 + d;
-      if (isv) U.dv[e] = U.dvp[src]; else U.dk[e] = U.dkp[src];
+      if (isv) U.dv[e] = U.dvp[src] * ginv; else U.dk[e] = U.dkp[src] * ginv;
     }
   }
 }
 
 struct BwdPlan {
   int nQp, nKp, mtiles, splits, tiles_per_split, items;
-  size_t off_qp, off_qpb, off_dop, off_kp, off_kpb, off_vp, off_vtp, off_xyz, off_geo, off_pb, off_dsb, off_ds4, off_dqp, off_dkp, off_dvp, total;
+  size_t off_qp, off_dop, off_kp, off_vp, off_max, off_xyz, off_geo, off_pb, off_dsb, off_ds4, off_dqp, off_dkp, off_dvp, total;
 };
 BwdPlan make_plan(const VdetrXattnShape* s) {
   BwdPlan p;
@@ -314,12 +319,10 @@ BwdPlan make_plan(const VdetrXattnShape* s) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += vdetr_align_up(bytes, 1024); return r; };
   p.off_qp = take(rows * 64 * 2);
-  p.off_qpb = take(rows * 64 * 2);
   p.off_dop = take(rows * 64 * 2);
   p.off_kp = take(krows * 64 * 2);
-  p.off_kpb = take(krows * 64 * 2);
   p.off_vp = take(krows * 64 * 2);
-  p.off_vtp = take(krows * 64 * 2);
+  p.off_max = take(16);
   p.off_xyz = take(s->has_bias ? (size_t)s->B * p.nKp * 16 : 0);
   p.off_geo = take(s->has_bias ? (size_t)s->B * p.nQp * GEO_F4 * 16 : 0);
   p.off_pb = take(rows * p.nKp * 2);
@@ -340,12 +343,12 @@ cublasHandle_t get_cublas() {
   return h[dev];
 }
 
-// row-major C[M,N] = op(A) op(B), bf16 inputs, fp32 output, strided batch
-int gemm_rm(cublasHandle_t hnd, bool ta, bool tb, int M, int N, int K, const __nv_bfloat16* A, int lda, long long sa,
-            const __nv_bfloat16* Bm, int ldb, long long sb, float* C, int ldc, long long sc, int batch) {
+// row-major C[M,N] = op(A) op(B), fp16 inputs, fp32 output, strided batch
+int gemm_rm(cublasHandle_t hnd, bool ta, bool tb, int M, int N, int K, const __half* A, int lda, long long sa,
+            const __half* Bm, int ldb, long long sb, float* C, int ldc, long long sc, int batch) {
   const float alpha = 1.f, beta = 0.f;
   cublasStatus_t st = cublasGemmStridedBatchedEx(hnd, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K,
-                                                 &alpha, Bm, CUDA_R_16BF, ldb, sb, A, CUDA_R_16BF, lda, sa, &beta, C, CUDA_R_32F,
+                                                 &alpha, Bm, CUDA_R_16F, ldb, sb, A, CUDA_R_16F, lda, sa, &beta, C, CUDA_R_32F,
                                                  ldc, sc, batch, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
   return st == CUBLAS_STATUS_SUCCESS ? 0 : VDETR_ERR_UNSUPPORTED;
 }
@@ -370,13 +373,16 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   VdetrPack pk = {};
   pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = pl.nQp; pk.nKp = pl.nKp; pk.kvh = s->kv_heads; pk.has_bias = s->has_bias;
   pk.q = q; pk.k = k; pk.v = v; pk.xyz = xyz; pk.ref = ref; pk.ang = (s->has_bias && s->rotate) ? ang : nullptr; pk.dout = dout;
+  unsigned* absmax = reinterpret_cast<unsigned*>(w + pl.off_max);
+  VDETR_CUDA_TRY(cudaMemsetAsync(absmax, 0, 4, st));
+  vdetr_absmax_kernel<<<vdetr_num_sms() * 2, 256, 0, st>>>(dout, (size_t)s->B * s->nQ * 4 * 64, absmax);
+  VDETR_LAUNCH_CHECK();
+  pk.dout_absmax_bits = absmax;
   pk.qp = reinterpret_cast<__half*>(w + pl.off_qp);
-  pk.qpb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_qpb);
-  pk.dop = reinterpret_cast<__nv_bfloat16*>(w + pl.off_dop);
+  pk.dop = reinterpret_cast<__half*>(w + pl.off_dop);
   pk.kp = reinterpret_cast<__half*>(w + pl.off_kp);
-  pk.kpb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_kpb);
-  pk.vp = reinterpret_cast<__nv_bfloat16*>(w + pl.off_vp);
-  pk.vtp = reinterpret_cast<__half*>(w + pl.off_vtp);
+  pk.vp = reinterpret_cast<__half*>(w + pl.off_vp);
+  pk.vtp = nullptr;
   pk.xyz4 = reinterpret_cast<float4*>(w + pl.off_xyz);
   pk.geo = reinterpret_cast<float4*>(w + pl.off_geo);
   vdetr_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(pk);
@@ -386,9 +392,9 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   CUtensorMap tmQ, tmdO, tmK, tmV;
   int rc;
   if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, rows, BM, true))) return rc;
-  if ((rc = vdetr_make_tmap_bf16_rows64(&tmdO, pk.dop, rows, BM))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmdO, pk.dop, rows, BM, true))) return rc;
   if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, krows, BN, true))) return rc;
-  if ((rc = vdetr_make_tmap_bf16_rows64(&tmV, pk.vp, krows, BN))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmV, pk.vp, krows, BN, true))) return rc;
 
   BwdParams P = {};
   P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = pl.nQp; P.nKp = pl.nKp; P.kvh = s->kv_heads;
@@ -399,8 +405,9 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   P.c0 = s->has_bias ? 0.5f * (float)(s->grid_n - 1) : 0.f;
   P.xyz4 = pk.xyz4; P.geo = pk.geo; P.tables = reinterpret_cast<const float4*>(tables);
   P.out = out; P.dout = dout; P.lse = lse;
-  P.pb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_pb);
-  P.dsb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_dsb);
+  P.absmax_bits = absmax;
+  P.pb = reinterpret_cast<__half*>(w + pl.off_pb);
+  P.dsb = reinterpret_cast<__half*>(w + pl.off_dsb);
   P.ds4 = reinterpret_cast<float4*>(w + pl.off_ds4);
 
   const int table_bytes = s->has_bias ? 8 * s->grid_n * s->grid_n * s->grid_n * 16 : 0;
@@ -433,10 +440,10 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   const int batch = mqa ? s->B : s->B * 4;
   const int rpb = mqa ? pl.nQp * 4 : pl.nQp;              // attention rows per batch entry
   const long long sRows = (long long)rpb * pl.nKp, sRow64 = (long long)rpb * 64, sK64 = (long long)pl.nKp * 64;
-  if ((rc = gemm_rm(hnd, false, false, rpb, 64, pl.nKp, P.dsb, pl.nKp, sRows, pk.kpb, 64, sK64, dqp, 64, sRow64, batch))) return rc;
-  if ((rc = gemm_rm(hnd, true, false, pl.nKp, 64, rpb, P.dsb, pl.nKp, sRows, pk.qpb, 64, sRow64, dkp, 64, sK64, batch))) return rc;
+  if ((rc = gemm_rm(hnd, false, false, rpb, 64, pl.nKp, P.dsb, pl.nKp, sRows, pk.kp, 64, sK64, dqp, 64, sRow64, batch))) return rc;
+  if ((rc = gemm_rm(hnd, true, false, pl.nKp, 64, rpb, P.dsb, pl.nKp, sRows, pk.qp, 64, sRow64, dkp, 64, sK64, batch))) return rc;
   if ((rc = gemm_rm(hnd, true, false, pl.nKp, 64, rpb, P.pb, pl.nKp, sRows, pk.dop, 64, sRow64, dvp, 64, sK64, batch))) return rc;
-  UnpackParams U = {s->B, s->nQ, s->nK, pl.nQp, pl.nKp, s->kv_heads, dqp, dkp, dvp, dq, dk, dv};
+  UnpackParams U = {s->B, s->nQ, s->nK, pl.nQp, pl.nKp, s->kv_heads, dqp, dkp, dvp, dq, dk, dv, absmax};
   bwd_unpack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(U);
   VDETR_LAUNCH_CHECK();
 

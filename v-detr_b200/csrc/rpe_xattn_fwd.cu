@@ -376,7 +376,16 @@ __global__ void fwd_combine_kernel(FwdParams P, int mqa) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ packing (shared with bwd)
+__global__ void vdetr_absmax_kernel(const float* x, size_t n, unsigned* out_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));      // non-negative floats order like uints
+}
+
 __global__ void vdetr_pack_kernel(VdetrPack K) {
+  const float gscale = K.dout ? vdetr_grad_scale(*K.dout_absmax_bits) : 1.f;
   const size_t nq = K.qp ? (size_t)K.B * K.nQp * 4 * 64 : 0;           // destination elements of Qp
   const size_t nk = K.kp ? (size_t)K.B * K.kvh * K.nKp * 64 : 0;
   const size_t nx = K.has_bias ? (size_t)K.B * K.nKp : 0;
@@ -393,11 +402,10 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       float val = 0.f;
       if (q < K.nQ) val = K.q[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
       K.qp[i] = __float2half_rn(val);
-      if (K.qpb) K.qpb[i] = __float2bfloat16_rn(val);
       if (K.dout) {
         float dv = 0.f;
         if (q < K.nQ) dv = K.dout[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
-        K.dop[i] = __float2bfloat16_rn(dv);
+        K.dop[i] = __float2half_rn(dv * gscale);
       }
     } else if (i < nq + nk) {
       const size_t e = i - nq;                               // Kp [b][hk][key][d]
@@ -408,13 +416,13 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       float val = 0.f;
       if (key < K.nK) val = K.k[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
       K.kp[e] = __float2half_rn(val);
-      if (K.kpb) K.kpb[e] = __float2bfloat16_rn(val);
       if (K.vp) {                                            // row-major V as well (backward: dP = dO V^T)
         float vv = 0.f;
         if (key < K.nK) vv = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-        K.vp[e] = __float2bfloat16_rn(vv);
+        K.vp[e] = __float2half_rn(vv);
       }
     } else if (i < nq + 2 * nk) {
+      if (!K.vtp) continue;
       const size_t e = i - nq - nk;                          // Vtp [b][hk][d][key]
       const int key = (int)(e % K.nKp);
       const size_t r = e / K.nKp;
