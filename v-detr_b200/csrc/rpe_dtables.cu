@@ -319,7 +319,6 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
       const bool live = p < p_end;
       int bin = -1;
       float c[32];
-      int cz0 = 0, cy0 = 0, cx0 = 0;
       if (live) {
         const int e = sorted[p];
         bin = binbuf[e];
@@ -332,7 +331,6 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
         const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
         const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
         const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
-        cz0 = az.n0; cy0 = ay.n0; cx0 = ax.n0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
@@ -342,18 +340,50 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
 #pragma unroll
         for (int k = 0; k < 32; ++k) c[k] = 0.f;
       }
-      // segments of this step, in sorted (= lane) order
-      unsigned todo = __ballot_sync(0xffffffffu, live);
-      while (todo) {
+      // segments of this step, in sorted (= lane) order.  Long segments (>= 12 lanes, or the continuation of the
+      // bin being accumulated) go to the lane-private registers; the long tail of nearly empty cells is summed
+      // through the scratch tile (rows of one segment are contiguous) and added straight to the table.
+      const unsigned all = __ballot_sync(0xffffffffu, live);
+      unsigned todo = all, longmask = 0u;
+      bool staged = false;
+      while (todo) {                                   // pass A: short segments
         const int leader = __ffs(todo) - 1;
         const int bsel = __shfl_sync(0xffffffffu, bin, leader);
         const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
         todo &= ~grp;
-        const bool mine = (grp >> lane) & 1u;
-        if (bsel == cur_bin || __popc(grp) >= 12) {
-          // long segment: private register accumulation, reduced across lanes only when the bin changes
-          if (bsel != cur_bin) {
-            if (cur_bin >= 0) flush(cur_bin);
+        const int cnt = __popc(grp);
+        if (bsel == cur_bin || cnt >= 12) { longmask |= grp; continue; }
+        if (!staged) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) my[lane * 33 + j] = c[j];
+          __syncwarp();
+          staged = true;
+        }
+        float ssum = 0.f;
+        for (int l = leader; l < leader + cnt; ++l) ssum += my[l * 33 + lane];
+        const int bx = bsel % P.R - 1, by = (bsel / P.R) % P.R - 1, bz = bsel / (P.R * P.R) - 1;
+        const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
+        if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && ssum != 0.f)
+          atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, ssum);
+      }
+      if (staged) __syncwarp();
+      todo = longmask;
+      while (todo) {                                   // pass B: long segments
+        const int leader = __ffs(todo) - 1;
+        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel) & longmask;
+        todo &= ~grp;
+        if (bsel != cur_bin) {
+          if (cur_bin >= 0) flush(cur_bin);
+          cur_bin = bsel;
+        }
+        if ((grp >> lane) & 1u) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[k] += c[k];
+        }
+      }
+    }
+    if (cur_bin >= 0) flush(cur_bin);
             cur_bin = bsel;
           }
           if (mine) {
