@@ -384,28 +384,6 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
       }
     }
     if (cur_bin >= 0) flush(cur_bin);
-            cur_bin = bsel;
-          }
-          if (mine) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) acc[k] += c[k];
-          }
-        } else if (mine) {
-          // short segment (the long tail of nearly empty cells): add this evaluation's 32 products directly
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int x = cx0 + (k & 1), y = cy0 + ((k >> 1) & 1), z = cz0 + (k >> 2);
-            if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n) {
-              float* cell = stab + (((z * P.n + y) * P.n + x) << 2);
-#pragma unroll
-              for (int h = 0; h < 4; ++h)
-                if (c[k * 4 + h] != 0.f) atomicAdd(cell + h, c[k * 4 + h]);
-            }
-          }
-        }
-      }
-    }
-    if (cur_bin >= 0) flush(cur_bin);
     __syncthreads();     // before the next unit overwrites hist / binbuf / sorted / sgeo
   }
   __syncthreads();
