@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
   float4* sgeo = reinterpret_cast<float4*>(stab + P.n * P.n * P.n * 4);     // [QB][2]: (vx,vy,vz,valid) (cos,sin,0,0)
   float* scratch = reinterpret_cast<float*>(sgeo + QB * 2);                 // [WARPS][32][33]
   __shared__ int s_total;
+  __shared__ int s_next;          // phase 3: next unclaimed chunk of the sorted list
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncell4 = P.n * P.n * P.n * 4;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
       }
       int run = x - mine;
       for (int i = lo; i < hi; ++i) { const int c = hist[i]; hist[i] = run; offs[i] = run; run += c; }
-      if (lane == 31) { offs[nbins] = x; s_total = x; }
+      if (lane == 31) { offs[nbins] = x; s_total = x; s_next = 0; }
     }
     __syncthreads();
     // ---- phase 2b: scatter
@@ -284,14 +285,13 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
     __syncthreads();
     // sorted[] no longer needs binbuf's bins except to find segment ends: re-use offs[] for that.
 
-    // ---- phase 3: accumulate
+    // ---- phase 3: accumulate.  Warps claim chunks of CHUNK sorted entries dynamically (the cost per entry varies
+    // a lot between long and short segments, so a static split leaves most warps idle at the barrier).
+    constexpr int CHUNK = 256;
     const int total = s_total;
-    const int span = ((total + WARPS - 1) / WARPS + 31) & ~31;     // entries per warp, multiple of 32
-    const int p_begin = warp * span, p_end = min(total, p_begin + span);
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    int cur_bin = -1;
     const float4* dbase = P.ds4 + ((size_t)b * P.nQp + q0) * P.nKp + k0;
     const int corner = lane >> 2, hsel = lane & 3;
 
@@ -314,76 +314,103 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
         atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, tot);
     };
 
-    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-      const int p = p0 + lane;
-      const bool live = p < p_end;
-      int bin = -1;
-      float c[32];
-      if (live) {
-        const int e = sorted[p];
-        bin = binbuf[e];
-        const int ql = e >> 10, kl = e & (KC - 1);
-        const float4 vq = sgeo[ql * 2], rot = sgeo[ql * 2 + 1];
-        const float4 kx = __ldg(xrow + kl);
-        const float4 ds = __ldg(dbase + (size_t)ql * P.nKp + kl);
-        const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
-        const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-        const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
-        const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
-        const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
-          c[k * 4 + 0] = w * ds.x; c[k * 4 + 1] = w * ds.y; c[k * 4 + 2] = w * ds.z; c[k * 4 + 3] = w * ds.w;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) c[k] = 0.f;
-      }
-      // segments of this step, in sorted (= lane) order.  Long segments (>= 12 lanes, or the continuation of the
-      // bin being accumulated) go to the lane-private registers; the long tail of nearly empty cells is summed
-      // through the scratch tile (rows of one segment are contiguous) and added straight to the table.
-      const unsigned all = __ballot_sync(0xffffffffu, live);
-      unsigned todo = all, longmask = 0u;
-      bool staged = false;
-      while (todo) {                                   // pass A: short segments
-        const int leader = __ffs(todo) - 1;
-        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
-        todo &= ~grp;
-        const int cnt = __popc(grp);
-        if (bsel == cur_bin || cnt >= 12) { longmask |= grp; continue; }
-        if (!staged) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) my[lane * 33 + j] = c[j];
-          __syncwarp();
-          staged = true;
-        }
-        float ssum = 0.f;
-        for (int l = leader; l < leader + cnt; ++l) ssum += my[l * 33 + lane];
-        const int bx = bsel % P.R - 1, by = (bsel / P.R) % P.R - 1, bz = bsel / (P.R * P.R) - 1;
-        const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
-        if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && ssum != 0.f)
-          atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, ssum);
-      }
-      if (staged) __syncwarp();
-      todo = longmask;
-      while (todo) {                                   // pass B: long segments
-        const int leader = __ffs(todo) - 1;
-        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel) & longmask;
-        todo &= ~grp;
-        if (bsel != cur_bin) {
-          if (cur_bin >= 0) flush(cur_bin);
-          cur_bin = bsel;
-        }
-        if ((grp >> lane) & 1u) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) acc[k] += c[k];
+    for (;;) {
+      int c0 = 0;
+      if (lane == 0) c0 = atomicAdd(&s_next, CHUNK);
+      c0 = __shfl_sync(0xffffffffu, c0, 0);
+      if (c0 >= total) break;
+      const int c1 = min(total, c0 + CHUNK);
+      int cur_bin = -1;
+      // software pipeline: the gathers of step s+1 are in flight while step s is accumulated
+      int bin_n = -1;
+      float4 vq_n = make_float4(0.f, 0.f, 0.f, 0.f), rot_n = vq_n, kx_n = vq_n, ds_n = vq_n;
+      {
+        const int p = c0 + lane;
+        if (p < c1) {
+          const int e = sorted[p];
+          bin_n = binbuf[e];
+          const int ql = e >> 10, kl = e & (KC - 1);
+          vq_n = sgeo[ql * 2]; rot_n = sgeo[ql * 2 + 1];
+          kx_n = __ldg(xrow + kl);
+          ds_n = __ldg(dbase + (size_t)ql * P.nKp + kl);
         }
       }
+      for (int p0 = c0; p0 < c1; p0 += 32) {
+        const int bin = bin_n;
+        const bool live = bin >= 0;
+        const float4 vq = vq_n, rot = rot_n, kx = kx_n, ds = ds_n;
+        bin_n = -1;
+        {
+          const int p = p0 + 32 + lane;
+          if (p < c1) {
+            const int e = sorted[p];
+            bin_n = binbuf[e];
+            const int ql = e >> 10, kl = e & (KC - 1);
+            vq_n = sgeo[ql * 2]; rot_n = sgeo[ql * 2 + 1];
+            kx_n = __ldg(xrow + kl);
+            ds_n = __ldg(dbase + (size_t)ql * P.nKp + kl);
+          }
+        }
+        float c[32];
+        if (live) {
+          const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
+          const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+          const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
+          const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
+          const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
+            c[k * 4 + 0] = w * ds.x; c[k * 4 + 1] = w * ds.y; c[k * 4 + 2] = w * ds.z; c[k * 4 + 3] = w * ds.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) c[k] = 0.f;
+        }
+        // segments of this step, in sorted (= lane) order.  Long segments (>= 12 lanes, or the continuation of the
+        // bin being accumulated) go to the lane-private registers; the long tail of nearly empty cells is summed
+        // through the scratch tile (rows of one segment are contiguous) and added straight to the table.
+        unsigned todo = __ballot_sync(0xffffffffu, live), longmask = 0u;
+        bool staged = false;
+        while (todo) {                                   // pass A: short segments
+          const int leader = __ffs(todo) - 1;
+          const int bsel = __shfl_sync(0xffffffffu, bin, leader);
+          const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
+          todo &= ~grp;
+          const int cnt = __popc(grp);
+          if (bsel == cur_bin || cnt >= 12) { longmask |= grp; continue; }
+          if (!staged) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) my[lane * 33 + j] = c[j];
+            __syncwarp();
+            staged = true;
+          }
+          float ssum = 0.f;
+          for (int l = leader; l < leader + cnt; ++l) ssum += my[l * 33 + lane];
+          const int bx = bsel % P.R - 1, by = (bsel / P.R) % P.R - 1, bz = bsel / (P.R * P.R) - 1;
+          const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
+          if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && ssum != 0.f)
+            atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, ssum);
+        }
+        if (staged) __syncwarp();
+        todo = longmask;
+        while (todo) {                                   // pass B: long segments
+          const int leader = __ffs(todo) - 1;
+          const int bsel = __shfl_sync(0xffffffffu, bin, leader);
+          const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel) & longmask;
+          todo &= ~grp;
+          if (bsel != cur_bin) {
+            if (cur_bin >= 0) flush(cur_bin);
+            cur_bin = bsel;
+          }
+          if ((grp >> lane) & 1u) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc[k] += c[k];
+          }
+        }
+      }
+      if (cur_bin >= 0) flush(cur_bin);
     }
-    if (cur_bin >= 0) flush(cur_bin);
     __syncthreads();     // before the next unit overwrites hist / binbuf / sorted / sgeo
   }
   __syncthreads();
