@@ -207,11 +207,12 @@ def main():
     dec = build_ours(torch).to(dev).train()
     for p in dec.pointcls_heads.parameters():        # used by ModelVDETR.forward, not by the decoder itself
         p.requires_grad_(False)
-    model = dec
-    if ddp:
-        model = torch.nn.parallel.DistributedDataParallel(dec, device_ids=[local])
+    from vdetr_b200 import parallel
+    model = parallel.wrap_data_parallel(dec, dev)        # DDP: one bucketed NCCL gradient all-reduce per step
     opt = torch.optim.AdamW([p for p in dec.parameters() if p.requires_grad], lr=1e-5, weight_decay=0.1, fused=True)
-    host = synth_scene(a.batch, NK, rank, torch)
+    lo, hi = parallel.shard_range(a.batch * world, rank, world)     # scenes [lo, hi) of the global batch live on this rank
+    assert hi - lo == a.batch
+    host = synth_scene(a.batch, NK, lo, torch)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
     weights = loss_weights(torch, NQ, NLAYERS, dev)
@@ -241,11 +242,10 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
         if ddp:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.barrier()
-        return ms.item()
+        return ms
 
     for _ in range(max(a.warmup, 3)):
         step(resident, False)

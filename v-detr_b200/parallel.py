@@ -1,0 +1,36 @@
+"""Data-parallel plumbing for the decoder hot path.
+
+The path shards naturally: scenes are independent, so a global batch is split by scene over ranks (one process per
+GPU) and the only data-path collective is the bucketed gradient all-reduce that DistributedDataParallel issues
+during backward (the reference does the same: main.py:515-517).  BatchNorm statistics stay per GPU (the reference
+converts to SyncBatchNorm, main.py:512-514; with 8 scenes x 1024 queries per GPU the local statistics already cover
+8192 samples per channel -- stated deviation).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Contiguous, balanced range of scene indices owned by `rank` (first `global_batch % world` ranks get one more)."""
+    base, extra = divmod(global_batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def wrap_data_parallel(module: torch.nn.Module, device=None, find_unused_parameters: bool = False):
+    """DistributedDataParallel with the reference's flags (main.py:515-517); identity when not distributed."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return module
+    ids = None if device is None or torch.device(device).type != "cuda" else [torch.device(device).index]
+    return torch.nn.parallel.DistributedDataParallel(module, device_ids=ids, find_unused_parameters=find_unused_parameters)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Every multi-GPU time is reported as the maximum over ranks (never wall clock)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -66,9 +66,20 @@ class ScanNetBoxConfig:
     """The part of ScannetDatasetConfig the decoder reads (datasets/scannet.py:38-41,168-171).  The reference's
     own config object can be passed instead; only these attributes are used."""
 
+    # mean box size (m) per ScanNet class: the data constants of datasets/scannet.py:72-91, used by ModelVDETR to
+    # pick the proposal anchors from the per-point class prediction (models/model_vdetr.py:347-353)
+    MEAN_SIZE = ((0.76966726, 0.81160211, 0.92573741), (1.876858, 1.84255952, 1.19315654), (0.61327999, 0.61486087, 0.71827014),
+                 (1.39550063, 1.51215451, 0.83443565), (0.97949596, 1.06751485, 0.63296875), (0.53166301, 0.59555772, 1.75001483),
+                 (0.96247056, 0.72462326, 1.14818682), (0.83221924, 1.04909355, 1.68756634), (0.21132214, 0.4206159, 0.53728459),
+                 (1.44400728, 1.89708334, 0.26985747), (1.02942616, 1.40407966, 0.87554322), (1.37664116, 0.65521793, 1.68131292),
+                 (0.66508189, 0.71111926, 1.29885307), (0.41999174, 0.37906947, 1.75139715), (0.59359559, 0.59124924, 0.73919014),
+                 (0.50867595, 0.50656087, 0.30136236), (1.15115265, 1.0546296, 0.49706794), (0.47535286, 0.49249493, 0.58021168))
+
     def __init__(self, num_semcls=18, num_angle_bin=1):
         self.num_semcls = num_semcls
         self.num_angle_bin = num_angle_bin
+        self.mean_size_arr = np.array(self.MEAN_SIZE)
+        self.mean_size_arr_hard_anchor = np.ones((18, 3))
 
     @staticmethod
     def box_parametrization_to_corners(center, size, angle):
