@@ -103,7 +103,8 @@ def test_bias_kernel_matches_numpy_oracle_and_reference_golden():
 # Product kernels (impl = 0: tcgen05 + TMA, fp32 bias / softmax / accumulation).  The S = QK^T and O = PV
 # products use FP16 tensor-core operands (2^-12 relative rounding, 8x tighter than the BF16 the configs name,
 # same cost); gradient operands are FP16 after a per-call power-of-two scaling.  Tolerances, as a fraction of the tensor's max:
-#   forward  vs the oracle evaluated on fp16-rounded q/k/v : 1e-3   (what the kernel itself adds)
+#   forward  vs the oracle evaluated on fp16-rounded q/k/v/tables : 1e-3   (what the kernel itself adds; the vertex
+#            tables live in shared memory as fp16)
 #   forward  vs the fp64 oracle on the original fp32 inputs : 4e-3   (includes the fp16 rounding of the inputs at
 #            this deliberately harsh logit scale, |S| ~ 4; at the decoder's real scale see test_decoder_gpu.py)
 #   backward vs the oracle on fp16-rounded inputs           : 4e-3   (fp16 P and scaled-fp16 dS in the gradient GEMMs)
@@ -126,7 +127,7 @@ def test_tc_forward_matches_oracle(seed, B, nQ, nK, kvh, rot):
     has_bias = kvh == 1
     I = _core_inputs(seed, B, nQ, nK, kvh, rot)
     want = _oracle(I, has_bias)
-    Ib = dict(I, q=_fp16_round(I["q"]), k=_fp16_round(I["k"]), v=_fp16_round(I["v"]))
+    Ib = dict(I, q=_fp16_round(I["q"]), k=_fp16_round(I["k"]), v=_fp16_round(I["v"]), tables=_fp16_round(I["tables"]))
     want_b = _oracle(Ib, has_bias)
     t = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in I.items()}
     with torch.no_grad():
@@ -150,7 +151,8 @@ TC_BWD_CASES = [(21, 1, 32, 64, 1, False), (22, 2, 24, 80, 1, False), (23, 1, 16
 def test_tc_backward_matches_oracle(seed, B, nQ, nK, kvh, rot):
     has_bias = kvh == 1
     I = _core_inputs(seed, B, nQ, nK, kvh, rot)
-    Ib = dict(I, q=_fp16_round(I["q"]), k=_fp16_round(I["k"]), v=_fp16_round(I["v"]), do=_fp16_round(I["do"]))
+    Ib = dict(I, q=_fp16_round(I["q"]), k=_fp16_round(I["k"]), v=_fp16_round(I["v"]), do=_fp16_round(I["do"]),
+              tables=_fp16_round(I["tables"]))
     want = _oracle(Ib, has_bias)
     got = _run(I, impl=0, has_bias=has_bias)
     for name, tol in (("o", 1e-3), ("dq", 4e-3), ("dk", 4e-3), ("dv", 4e-3)):

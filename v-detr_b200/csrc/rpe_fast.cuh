@@ -2,6 +2,7 @@
 // Same formula as rpe_common.cuh / the reference (vdetr_transformer.py:708-731) with MUFU lg2 and a
 // round-to-nearest floor; differences to the exact variant are ~1e-6 in the pixel coordinate.
 #pragma once
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace rpe {
@@ -35,47 +36,83 @@ __device__ __forceinline__ Axis rpe_axis_fast(float d, float ls, float c1, float
   return a;
 }
 
-__device__ __forceinline__ void corner8(float4& acc, const char* tab, const Axis& ax, const Axis& ay, const Axis& az) {
+// ---- table layout in shared memory -----------------------------------------------------------------------
+// The fused kernels are bound by shared-memory wavefronts (an LDS.128 always costs 4, broadcast or not), so the
+// tables are stored as FP16 *x-pairs*: entry (i, z, y, p), p in [0, n-2], holds the 4 heads of cells x = p and
+// x = p + 1 (8 halves = 16 B).  One LDS.128 then serves both x-corners of a (z, y) corner pair: 32 loads per
+// (query, key) pair instead of 64.  Cells outside [0, n-1] are padding (weight 0), so x0 = -1 maps to pair 0 with
+// the weight on its low element and x0 = n-1 to pair n-2 with the weight on its high element.
+__host__ __device__ inline int pair_table_bytes(int n) { return 8 * n * n * (n - 1) * 16; }
+
+struct XPair {
+  float wl, wh;     // weights of the low / high cell of the pair
+  int off;          // byte offset of the pair inside a (z, y) row
+};
+__device__ __forceinline__ XPair make_xpair(const Axis& a, int n) {
+  XPair x;
+  const bool lt = a.n0 < 0, gt = a.n0 > n - 2;
+  x.wl = lt ? a.w1 : (gt ? 0.0f : a.w0);
+  x.wh = lt ? 0.0f : (gt ? a.w0 : a.w1);
+  x.off = min(max(a.n0, 0), n - 2) * 16;
+  return x;
+}
+
+__device__ __forceinline__ void corner_pairs(float4& acc, const char* tab, const XPair& x, const Axis& ay, const Axis& az) {
 #pragma unroll
   for (int cz = 0; cz < 2; ++cz) {
     const int oz = cz ? az.o1 : az.o0;
     const float wz = cz ? az.w1 : az.w0;
 #pragma unroll
     for (int cy = 0; cy < 2; ++cy) {
-      const int ozy = oz + (cy ? ay.o1 : ay.o0);
       const float wzy = wz * (cy ? ay.w1 : ay.w0);
-#pragma unroll
-      for (int cx = 0; cx < 2; ++cx) {
-        const float w = wzy * (cx ? ax.w1 : ax.w0);
-        const float4 t = *reinterpret_cast<const float4*>(tab + ozy + (cx ? ax.o1 : ax.o0));
-        acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y);
-        acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
-      }
+      const uint4 raw = *reinterpret_cast<const uint4*>(tab + oz + (cy ? ay.o1 : ay.o0) + x.off);
+      const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      const float2 l23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+      const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
+      const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
+      const float a = wzy * x.wl, b = wzy * x.wh;
+      acc.x = fmaf(a, l01.x, fmaf(b, h01.x, acc.x)); acc.y = fmaf(a, l01.y, fmaf(b, h01.y, acc.y));
+      acc.z = fmaf(a, l23.x, fmaf(b, h23.x, acc.z)); acc.w = fmaf(a, l23.y, fmaf(b, h23.y, acc.w));
     }
   }
 }
 
-// Bias of one (query,key) pair for the 4 heads.  geo: the query's record in shared memory (see pack kernel).
+// fp32 tables [8][n][n][n] float4 (global) -> fp16 x-pair tables (shared); cooperative, `nthreads` participants
+__device__ __forceinline__ void load_pair_tables(uint4* dst, const float4* __restrict__ src, int n, int tid, int nthreads) {
+  const int npair = n - 1, total = 8 * n * n * npair;
+  for (int i = tid; i < total; i += nthreads) {
+    const int p = i % npair, row = i / npair;
+    const float4 lo = __ldg(src + row * n + p), hi = __ldg(src + row * n + p + 1);
+    uint4 o;
+    o.x = tc::pack_f16x2(lo.x, lo.y); o.y = tc::pack_f16x2(lo.z, lo.w);
+    o.z = tc::pack_f16x2(hi.x, hi.y); o.w = tc::pack_f16x2(hi.z, hi.w);
+    dst[i] = o;
+  }
+}
+
+// Bias of one (query,key) pair for the 4 heads.  geo: the query's record in shared memory (see pack kernel);
+// tab: fp16 x-pair tables in shared memory.
 __device__ __forceinline__ float4 rpe_bias_pair(const float4* __restrict__ geo, float kx, float ky, float kz,
                                                 const char* __restrict__ tab, int n, float ls, float c1, float c0) {
-  const int sx = 16, sy = 16 * n, sz = 16 * n * n, st = 16 * n * n * n;
+  const int sx = 16, sy = 16 * (n - 1), sz = 16 * n * (n - 1), st = 16 * n * n * (n - 1);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 hi = geo[0];
   if (__float_as_int(hi.w) != 0) {
     // axis-aligned box: 2 distinct coordinates per axis -> 6 transforms instead of 24
     const float4 lo = geo[1];
-    const Axis xp = rpe_axis_fast(hi.x - kx, ls, c1, c0, n, sx), xm = rpe_axis_fast(lo.x - kx, ls, c1, c0, n, sx);
+    const XPair xp = make_xpair(rpe_axis_fast(hi.x - kx, ls, c1, c0, n, sx), n);
+    const XPair xm = make_xpair(rpe_axis_fast(lo.x - kx, ls, c1, c0, n, sx), n);
     const Axis yp = rpe_axis_fast(hi.y - ky, ls, c1, c0, n, sy), ym = rpe_axis_fast(lo.y - ky, ls, c1, c0, n, sy);
     const Axis zp = rpe_axis_fast(hi.z - kz, ls, c1, c0, n, sz), zm = rpe_axis_fast(lo.z - kz, ls, c1, c0, n, sz);
     // vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4:(+,+,+) 5:(+,-,+) 6:(-,-,+) 7:(-,+,+)
-    corner8(acc, tab + 0 * st, xp, yp, zm);
-    corner8(acc, tab + 1 * st, xp, ym, zm);
-    corner8(acc, tab + 2 * st, xm, ym, zm);
-    corner8(acc, tab + 3 * st, xm, yp, zm);
-    corner8(acc, tab + 4 * st, xp, yp, zp);
-    corner8(acc, tab + 5 * st, xp, ym, zp);
-    corner8(acc, tab + 6 * st, xm, ym, zp);
-    corner8(acc, tab + 7 * st, xm, yp, zp);
+    corner_pairs(acc, tab + 0 * st, xp, yp, zm);
+    corner_pairs(acc, tab + 1 * st, xp, ym, zm);
+    corner_pairs(acc, tab + 2 * st, xm, ym, zm);
+    corner_pairs(acc, tab + 3 * st, xm, yp, zm);
+    corner_pairs(acc, tab + 4 * st, xp, yp, zp);
+    corner_pairs(acc, tab + 5 * st, xp, ym, zp);
+    corner_pairs(acc, tab + 6 * st, xm, ym, zp);
+    corner_pairs(acc, tab + 7 * st, xm, yp, zp);
   } else {
     const float4 rot = geo[8];
     const float* v = reinterpret_cast<const float*>(geo + 2);
@@ -83,13 +120,12 @@ __device__ __forceinline__ float4 rpe_bias_pair(const float4* __restrict__ geo, 
     for (int i = 0; i < 8; ++i) {
       float dx = v[i * 3 + 0] - kx, dy = v[i * 3 + 1] - ky, dz = v[i * 3 + 2] - kz;
       const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;     // identity when not rotated
-      const Axis ax = rpe_axis_fast(tx, ls, c1, c0, n, sx), ay = rpe_axis_fast(ty, ls, c1, c0, n, sy),
-                 az = rpe_axis_fast(dz, ls, c1, c0, n, sz);
-      corner8(acc, tab + i * st, ax, ay, az);
+      const XPair ax = make_xpair(rpe_axis_fast(tx, ls, c1, c0, n, sx), n);
+      const Axis ay = rpe_axis_fast(ty, ls, c1, c0, n, sy), az = rpe_axis_fast(dz, ls, c1, c0, n, sz);
+      corner_pairs(acc, tab + i * st, ax, ay, az);
     }
   }
   return acc;
 }
-
 
 }  // namespace rpe

@@ -67,7 +67,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(HAS_BIAS ? 8 * P.grid_n * P.grid_n * P.grid_n * 16 : 0);
+  const SmemLayout L = smem_layout(HAS_BIAS ? rpe::pair_table_bytes(P.grid_n) : 0);
   uint8_t* sQ = smem + L.q;
   uint8_t* sdO = smem + L.dO;
   uint8_t* sK = smem + L.k;
@@ -98,9 +98,8 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncwarp();
     tmem_alloc<TMEM_COLS>(tmem_slot);
   } else if (HAS_BIAS) {
-    const int n4 = 8 * P.grid_n * P.grid_n * P.grid_n;
-    float4* dst = reinterpret_cast<float4*>(smem + L.tables);
-    for (int i = tid; i < n4; i += NCOMPUTE) dst[i] = __ldg(P.tables + i);
+    // tables -> shared memory as fp16 x-pairs, once per (persistent) CTA
+    rpe::load_pair_tables(reinterpret_cast<uint4*>(smem + L.tables), P.tables, P.grid_n, tid, NCOMPUTE);
   }
   tc_fence_before();
   __syncthreads();
@@ -410,7 +409,7 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   P.dsb = reinterpret_cast<__half*>(w + pl.off_dsb);
   P.ds4 = reinterpret_cast<float4*>(w + pl.off_ds4);
 
-  const int table_bytes = s->has_bias ? 8 * s->grid_n * s->grid_n * s->grid_n * 16 : 0;
+  const int table_bytes = s->has_bias ? rpe::pair_table_bytes(s->grid_n) : 0;
   const SmemLayout L = smem_layout(table_bytes);
   if (L.total + 1024 > 232448) return VDETR_ERR_UNSUPPORTED;
   const size_t smem = L.total + 1024;

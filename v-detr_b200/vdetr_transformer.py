@@ -46,14 +46,25 @@ def scale_points(pred_xyz, mult_factor):
     return pred_xyz * mult_factor[:, None, :]
 
 
+_CORNER_SIGNS = {}
+
+
+def _corner_signs(like):
+    """Per-device constant sign vectors (cached: creating them from Python lists is a host->device copy, which is
+    not allowed while a CUDA graph is being captured)."""
+    key = (like.device, like.dtype)
+    if key not in _CORNER_SIGNS:
+        _CORNER_SIGNS[key] = tuple(torch.tensor(v, dtype=like.dtype, device=like.device) for v in (
+            [1., 1., -1., -1., 1., 1., -1., -1.], [1., 1., 1., 1., -1., -1., -1., -1.], [1., -1., -1., 1., 1., -1., -1., 1.]))
+    return _CORNER_SIGNS[key]
+
+
 def box_corners_camera(center, size, angle):
     """dataset_config.box_parametrization_to_corners for ScanNet (datasets/scannet.py:168-171 ->
     utils/box_util.py:294-358): 8 corners in the camera frame, reference vertex order."""
     cam = torch.stack((center[..., 0], -center[..., 2], center[..., 1]), dim=-1)
     hl, hw, hh = size[..., 0:1] * 0.5, size[..., 1:2] * 0.5, size[..., 2:3] * 0.5
-    sx = size.new_tensor([1., 1., -1., -1., 1., 1., -1., -1.])
-    sy = size.new_tensor([1., 1., 1., 1., -1., -1., -1., -1.])
-    sz = size.new_tensor([1., -1., -1., 1., 1., -1., -1., 1.])
+    sx, sy, sz = _corner_signs(size)
     local = torch.stack((hl * sx, hh * sy, hw * sz), dim=-1)
     c, s = torch.cos(angle), torch.sin(angle)
     zero, one = torch.zeros_like(c), torch.ones_like(c)
