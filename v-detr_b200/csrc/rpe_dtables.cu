@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
 
     // ---- phase 3: accumulate.  Warps claim chunks of CHUNK sorted entries dynamically (the cost per entry varies
     // a lot between long and short segments, so a static split leaves most warps idle at the barrier).
-    constexpr int CHUNK = 256;
+    constexpr int CHUNK = 512;
     const int total = s_total;
     float acc[32];
 #pragma unroll
@@ -349,6 +349,34 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P
             vq_n = sgeo[ql * 2]; rot_n = sgeo[ql * 2 + 1];
             kx_n = __ldg(xrow + kl);
             ds_n = __ldg(dbase + (size_t)ql * P.nKp + kl);
+          }
+        }
+        // fast path: the whole step is one long segment (the common case after sorting) -> FFMA straight into
+        // the lane-private accumulators, no staging of the 32 products
+        {
+          const unsigned livemask = __ballot_sync(0xffffffffu, live);
+          const int lead = __ffs(livemask) - 1;
+          const int b0 = __shfl_sync(0xffffffffu, bin, lead < 0 ? 0 : lead);
+          const bool uniform = livemask != 0u && __all_sync(0xffffffffu, !live || bin == b0);
+          if (uniform && (b0 == cur_bin || __popc(livemask) >= 12)) {
+            if (b0 != cur_bin) {
+              if (cur_bin >= 0) flush(cur_bin);
+              cur_bin = b0;
+            }
+            if (live) {
+              const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
+              const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+              const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
+              const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
+              const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
+                acc[k * 4 + 0] = fmaf(w, ds.x, acc[k * 4 + 0]); acc[k * 4 + 1] = fmaf(w, ds.y, acc[k * 4 + 1]);
+                acc[k * 4 + 2] = fmaf(w, ds.z, acc[k * 4 + 2]); acc[k * 4 + 3] = fmaf(w, ds.w, acc[k * 4 + 3]);
+              }
+            }
+            continue;
           }
         }
         float c[32];
