@@ -184,7 +184,7 @@ def main():
         line = {"impl": "reference", "metric": "scenes/sec fwd+bwd, 4096 keys x 1024 queries x 8 dec layers", "value": val,
                 "unit": "scenes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * sec_per_scene,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, workload=config["workload"] + " [CPU sample: 1 scene, 1 of 8 layers fwd+bwd, x8]"),
+                "config": config,
                 "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": threads, "kind": "port",
                                  "sample": f"1 scene, 1 decoder layer + proposal stage fwd+bwd ({sample_s:.1f} s), "
                                            f"extrapolated to 8 layers; host has {cores} cores, {threads} threads used"},
