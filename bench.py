@@ -7,7 +7,7 @@
 Workload (config C3 of BASELINE.md at N=1, C4 at N=8): per GPU a batch of 8 synthetic ScanNet-shaped scenes,
 4096 key tokens x 1024 queries x 8 decoder layers, train mode, forward + backward through the whole
 TransformerDecoder (fused Vertex-RPE cross attention, fused self attention, FFN, box heads) + AdamW step; for
-N > 1 the model is wrapped in DistributedDataParallel (one NCCL gradient all-reduce, overlapped with backward);
+N > 1 all gradients live in one flat buffer that is summed with ONE NCCL all-reduce per step (parallel.py);
 scenes are independent, so the batch is sharded over ranks with no other collective (weak scaling).
 
 One JSON line on rank 0.  `value` = scenes/s with the step's inputs already resident in HBM; `e2e` = the same
@@ -202,6 +202,7 @@ def main():
     ddp = world > 1
     if ddp:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # the all-reduce is captured in a CUDA graph
         dist.init_process_group("nccl", device_id=dev)
     import vdetr_b200._C as C
 
@@ -209,10 +210,11 @@ def main():
     for p in dec.pointcls_heads.parameters():        # used by ModelVDETR.forward, not by the decoder itself
         p.requires_grad_(False)
     from vdetr_b200 import parallel
-    model = parallel.wrap_data_parallel(dec, dev)        # DDP: one bucketed NCCL gradient all-reduce per step
-    use_graph = not a.no_graph and not ddp and not a.profile
+    model = dec
+    use_graph = not a.no_graph and not a.profile
     opt = torch.optim.AdamW([p for p in dec.parameters() if p.requires_grad], lr=1e-5, weight_decay=0.1, fused=True,
                             capturable=use_graph)
+    gsync = parallel.FlatGradAllReduce(dec.parameters())    # all .grad are views of one buffer: ONE NCCL all-reduce / step
     lo, hi = parallel.shard_range(a.batch * world, rank, world)     # scenes [lo, hi) of the global batch live on this rank
     assert hi - lo == a.batch
     host = synth_scene(a.batch, NK, lo, torch)
@@ -226,8 +228,9 @@ def main():
                        enc_box_predictions={"center_normalized": inp["center_normalized"],
                                             "size_normalized": inp["size_normalized"]}, enc_box_features=inp["feat"])
         loss = synthetic_loss(out, weights)
-        opt.zero_grad(set_to_none=True)
+        gsync.zero_()
         loss.backward()
+        gsync.sync_()
         opt.step()
         return loss.item() if fetch_loss else loss
 
@@ -275,7 +278,6 @@ def main():
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
             static_loss = step(static_in, False)
         torch.cuda.synchronize()

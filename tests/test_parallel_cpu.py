@@ -47,6 +47,18 @@ def _worker(rank, world, port, q):
             if p.grad is not None:
                 acc[n] = acc.get(n, 0) + p.grad / world
     err = max(float((got[n] - acc[n]).abs().max() / (acc[n].abs().max() + 1e-12)) for n in got)
+    # the flat single-all-reduce path used by bench.py must give the same averaged gradients
+    flat_model = odt.OracleDecoder(num_layers=1, num_queries=8, dropout=0.0, mlp_dropout=0.0).eval()
+    flat_model.load_state_dict(dec.state_dict())
+    for p_ in flat_model.pointcls_heads.parameters():
+        p_.requires_grad_(False)
+    sync = parallel.FlatGradAllReduce(flat_model.parameters())
+    sync.zero_()
+    run(flat_model, slice(lo, hi)).backward()
+    sync.sync_()
+    err2 = max(float((p_.grad - acc[n]).abs().max() / (acc[n].abs().max() + 1e-12))
+               for n, p_ in flat_model.named_parameters() if p_.requires_grad and n in acc)
+    err = max(err, err2)
     t = parallel.max_over_ranks(10.0 + rank)
     q.put((rank, err, t, (lo, hi)))
     dist.destroy_process_group()

@@ -34,3 +34,32 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class FlatGradAllReduce:
+    """ONE all-reduce of all gradients per step (the "single NCCL all-reduce on gradients" of the north star).
+
+    All ``.grad`` tensors are views into one flat buffer, so synchronisation is a single collective on a static
+    address -- which also makes the whole step (forward, backward, this all-reduce, optimizer) capturable in one CUDA
+    graph.  The decoder's gradients are 46.5 MB fp32; on NVLink 5 that is a few hundred microseconds against a
+    ~100 ms step, so overlapping it with backward (what DistributedDataParallel's buckets do) buys nothing here.
+    """
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def sync_(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(dist.get_world_size())
+        return self.flat
