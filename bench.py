@@ -163,7 +163,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of one step to this file and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying a captured CUDA graph")
+    ap.add_argument("--max-seconds", type=int, default=480, help="hard watchdog: abort instead of hanging")
     a = ap.parse_args()
+    import signal
+
+    def _abort(signum, frame):
+        sys.stderr.write("bench.py: watchdog expired, aborting\n")
+        os._exit(3)
+    signal.signal(signal.SIGALRM, _abort)
+    signal.alarm(a.max_seconds)
 
     import torch
     rank = int(os.environ.get("RANK", 0))
@@ -223,14 +231,18 @@ def main():
     weights = loss_weights(torch, NQ, NLAYERS, dev)
     resident = {k: v.to(dev) for k, v in host.items()}
 
-    def step(inp, fetch_loss):
+    def fwd_bwd(inp):
         out, _ = model(None, inp["feat"], inp["xyz"], inp["xyz"], [inp["mins"], inp["maxs"]], query_pos=None,
                        enc_box_predictions={"center_normalized": inp["center_normalized"],
                                             "size_normalized": inp["size_normalized"]}, enc_box_features=inp["feat"])
         loss = synthetic_loss(out, weights)
         gsync.zero_()
         loss.backward()
-        gsync.sync_()
+        return loss
+
+    def step(inp, fetch_loss):
+        loss = fwd_bwd(inp)
+        gsync.sync_()          # N > 1: the single NCCL all-reduce of the flat gradient buffer
         opt.step()
         return loss.item() if fetch_loss else loss
 
@@ -277,19 +289,25 @@ def main():
                 step(static_in, False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # two graphs with the (eager, one launch) NCCL all-reduce between them: forward+backward | optimizer
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            static_loss = step(static_in, False)
+            static_loss = fwd_bwd(static_in)
+        graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_opt, pool=graph.pool()):
+            opt.step()
         torch.cuda.synchronize()
 
         def graph_step():
             graph.replay()
+            gsync.sync_()
+            graph_opt.replay()
             return static_loss
 
         def e2e_graph_step():
             for k_, v_ in pinned.items():
                 static_in[k_].copy_(v_, non_blocking=True)
-            graph.replay()
+            graph_step()
             return static_loss.item()
     if a.profile:
         from torch.profiler import profile, ProfilerActivity
@@ -328,7 +346,8 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     # fused forward kernel: algorithmic FLOPs = 4*H*nQ*nK*hd per layer-scene (QK^T + PV), BASELINE.md section 3
     flops_fwd = 4.0 * 4 * NQ * NK * 64 * a.batch
-    config["launch"] = "CUDA graph replay of the whole step" if graph is not None else "eager launches"
+    config["launch"] = ("CUDA graph replay (fwd+bwd graph, eager NCCL all-reduce, optimizer graph)" if graph is not None
+                        else "eager launches")
     fwd_ms = tot[0] / max(cnt[0], 1)
     achieved = flops_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
     evals = 8.0 * NQ * NK * a.batch                            # vertex evaluations per fused-forward launch
