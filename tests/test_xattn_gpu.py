@@ -174,7 +174,7 @@ def test_tc_backward_is_invariant_to_gradient_magnitude():
 
 
 def test_dtables_op_matches_oracle():
-    """dTables kernel alone (fp32 dS in): tight tolerance against the fp64 oracle."""
+    """dTables kernel alone (dense fp32 dS in, converted to the scaled fp16 rows the kernel consumes) against the fp64 oracle."""
     from vdetr_b200 import ops
     I = _core_inputs(31, 2, 37, 150, 1, False, far=0.2)
     rs = np.random.RandomState(5)
@@ -182,11 +182,11 @@ def test_dtables_op_matches_oracle():
     want = ora.rpe_bias_backward_tables(I["ref"], I["xyz"], I["tables"].shape, ds.astype(np.float64))
     got = ops.rpe_bias_grad_tables(torch.from_numpy(I["xyz"]).cuda(), torch.from_numpy(I["ref"]).cuda(), None,
                                    torch.from_numpy(I["tables"]).cuda(), torch.from_numpy(ds).cuda()).cpu().numpy()
-    _cmp(got, want, 2e-4, 1e-6, "dtables")
+    _cmp(got, want, 5e-4, 1e-6, "dtables")          # dS enters the kernel as scaled fp16 (2^-11 relative)
     Ir = _core_inputs(32, 1, 20, 90, 1, True)
     ds = rs.standard_normal((1, 4, 20, 90)).astype(np.float32)
     want = ora.rpe_bias_backward_tables(Ir["ref"], Ir["xyz"], Ir["tables"].shape, ds.astype(np.float64), Ir["angle"])
     got = ops.rpe_bias_grad_tables(torch.from_numpy(Ir["xyz"]).cuda(), torch.from_numpy(Ir["ref"]).cuda(),
                                    torch.from_numpy(Ir["angle"]).cuda(), torch.from_numpy(Ir["tables"]).cuda(),
                                    torch.from_numpy(ds).cuda()).cpu().numpy()
-    _cmp(got, want, 2e-4, 1e-6, "dtables rotated")
+    _cmp(got, want, 5e-4, 1e-6, "dtables rotated")

@@ -1,513 +1,601 @@
 // dTables[i][z][y][x][h] = sum_{b,q,k} dS[b,q,k,h] * w_{i,corner}(b,q,k)        (adjoint of the bias gather;
 // the reference gets it from grid_sampler_3d_backward's global atomics, vdetr_transformer.py:727-731).
 //
-// The scatter is 8 vertices x 8 corners x 4 heads = 256 adds per (query,key) pair into 32,000 cells of which
-// a few hundred are hot, so neither global nor shared atomics per contribution are affordable (shared fp32
-// atomicAdd is a CAS loop on sm_100).  Scheme:
-//   * a warp owns one (scene, query, vertex) task and walks the keys 32 at a time (lane = key, Morton order);
-//   * every lane writes its 32 products w_corner * dS_h to a private row of a 32x33 scratch tile;
-//   * lanes are grouped by table cell ("bin" = floor of the pixel coordinate, usually 1-4 groups per step);
-//     for each group lane j sums column j over the group's rows  ->  the group's 32 (corner,head) totals;
-//   * the totals go into a 4-entry warp-level cache (tags are warp-uniform registers, lane j holds value j),
-//     hot bins therefore stay in registers across many steps; evictions go to a per-CTA fp32 copy of the
-//     tables in shared memory (CAS atomics, rare), which is added to global memory once per CTA at the end.
+// The scatter is 8 vertices x 8 corners x 4 heads = 256 adds per (query,key) pair into 8 x 1000 cells of which a
+// few hundred are hot.  Shared-memory fp32 atomics are CAS loops on sm_100 and a warp-wide reduction of 32
+// accumulators costs ~120 instructions, so the kernel is organised to make reductions rare:
+//
+//   unit    = (scene, 16 Morton-adjacent queries, 512 Morton-adjacent keys) = 8192 pairs, resident in shared memory
+//   phase A   per pair, ONCE for all 8 vertices: the 6 axis transforms of an axis-aligned box (x+,x-,y+,y-,z+,z-)
+//             -> a 16-byte record (6 x 16-bit interpolation fractions, 6 x 4-bit cell indices) + dS of the 4 heads
+//             as the scaled fp16 the backward kernel already wrote for the dQ/dK GEMMs (8 bytes);
+//   per vertex (bins = table cells, independent of query and key, so the whole unit sorts together):
+//     B1/B2/B3  histogram, scan, counting-sort of the pair ids by cell (run-aggregated integer atomics);
+//     B4        every warp walks a contiguous chunk of the sorted list, 32 pairs per step.  Inside a segment every
+//               lane FFMA2s its 8 corners x 4 heads into 32 private registers; when the cell changes the 32 x 32
+//               partial sums are transposed/reduced with shuffles and sent with ONE RED.ADD.F32 per lane to a
+//               per-CTA private copy of the (zero-padded, (n+2)^3) table in global memory (L2 resident).  Segments
+//               shorter than TINY pairs skip the registers: lane = (corner, head), pairs broadcast one by one.
+//   a last kernel sums the private copies, drops the padding cells and undoes the fp16 gradient scale.
+//
+// Boxes that are not axis aligned (rotated `object_coords` boxes, arbitrary vertex sets) use the same records: their
+// 3 transforms are recomputed per vertex into the slots that vertex reads (phase B0).
 #include "rpe_internal.h"
 #include "rpe_fast.cuh"
-#include <stdlib.h>
 
-namespace {
+namespace dt3 {
 
-constexpr int DT_WARPS = 16;
-constexpr int DT_THREADS = DT_WARPS * 32;
-constexpr int CACHE = 8;                       // warp-level cache entries (bins held in registers)
-
-struct DtParams {
-  int B, nQ, nK, nQp, nKp, n;
-  float log_scale, c1, c0;
-  const float4* xyz4;       // [B][nKp]
-  const float4* geo;        // [B][nQp][9]
-  const float4* ds4;        // [B][nQp][nKp]  (dS of the 4 heads of one (query,key) pair)
-  float* dtables;           // [8][n^3][4], zero-initialised by the caller
-};
-
-__device__ __forceinline__ void flush_slot(float* stab, int tag, float acc, int lane, int vert, int n) {
-  if (tag < 0) return;
-  const int n0x = (tag & 31) - 2, n0y = ((tag >> 5) & 31) - 2, n0z = ((tag >> 10) & 31) - 2;
-  const int corner = lane >> 2, h = lane & 3;
-  const int x = n0x + (corner & 1), y = n0y + ((corner >> 1) & 1), z = n0z + (corner >> 2);
-  if ((unsigned)x < (unsigned)n && (unsigned)y < (unsigned)n && (unsigned)z < (unsigned)n && acc != 0.f)
-    atomicAdd(stab + ((((size_t)vert * n + z) * n + y) * n + x) * 4 + h, acc);
-}
-
-// sum of column `lane` of the 32x33 scratch tile over the rows selected by `mask` (fully unrolled: the 32
-// predicated loads are independent, so their latency overlaps)
-__device__ __forceinline__ float column_sum(const float* my, int lane, unsigned mask) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int l = 0; l < 32; l += 4) {
-    if (mask & (1u << l)) s0 += my[l * 33 + lane];
-    if (mask & (2u << l)) s1 += my[(l + 1) * 33 + lane];
-    if (mask & (4u << l)) s2 += my[(l + 2) * 33 + lane];
-    if (mask & (8u << l)) s3 += my[(l + 3) * 33 + lane];
-  }
-  return (s0 + s1) + (s2 + s3);
-}
-
-__global__ void __launch_bounds__(DT_THREADS, 1) rpe_dtables_kernel(DtParams P) {
-  extern __shared__ float dsm[];
-  const int ncell4 = 8 * P.n * P.n * P.n * 4;
-  float* stab = dsm;                                   // [8][n^3][4]
-  float* scratch = dsm + ncell4;                       // [DT_WARPS][32][33]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < ncell4; i += DT_THREADS) stab[i] = 0.f;
-  __syncthreads();
-  float* my = scratch + warp * 32 * 33;
-  const int sx = 16, sy = 16 * P.n, sz = 16 * P.n * P.n;
-
-  const long tasks = (long)P.B * P.nQ * 8;
-  const long gw = (long)blockIdx.x * DT_WARPS + warp, nw = (long)gridDim.x * DT_WARPS;
-  for (long t = gw; t < tasks; t += nw) {
-    const int vert = (int)(t & 7);
-    const long bq = t >> 3;
-    const int q = (int)(bq % P.nQ), b = (int)(bq / P.nQ);
-    const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
-    const float* vv = reinterpret_cast<const float*>(g + 2);
-    const float vx = __ldg(vv + vert * 3), vy = __ldg(vv + vert * 3 + 1), vz = __ldg(vv + vert * 3 + 2);
-    const float4 rot = __ldg(g + 8);
-    const float4* xrow = P.xyz4 + (size_t)b * P.nKp;
-    const float4* drow = P.ds4 + ((size_t)b * P.nQp + q) * P.nKp;
-
-    int tag[CACHE];
-    float acc[CACHE];
-#pragma unroll
-    for (int c = 0; c < CACHE; ++c) { tag[c] = -1; acc[c] = 0.f; }
-    int victim = 0;
-
-    // software prefetch of the next step's inputs
-    float4 kx_n = make_float4(0.f, 0.f, 0.f, 0.f), ds_n = kx_n;
-    if (lane < P.nK) { kx_n = __ldg(xrow + lane); ds_n = __ldg(drow + lane); }
-    for (int k0 = 0; k0 < P.nK; k0 += 32) {
-      const int key = k0 + lane;
-      const float4 kx = kx_n, ds = ds_n;
-      if (key + 32 < P.nK) { kx_n = __ldg(xrow + key + 32); ds_n = __ldg(drow + key + 32); }
-      int bin = -1;
-      if (key < P.nK && (ds.x != 0.f || ds.y != 0.f || ds.z != 0.f || ds.w != 0.f)) {
-        const float dx = vx - kx.x, dy = vy - kx.y, dz = vz - kx.z;
-        const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-        const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
-        const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
-        const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
-        bin = ((az.n0 + 2) << 10) | ((ay.n0 + 2) << 5) | (ax.n0 + 2);
-        float* row = my + lane * 33;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float w = ((c & 4) ? az.w1 : az.w0) * ((c & 2) ? ay.w1 : ay.w0) * ((c & 1) ? ax.w1 : ax.w0);
-          row[c * 4 + 0] = w * ds.x; row[c * 4 + 1] = w * ds.y; row[c * 4 + 2] = w * ds.z; row[c * 4 + 3] = w * ds.w;
-        }
-      }
-      __syncwarp();
-      unsigned rem = __ballot_sync(0xffffffffu, bin >= 0);
-      // 1. bins already cached: one masked column sum per cache entry that is hit
-#pragma unroll
-      for (int c = 0; c < CACHE; ++c) {
-        const unsigned hit = __ballot_sync(0xffffffffu, bin == tag[c]) & rem;   // tag -1 never matches a live bin
-        if (hit) { acc[c] += column_sum(my, lane, hit); rem &= ~hit; }
-      }
-      // 2. new bins: evict round-robin
-      while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, bin == bsel) & rem;
-        rem &= ~grp;
-        const float s = column_sum(my, lane, grp);
-#pragma unroll
-        for (int c = 0; c < CACHE; ++c)
-          if (c == victim) { flush_slot(stab, tag[c], acc[c], lane, vert, P.n); tag[c] = bsel; acc[c] = s; }
-        victim = (victim + 1) & (CACHE - 1);
-      }
-      __syncwarp();
-    }
-#pragma unroll
-    for (int c = 0; c < CACHE; ++c) flush_slot(stab, tag[c], acc[c], lane, vert, P.n);
-  }
-  __syncthreads();
-  for (int i = tid; i < ncell4; i += DT_THREADS) {
-    const float v = stab[i];
-    if (v != 0.f) atomicAdd(P.dtables + i, v);
-  }
-}
-
-}  // namespace
-
-// =====================================================================================================
-// Version 2: bucket the evaluations by table cell first, then accumulate in registers.
-//
-// A unit is (scene b, vertex i, block of 32 queries, chunk of 1024 keys) = 32,768 evaluations.
-//   phase 1  every thread computes the bin (floor of the 3 pixel coordinates) of its evaluations, stores it and
-//            counts it in a shared-memory histogram (native integer atomics);
-//   phase 2  exclusive scan of the histogram, then a counting-sort scatter of the evaluation ids;
-//   phase 3  each warp walks a contiguous range of the sorted list, 32 evaluations per step (lane = evaluation).
-//            Sorted order means a whole step normally belongs to ONE bin, so every lane simply accumulates its
-//            8 corners x 4 heads into 32 private registers; only when the bin changes are the 32x32 partial sums
-//            reduced across lanes (transpose through a scratch tile) and added to a per-CTA fp32 copy of table i.
-// Per evaluation this costs ~4 warp-instructions instead of ~35 for the cache-based version above.
-namespace v2 {
-
-constexpr int QB = 32, KC = 1024, UNIT = QB * KC;          // evaluations per unit
+constexpr int QB = 16, KC = 512, NP = QB * KC;       // pairs per unit
 constexpr int THREADS = 512, WARPS = THREADS / 32;
+constexpr int TINY = 8;                              // segments shorter than this use the broadcast mode
+constexpr int MAX_N = 12;                            // cell index + 1 must fit 4 bits with 15 = invalid
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float FRAC_Q = 65535.0f, FRAC_INV = 1.0f / 65535.0f;
+static_assert(KC == THREADS, "phase A maps one thread to one key of the chunk");
 
 struct Params {
-  int B, nQ, nK, nQp, nKp, n, R;     // R = n + 1 values of n0 per axis that can contribute: [-1, n-1]
-  int qblocks, kchunks, units;
+  int B, nQ, nK, nQp, nKp, n, R, P3;      // R = n + 1 base cells per axis, P3 = n + 2 padded table points per axis
+  int qblocks, kchunks, units, dense_scale;
   float log_scale, c1, c0;
-  const float4* xyz4;
-  const float4* geo;
-  const float4* ds4;
-  float* dtables;
+  const float4* xyz4;                     // [B][nKp]
+  const float4* geo;                      // [B][nQp][9]
+  const __half* dsb;                      // [(b*nQp + q)*4 + h][nKp]   scale * dS
+  const int* qperm;                       // [B][nQ] Morton order of the queries
+  const unsigned* absmax_bits;            // -> scale
+  float* priv;                            // [gridDim.x][8][P3^3][4]
 };
 
-__device__ __forceinline__ int axis_n0(float d, float ls, float c1, float c0, int n) {
+__device__ __forceinline__ float scale_of(unsigned bits, int dense) {
+  if (!dense) return vdetr_grad_scale(bits);
+  const float m = __uint_as_float(bits);
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
+  float e = floorf(log2f(16384.f / m));
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
+
+// one axis: cell index + 1 in [0, n] (15 = both corners outside the table) and the 16-bit fraction
+__device__ __forceinline__ void axis_rec(float d, float ls, float c1, float c0, int n, unsigned& nib, unsigned& frac) {
   float t = tc::lg2_approx(fmaf(fabsf(d), ls, 1.0f)) * c1;
   float ts = copysignf(t, d);
   ts = fminf(fmaxf(ts, -c0 - 1.5f), (float)n - c0 + 0.5f);
-  float r = ((ts + c0) - 0.5f) + rpe::MAGIC;
-  return __float_as_int(r) - rpe::MAGIC_BITS;
+  const float p = ts + c0;
+  const float r = (p - 0.5f) + rpe::MAGIC;
+  const float f = p - (r - rpe::MAGIC);
+  const int n0 = __float_as_int(r) - rpe::MAGIC_BITS;
+  nib = ((unsigned)(n0 + 1) <= (unsigned)n) ? (unsigned)(n0 + 1) : 15u;
+  frac = __float2uint_rn(fminf(fmaxf(f, 0.f), 1.f) * FRAC_Q);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) rpe_dtables_sorted_kernel(Params P) {
+// vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4:(+,+,+) 5:(+,-,+) 6:(-,-,+) 7:(-,+,+)
+// -> slot selector (0 = '+', 1 = '-') per axis
+__device__ __forceinline__ void vertex_slots(int v, int& xs, int& ys, int& zs) {
+  xs = ((v & 3) == 2 || (v & 3) == 3) ? 1 : 0;
+  ys = ((v & 3) == 1 || (v & 3) == 2) ? 1 : 0;
+  zs = (v < 4) ? 1 : 0;
+}
+
+struct Smem {
+  uint4* recs;        // [NP]  x: fx+ | fx- << 16   y: fy+ | fy-   z: fz+ | fz-   w: nibbles x+,x-,y+,y-,z+,z- (4 bits each)
+  uint2* dsv;         // [NP]  4 x fp16 scaled dS
+  uint16_t* sorted;   // [NP]
+  int* hist;          // [nbins]   counts, then scatter cursors      } this region doubles as the key xyz
+  int* offs;          // [nbins+1] exclusive scan                    } staging buffer during phase A
+  float4* sxyz;       // [KC] (aliases hist/offs)
+  float4* sgeo;       // [QB][2]
+  int* sq;            // [QB] query index (or -1), [QB] slow flags, misc
+};
+
+__host__ __device__ inline size_t region_bytes(int n) {
+  const size_t nbins = (size_t)(n + 1) * (n + 1) * (n + 1);
+  size_t r = (2 * nbins + 1 + 3) / 4 * 16;
+  return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
+}
+__host__ __device__ inline size_t smem_bytes(int n) {
+  return (size_t)NP * 16 + (size_t)NP * 8 + (size_t)NP * 2 + region_bytes(n) + QB * 2 * 16 + 64 * 4;
+}
+
+// transposed reduction: on return lane j holds sum over lanes of acc[j]
+__device__ __forceinline__ float transpose_reduce(float (&a)[32], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = up ? a[i] : a[i + 16], keep = up ? a[i + 16] : a[i];
+      a[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
+      a[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? a[i] : a[i + 4], keep = up ? a[i + 4] : a[i];
+      a[i] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? a[i] : a[i + 2], keep = up ? a[i + 2] : a[i];
+      a[i] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+  }
+  const bool up = lane & 1;
+  const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+  return keep + __shfl_xor_sync(FULL, send, 1);
+}
+
+__device__ __forceinline__ float2 ffma2(float w, float2 d, float2 c) {
+  unsigned long long rd, rc, ra, rb;
+  const float2 ww = make_float2(w, w);
+  ra = *reinterpret_cast<const unsigned long long*>(&ww);
+  rb = *reinterpret_cast<const unsigned long long*>(&d);
+  rc = *reinterpret_cast<const unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+// run-aggregated shared-memory counter update: lanes with equal, adjacent `bin` form a run; the run head adds the
+// run length.  Returns the value before the add (broadcast to the run) and this lane's rank inside its run.
+__device__ __forceinline__ int run_add(int* counters, int bin, int lane, int& rank, bool want_old) {
+  const int prev = __shfl_up_sync(FULL, bin, 1);
+  const bool head = lane == 0 || bin != prev;
+  const unsigned heads = __ballot_sync(FULL, head);
+  const unsigned below = heads & (FULL >> (31 - lane));
+  const int hl = 31 - __clz(below);
+  const unsigned above = (hl == 31) ? 0u : (heads & ~((2u << hl) - 1u));
+  const int end = above ? (__ffs(above) - 1) : 32;
+  rank = lane - hl;
+  int old = 0;
+  if (head && bin >= 0) old = atomicAdd(counters + bin, end - hl);
+  if (want_old) old = __shfl_sync(FULL, old, hl);
+  return old;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P) {
   extern __shared__ __align__(16) uint8_t sm[];
+  Smem S;
+  S.recs = reinterpret_cast<uint4*>(sm);
+  S.dsv = reinterpret_cast<uint2*>(sm + (size_t)NP * 16);
+  S.sorted = reinterpret_cast<uint16_t*>(sm + (size_t)NP * 24);
+  uint8_t* region = sm + (size_t)NP * 26;
   const int nbins = P.R * P.R * P.R;
-  const int nbins_pad = (2 * nbins + 1 + 3) & ~3;                           // ints, keeps what follows 16-B aligned
-  uint16_t* binbuf = reinterpret_cast<uint16_t*>(sm);                       // [UNIT]
-  uint16_t* sorted = binbuf + UNIT;                                         // [UNIT]
-  int* hist = reinterpret_cast<int*>(sorted + UNIT);                        // [nbins]  counts, then cursors
-  int* offs = hist + nbins;                                                 // [nbins + 1] exclusive scan
-  float* stab = reinterpret_cast<float*>(hist + nbins_pad);                 // [n^3 * 4] table of the current vertex
-  float4* sgeo = reinterpret_cast<float4*>(stab + P.n * P.n * P.n * 4);     // [QB][2]: (vx,vy,vz,valid) (cos,sin,0,0)
-  float* scratch = reinterpret_cast<float*>(sgeo + QB * 2);                 // [WARPS][32][33]
-  __shared__ int s_total;
-  __shared__ int s_next;          // phase 3: next unclaimed chunk of the sorted list
+  S.hist = reinterpret_cast<int*>(region);
+  S.offs = S.hist + nbins;
+  S.sxyz = reinterpret_cast<float4*>(region);
+  S.sgeo = reinterpret_cast<float4*>(region + region_bytes(P.n));
+  S.sq = reinterpret_cast<int*>(S.sgeo + QB * 2);
+  int* s_slow = S.sq + QB;          // [QB]
+  int* s_misc = S.sq + 2 * QB;      // [1] number of sorted entries, [2..2+WARPS] scan scratch
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ncell4 = P.n * P.n * P.n * 4;
-  float* my = scratch + warp * 32 * 33;
-  const int sx = 16, sy = 16 * P.n, sz = 16 * P.n * P.n;
+  const int cells_pad = P.P3 * P.P3 * P.P3;
+  float* my_priv = P.priv + (size_t)blockIdx.x * 8 * cells_pad * 4;
+  const int corner = lane >> 2, hsel = lane & 3;
+  const int cz = corner >> 2, cy = (corner >> 1) & 1, cx = corner & 1;
+  // lane-constant affine maps fraction -> weight of this lane's corner along each axis (broadcast mode)
+  const float mzs = cz ? 1.f : -1.f, mzo = cz ? 0.f : 1.f;
+  const float mys = cy ? 1.f : -1.f, myo = cy ? 0.f : 1.f;
+  const float mxs = cx ? 1.f : -1.f, mxo = cx ? 0.f : 1.f;
 
-  // contiguous range of units per CTA, vertex-major, so that the shared table is flushed only a few times
-  const int per = (P.units + gridDim.x - 1) / gridDim.x;
-  const int u_begin = blockIdx.x * per, u_end = min(P.units, u_begin + per);
-  int cur_vert = -1;
-
-  for (int u = u_begin; u < u_end; ++u) {
-    // unit -> (vert, b, qblock, kchunk)
+  for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
     int r = u;
     const int kc = r % P.kchunks; r /= P.kchunks;
-    const int qb = r % P.qblocks; r /= P.qblocks;
-    const int b = r % P.B;
-    const int vert = r / P.B;
+    const int qb = r % P.qblocks;
+    const int b = r / P.qblocks;
     const int q0 = qb * QB, k0 = kc * KC;
 
-    if (vert != cur_vert) {
-      __syncthreads();
-      if (cur_vert >= 0)
-        for (int i = tid; i < ncell4; i += THREADS) {
-          const float v = stab[i];
-          if (v != 0.f) atomicAdd(P.dtables + (size_t)cur_vert * ncell4 + i, v);
-        }
-      __syncthreads();
-      for (int i = tid; i < ncell4; i += THREADS) stab[i] = 0.f;
-      cur_vert = vert;
-    }
-    for (int i = tid; i < nbins; i += THREADS) hist[i] = 0;
+    __syncthreads();                      // previous unit completely done with shared memory
     if (tid < QB) {
-      const int q = q0 + tid;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = make_float4(1.f, 0.f, 0.f, 0.f);
-      if (q < P.nQ) {
+      const int qi = q0 + tid;
+      int q = -1, slow = 0;
+      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+      if (qi < P.nQ) {
+        q = __ldg(P.qperm + (size_t)b * P.nQ + qi);
         const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
-        const float* vv = reinterpret_cast<const float*>(g + 2);
-        a = make_float4(__ldg(vv + vert * 3), __ldg(vv + vert * 3 + 1), __ldg(vv + vert * 3 + 2), 1.f);
-        c = __ldg(g + 8);
+        hi = __ldg(g); lo = __ldg(g + 1);
+        slow = __float_as_int(hi.w) == 0;
       }
-      sgeo[tid * 2] = a; sgeo[tid * 2 + 1] = c;
+      S.sgeo[tid * 2] = hi; S.sgeo[tid * 2 + 1] = lo;
+      S.sq[tid] = q; s_slow[tid] = slow;
+    }
+    {
+      float4 kx = make_float4(1e9f, 1e9f, 1e9f, 0.f);
+      if (k0 + tid < P.nK) kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + tid);
+      S.sxyz[tid] = kx;
     }
     __syncthreads();
-
-    // ---- phase 1: bins + histogram.  e = ql * KC + kl ; a warp covers 32 consecutive keys of one query
-    const float4* xrow = P.xyz4 + (size_t)b * P.nKp + k0;
-    for (int e = tid; e < UNIT; e += THREADS) {
-      const int ql = e >> 10, kl = e & (KC - 1);
-      const float4 vq = sgeo[ql * 2], rot = sgeo[ql * 2 + 1];
-      int bin = 0xFFFF;
-      if (vq.w != 0.f && k0 + kl < P.nK) {
-        const float4 kx = __ldg(xrow + kl);
-        const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
-        const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-        const int nx = axis_n0(tx, P.log_scale, P.c1, P.c0, P.n) + 1;
-        const int ny = axis_n0(ty, P.log_scale, P.c1, P.c0, P.n) + 1;
-        const int nz = axis_n0(dz, P.log_scale, P.c1, P.c0, P.n) + 1;
-        if ((unsigned)nx < (unsigned)P.R && (unsigned)ny < (unsigned)P.R && (unsigned)nz < (unsigned)P.R)
-          bin = (nz * P.R + ny) * P.R + nx;
-      }
-      binbuf[e] = (uint16_t)bin;
-      // warp-aggregated histogram update: the 32 keys of a warp mostly share a bin, and same-address shared
-      // atomics serialise, so one lane per distinct bin adds the group's population
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (bin != 0xFFFF && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
-    }
-    __syncthreads();
-    // ---- phase 2a: exclusive scan (warp 0: each lane owns a contiguous slice of bins), cursors = offsets
-    if (warp == 0) {
-      const int per_lane = (nbins + 31) / 32;
-      const int lo = lane * per_lane, hi = min(nbins, lo + per_lane);
-      int mine = 0;
-      for (int i = lo; i < hi; ++i) mine += hist[i];
-      int x = mine;
+    bool any_slow = false;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      int run = x - mine;
-      for (int i = lo; i < hi; ++i) { const int c = hist[i]; hist[i] = run; offs[i] = run; run += c; }
-      if (lane == 31) { offs[nbins] = x; s_total = x; s_next = 0; }
-    }
-    __syncthreads();
-    // ---- phase 2b: scatter
-    for (int e = tid; e < UNIT; e += THREADS) {
-      const int bin = binbuf[e];
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      const int leader = __ffs(peers) - 1;
-      int base = 0;
-      if (bin != 0xFFFF && lane == leader) base = atomicAdd(&hist[bin], __popc(peers));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (bin != 0xFFFF) sorted[base + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)e;
-    }
-    __syncthreads();
-    // sorted[] no longer needs binbuf's bins except to find segment ends: re-use offs[] for that.
+    for (int ql = 0; ql < QB; ++ql) any_slow = any_slow || (s_slow[ql] != 0 && S.sq[ql] >= 0);
 
-    // ---- phase 3: accumulate.  Warps claim chunks of CHUNK sorted entries dynamically (the cost per entry varies
-    // a lot between long and short segments, so a static split leaves most warps idle at the barrier).
-    constexpr int CHUNK = 512;
-    const int total = s_total;
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    const float4* dbase = P.ds4 + ((size_t)b * P.nQp + q0) * P.nKp + k0;
-    const int corner = lane >> 2, hsel = lane & 3;
-
-    // reduce the 32 lanes' private partial sums of bin `bin` (transpose through the scratch tile) into the table
-    auto flush = [&](int bin) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { my[lane * 33 + j] = acc[j]; acc[j] = 0.f; }
-      __syncwarp();
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int l = 0; l < 32; l += 4) {
-        s0 += my[l * 33 + lane]; s1 += my[(l + 1) * 33 + lane];
-        s2 += my[(l + 2) * 33 + lane]; s3 += my[(l + 3) * 33 + lane];
-      }
-      __syncwarp();
-      const float tot = (s0 + s1) + (s2 + s3);
-      const int bx = bin % P.R - 1, by = (bin / P.R) % P.R - 1, bz = bin / (P.R * P.R) - 1;
-      const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
-      if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && tot != 0.f)
-        atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, tot);
-    };
-
-    for (;;) {
-      int c0 = 0;
-      if (lane == 0) c0 = atomicAdd(&s_next, CHUNK);
-      c0 = __shfl_sync(0xffffffffu, c0, 0);
-      if (c0 >= total) break;
-      const int c1 = min(total, c0 + CHUNK);
-      int cur_bin = -1;
-      // software pipeline: the gathers of step s+1 are in flight while step s is accumulated
-      int bin_n = -1;
-      float4 vq_n = make_float4(0.f, 0.f, 0.f, 0.f), rot_n = vq_n, kx_n = vq_n, ds_n = vq_n;
-      {
-        const int p = c0 + lane;
-        if (p < c1) {
-          const int e = sorted[p];
-          bin_n = binbuf[e];
-          const int ql = e >> 10, kl = e & (KC - 1);
-          vq_n = sgeo[ql * 2]; rot_n = sgeo[ql * 2 + 1];
-          kx_n = __ldg(xrow + kl);
-          ds_n = __ldg(dbase + (size_t)ql * P.nKp + kl);
-        }
-      }
-      for (int p0 = c0; p0 < c1; p0 += 32) {
-        const int bin = bin_n;
-        const bool live = bin >= 0;
-        const float4 vq = vq_n, rot = rot_n, kx = kx_n, ds = ds_n;
-        bin_n = -1;
-        {
-          const int p = p0 + 32 + lane;
-          if (p < c1) {
-            const int e = sorted[p];
-            bin_n = binbuf[e];
-            const int ql = e >> 10, kl = e & (KC - 1);
-            vq_n = sgeo[ql * 2]; rot_n = sgeo[ql * 2 + 1];
-            kx_n = __ldg(xrow + kl);
-            ds_n = __ldg(dbase + (size_t)ql * P.nKp + kl);
+    // ---- phase A: records.  One query row (512 keys) per iteration, thread = key.
+    {
+      const float4 kx = S.sxyz[tid];
+      const bool kvalid = k0 + tid < P.nK;
+#pragma unroll 2
+      for (int ql = 0; ql < QB; ++ql) {
+        const int q = S.sq[ql];
+        uint4 rec = make_uint4(0u, 0u, 0u, 0x00FFFFFFu);
+        uint2 dv = make_uint2(0u, 0u);
+        if (q >= 0 && kvalid) {
+          const __half* dp = P.dsb + ((size_t)b * P.nQp + q) * 4 * P.nKp + k0 + tid;
+          const unsigned short d0 = __ldg(reinterpret_cast<const unsigned short*>(dp));
+          const unsigned short d1 = __ldg(reinterpret_cast<const unsigned short*>(dp + P.nKp));
+          const unsigned short d2 = __ldg(reinterpret_cast<const unsigned short*>(dp + 2 * (size_t)P.nKp));
+          const unsigned short d3 = __ldg(reinterpret_cast<const unsigned short*>(dp + 3 * (size_t)P.nKp));
+          dv = make_uint2((unsigned)d0 | ((unsigned)d1 << 16), (unsigned)d2 | ((unsigned)d3 << 16));
+          if (!s_slow[ql]) {
+            const float4 hi = S.sgeo[ql * 2], lo = S.sgeo[ql * 2 + 1];
+            unsigned nxp, nxm, nyp, nym, nzp, nzm, fxp, fxm, fyp, fym, fzp, fzm;
+            axis_rec(hi.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxp, fxp);
+            axis_rec(lo.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxm, fxm);
+            axis_rec(hi.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nyp, fyp);
+            axis_rec(lo.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nym, fym);
+            axis_rec(hi.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzp, fzp);
+            axis_rec(lo.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzm, fzm);
+            rec.x = fxp | (fxm << 16); rec.y = fyp | (fym << 16); rec.z = fzp | (fzm << 16);
+            rec.w = nxp | (nxm << 4) | (nyp << 8) | (nym << 12) | (nzp << 16) | (nzm << 20);
           }
         }
-        // fast path: the whole step is one long segment (the common case after sorting) -> FFMA straight into
-        // the lane-private accumulators, no staging of the 32 products
-        {
-          const unsigned livemask = __ballot_sync(0xffffffffu, live);
-          const int lead = __ffs(livemask) - 1;
-          const int b0 = __shfl_sync(0xffffffffu, bin, lead < 0 ? 0 : lead);
-          const bool uniform = livemask != 0u && __all_sync(0xffffffffu, !live || bin == b0);
-          if (uniform && (b0 == cur_bin || __popc(livemask) >= 12)) {
-            if (b0 != cur_bin) {
-              if (cur_bin >= 0) flush(cur_bin);
-              cur_bin = b0;
-            }
-            if (live) {
-              const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
-              const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-              const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
-              const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
-              const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
+        S.recs[ql * KC + tid] = rec;
+        S.dsv[ql * KC + tid] = dv;
+      }
+    }
+    __syncthreads();                      // records complete; the xyz staging area becomes hist / offs
+
+    for (int vert = 0; vert < 8; ++vert) {
+      int xs, ys, zs;
+      vertex_slots(vert, xs, ys, zs);
+      const int shx = 16 * xs, shy = 16 * ys, shz = 16 * zs;                 // fraction shifts
+      const int nbx = 4 * xs, nby = 8 + 4 * ys, nbz = 16 + 4 * zs;           // nibble shifts
+
+      // ---- B0: boxes that are not axis aligned: this vertex's own 3 transforms go into the slots it reads
+      if (any_slow) {
+        for (int ql = 0; ql < QB; ++ql) {
+          if (!s_slow[ql] || S.sq[ql] < 0) continue;                         // block-uniform
+          if (k0 + tid < P.nK) {
+            const float4* g = P.geo + ((size_t)b * P.nQp + S.sq[ql]) * 9;
+            const float* vv = reinterpret_cast<const float*>(g + 2);
+            const float4 rot = __ldg(g + 8);
+            const float4 kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + tid);
+            const float dx = __ldg(vv + vert * 3) - kx.x, dy = __ldg(vv + vert * 3 + 1) - kx.y, dz = __ldg(vv + vert * 3 + 2) - kx.z;
+            const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+            unsigned nx, ny, nz, fx, fy, fz;
+            axis_rec(tx, P.log_scale, P.c1, P.c0, P.n, nx, fx);
+            axis_rec(ty, P.log_scale, P.c1, P.c0, P.n, ny, fy);
+            axis_rec(dz, P.log_scale, P.c1, P.c0, P.n, nz, fz);
+            uint4 rec = S.recs[ql * KC + tid];
+            rec.x = (rec.x & ~(0xFFFFu << shx)) | (fx << shx);
+            rec.y = (rec.y & ~(0xFFFFu << shy)) | (fy << shy);
+            rec.z = (rec.z & ~(0xFFFFu << shz)) | (fz << shz);
+            rec.w = (rec.w & ~((15u << nbx) | (15u << nby) | (15u << nbz))) | (nx << nbx) | (ny << nby) | (nz << nbz);
+            S.recs[ql * KC + tid] = rec;
+          }
+        }
+      }
+      for (int i = tid; i < nbins; i += THREADS) S.hist[i] = 0;
+      __syncthreads();
+
+      // ---- B1: histogram of the cells
+      int mybin[QB];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
-                acc[k * 4 + 0] = fmaf(w, ds.x, acc[k * 4 + 0]); acc[k * 4 + 1] = fmaf(w, ds.y, acc[k * 4 + 1]);
-                acc[k * 4 + 2] = fmaf(w, ds.z, acc[k * 4 + 2]); acc[k * 4 + 3] = fmaf(w, ds.w, acc[k * 4 + 3]);
+      for (int ql = 0; ql < QB; ++ql) {
+        const unsigned w = S.recs[ql * KC + tid].w;
+        const int nx = (w >> nbx) & 15, ny = (w >> nby) & 15, nz = (w >> nbz) & 15;
+        int bin = (nz * P.R + ny) * P.R + nx;
+        if (max(nx, max(ny, nz)) == 15) bin = -1;
+        mybin[ql] = bin;
+        int rank;
+        run_add(S.hist, bin, lane, rank, false);
+      }
+      __syncthreads();
+
+      // ---- B2: exclusive scan of the histogram (all threads, contiguous slices of bins)
+      {
+        const int per = (nbins + THREADS - 1) / THREADS;
+        const int lo = tid * per, hi = min(nbins, lo + per);
+        int mine = 0;
+        for (int i = lo; i < hi; ++i) mine += S.hist[i];
+        int x = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(FULL, x, o);
+          if (lane >= o) x += y;
+        }
+        if (lane == 31) s_misc[2 + warp] = x;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_misc[2 + w];
+        int run = wbase + x - mine;
+        for (int i = lo; i < hi; ++i) { const int c = S.hist[i]; S.hist[i] = run; S.offs[i] = run; run += c; }
+        if (tid == THREADS - 1) { S.offs[nbins] = run; s_misc[1] = run; }
+      }
+      __syncthreads();
+
+      // ---- B3: counting-sort scatter of the pair ids
+#pragma unroll
+      for (int ql = 0; ql < QB; ++ql) {
+        const int bin = mybin[ql];
+        int rank;
+        const int base = run_add(S.hist, bin, lane, rank, true);
+        if (bin >= 0) S.sorted[base + rank] = (uint16_t)(ql * KC + tid);
+      }
+      __syncthreads();
+
+      // ---- B4: accumulate.  Warp w owns sorted[c0, c1).
+      {
+        const int total = s_misc[1];
+        const int csz = (((total + WARPS - 1) / WARPS) + 31) & ~31;
+        const int c0 = warp * csz, c1 = min(total, c0 + csz);
+        float* tab = my_priv + (size_t)vert * cells_pad * 4;
+        float2 acc[16];                   // [corner][head pair]
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+        int cur_bin = -1;
+
+        auto cell_addr = [&](int bin) -> float* {
+          const int nx = bin % P.R, ny = (bin / P.R) % P.R, nz = bin / (P.R * P.R);
+          return tab + ((((nz + cz) * P.P3 + (ny + cy)) * P.P3 + (nx + cx)) << 2) + hsel;
+        };
+        auto flush = [&](int bin) {
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { a[2 * j] = acc[j].x; a[2 * j + 1] = acc[j].y; acc[j] = make_float2(0.f, 0.f); }
+          // a[corner * 4 + head] with head pairs (0,1) (2,3): index = corner*4 + hp*2 + e == lane's (corner, hsel)
+          const float tot = transpose_reduce(a, lane);
+          if (tot != 0.f) atomicAdd(cell_addr(bin), tot);
+        };
+
+        for (int p0 = c0; p0 < c1; p0 += 32) {
+          const int p = p0 + lane;
+          const bool live = p < c1;
+          const int id = live ? S.sorted[p] : S.sorted[c0];
+          const uint4 rec = S.recs[id];
+          const uint2 dv = S.dsv[id];
+          const int nx = (rec.w >> nbx) & 15, ny = (rec.w >> nby) & 15, nz = (rec.w >> nbz) & 15;
+          const int bin = live ? (nz * P.R + ny) * P.R + nx : -1;
+          const float fx = (float)((rec.x >> shx) & 0xFFFFu) * FRAC_INV;
+          const float fy = (float)((rec.y >> shy) & 0xFFFFu) * FRAC_INV;
+          const float fz = (float)((rec.z >> shz) & 0xFFFFu) * FRAC_INV;
+
+          unsigned todo = __ballot_sync(FULL, live);
+          bool weights_ready = false;
+          float w[8];
+          float2 d01 = make_float2(0.f, 0.f), d23 = d01;
+          while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int bsel = __shfl_sync(FULL, bin, leader);
+            const unsigned grp = __ballot_sync(FULL, bin == bsel) & todo;
+            todo &= ~grp;
+            const int seg = S.offs[bsel + 1] - S.offs[bsel];
+            if (bsel != cur_bin && seg < TINY) {
+              // broadcast mode: lane = (corner, head); the pairs of the run are visited one by one
+              float t = 0.f;
+              unsigned g2 = grp;
+              while (g2) {
+                const int e = __ffs(g2) - 1;
+                g2 &= g2 - 1;
+                const float ez = __shfl_sync(FULL, fz, e), ey = __shfl_sync(FULL, fy, e), ex = __shfl_sync(FULL, fx, e);
+                const unsigned dlo = __shfl_sync(FULL, dv.x, e), dhi = __shfl_sync(FULL, dv.y, e);
+                const unsigned word = (hsel & 2) ? dhi : dlo;
+                const float dval = __half2float(__ushort_as_half((unsigned short)((hsel & 1) ? (word >> 16) : (word & 0xFFFFu))));
+                const float wz = fmaf(ez, mzs, mzo), wy = fmaf(ey, mys, myo), wx = fmaf(ex, mxs, mxo);
+                t = fmaf(wz * wy * wx, dval, t);
+              }
+              if (t != 0.f) atomicAdd(cell_addr(bsel), t);
+              continue;
+            }
+            if (bsel != cur_bin) {
+              if (cur_bin >= 0) flush(cur_bin);
+              cur_bin = bsel;
+            }
+            if (!weights_ready) {
+              const float wz1 = fz, wz0 = 1.f - fz, wy1 = fy, wy0 = 1.f - fy, wx1 = fx, wx0 = 1.f - fx;
+              const float a00 = wz0 * wy0, a01 = wz0 * wy1, a10 = wz1 * wy0, a11 = wz1 * wy1;
+              w[0] = a00 * wx0; w[1] = a00 * wx1; w[2] = a01 * wx0; w[3] = a01 * wx1;
+              w[4] = a10 * wx0; w[5] = a10 * wx1; w[6] = a11 * wx0; w[7] = a11 * wx1;
+              d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv.x));
+              d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv.y));
+              weights_ready = true;
+            }
+            if ((grp >> lane) & 1u) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                acc[2 * c] = ffma2(w[c], d01, acc[2 * c]);
+                acc[2 * c + 1] = ffma2(w[c], d23, acc[2 * c + 1]);
               }
             }
-            continue;
           }
         }
-        float c[32];
-        if (live) {
-          const float dx = vq.x - kx.x, dy = vq.y - kx.y, dz = vq.z - kx.z;
-          const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-          const rpe::Axis ax = rpe::rpe_axis_fast(tx, P.log_scale, P.c1, P.c0, P.n, sx);
-          const rpe::Axis ay = rpe::rpe_axis_fast(ty, P.log_scale, P.c1, P.c0, P.n, sy);
-          const rpe::Axis az = rpe::rpe_axis_fast(dz, P.log_scale, P.c1, P.c0, P.n, sz);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float w = ((k & 4) ? az.w1 : az.w0) * ((k & 2) ? ay.w1 : ay.w0) * ((k & 1) ? ax.w1 : ax.w0);
-            c[k * 4 + 0] = w * ds.x; c[k * 4 + 1] = w * ds.y; c[k * 4 + 2] = w * ds.z; c[k * 4 + 3] = w * ds.w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) c[k] = 0.f;
-        }
-        // segments of this step, in sorted (= lane) order.  Long segments (>= 12 lanes, or the continuation of the
-        // bin being accumulated) go to the lane-private registers; the long tail of nearly empty cells is summed
-        // through the scratch tile (rows of one segment are contiguous) and added straight to the table.
-        unsigned todo = __ballot_sync(0xffffffffu, live), longmask = 0u;
-        bool staged = false;
-        while (todo) {                                   // pass A: short segments
-          const int leader = __ffs(todo) - 1;
-          const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-          const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel);
-          todo &= ~grp;
-          const int cnt = __popc(grp);
-          if (bsel == cur_bin || cnt >= 12) { longmask |= grp; continue; }
-          if (!staged) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) my[lane * 33 + j] = c[j];
-            __syncwarp();
-            staged = true;
-          }
-          float ssum = 0.f;
-          for (int l = leader; l < leader + cnt; ++l) ssum += my[l * 33 + lane];
-          const int bx = bsel % P.R - 1, by = (bsel / P.R) % P.R - 1, bz = bsel / (P.R * P.R) - 1;
-          const int x = bx + (corner & 1), y = by + ((corner >> 1) & 1), z = bz + (corner >> 2);
-          if ((unsigned)x < (unsigned)P.n && (unsigned)y < (unsigned)P.n && (unsigned)z < (unsigned)P.n && ssum != 0.f)
-            atomicAdd(stab + (((z * P.n + y) * P.n + x) << 2) + hsel, ssum);
-        }
-        if (staged) __syncwarp();
-        todo = longmask;
-        while (todo) {                                   // pass B: long segments
-          const int leader = __ffs(todo) - 1;
-          const int bsel = __shfl_sync(0xffffffffu, bin, leader);
-          const unsigned grp = __ballot_sync(0xffffffffu, live && bin == bsel) & longmask;
-          todo &= ~grp;
-          if (bsel != cur_bin) {
-            if (cur_bin >= 0) flush(cur_bin);
-            cur_bin = bsel;
-          }
-          if ((grp >> lane) & 1u) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) acc[k] += c[k];
-          }
-        }
+        if (cur_bin >= 0) flush(cur_bin);
       }
-      if (cur_bin >= 0) flush(cur_bin);
+      __syncthreads();                    // hist / offs / sorted are rewritten by the next vertex
     }
-    __syncthreads();     // before the next unit overwrites hist / binbuf / sorted / sgeo
+  }
+}
+
+// sum of the per-CTA private tables, without the padding cells, times 1 / scale
+__global__ void rpe_dtables_reduce_kernel(const float* __restrict__ priv, int copies, int n, int P3, float* __restrict__ out,
+                                          const unsigned* absmax_bits, int dense) {
+  const float inv = 1.0f / scale_of(*absmax_bits, dense);
+  const int total = 8 * n * n * n * 4;
+  const size_t copy_stride = (size_t)8 * P3 * P3 * P3 * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int h = i & 3;
+    int r = i >> 2;
+    const int x = r % n; r /= n;
+    const int y = r % n; r /= n;
+    const int z = r % n;
+    const int v = r / n;
+    const size_t src = ((((size_t)v * P3 + z + 1) * P3 + y + 1) * P3 + x + 1) * 4 + h;
+    float s = 0.f;
+    for (int c = 0; c < copies; ++c) s += priv[c * copy_stride + src];
+    out[i] = s * inv;
+  }
+}
+
+// Morton order of the queries of every scene (box centre = mean of vertices 2 (-,-,-) and 4 (+,+,+)): neighbouring
+// boxes see the keys in the same table cells, which halves the number of segments per unit.
+constexpr int QSORT_MAX = 4096;
+__global__ void __launch_bounds__(1024, 1) rpe_dtables_qorder_kernel(const float4* __restrict__ geo, int nQ, int nQp, int* __restrict__ qperm) {
+  __shared__ unsigned long long keys[QSORT_MAX];
+  __shared__ float red[6][32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* out = qperm + (size_t)b * nQ;
+  if (nQ > QSORT_MAX) {                   // identity: still correct, only less coherent
+    for (int i = tid; i < nQ; i += blockDim.x) out[i] = i;
+    return;
+  }
+  int N = 1;
+  while (N < nQ) N <<= 1;
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int i = tid; i < nQ; i += blockDim.x) {
+    const float* v = reinterpret_cast<const float*>(geo + ((size_t)b * nQp + i) * 9 + 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float c = 0.5f * (v[6 + a] + v[12 + a]);
+      if (c == c) { mn[a] = fminf(mn[a], c); mx[a] = fmaxf(mx[a], c); }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+    }
+    if (lane == 0) { red[a][warp] = mn[a]; red[3 + a][warp] = mx[a]; }
   }
   __syncthreads();
-  if (cur_vert >= 0)
-    for (int i = tid; i < ncell4; i += THREADS) {
-      const float v = stab[i];
-      if (v != 0.f) atomicAdd(P.dtables + (size_t)cur_vert * ncell4 + i, v);
+  const int nw = blockDim.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float m0 = 3.0e38f, m1 = -3.0e38f;
+    for (int w = 0; w < nw; ++w) { m0 = fminf(m0, red[a][w]); m1 = fmaxf(m1, red[3 + a][w]); }
+    mn[a] = m0; mx[a] = m1;
+  }
+  for (int i = tid; i < N; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < nQ) {
+      const float* v = reinterpret_cast<const float*>(geo + ((size_t)b * nQp + i) * 9 + 2);
+      unsigned code = 0;
+      unsigned qv[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float c = 0.5f * (v[6 + a] + v[12 + a]);
+        const float ext = mx[a] - mn[a];
+        float t = (ext > 0.f && c == c) ? (c - mn[a]) / ext : 0.f;
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        qv[a] = (unsigned)(t * 1023.0f);
+      }
+#pragma unroll
+      for (int bit = 0; bit < 10; ++bit)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) code |= ((qv[a] >> bit) & 1u) << (3 * bit + a);
+      key = ((unsigned long long)code << 32) | (unsigned)i;
     }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < N; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], c = keys[ixj];
+          const bool asc = (i & k) == 0;
+          if ((a > c) == asc) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < nQ; i += blockDim.x) out[i] = (int)(keys[i] & 0xffffffffu);
 }
 
-size_t smem_bytes(int n) {
-  const int R = n + 1, nbins = R * R * R;
-  size_t o = (size_t)UNIT * 2 * 2;
-  o += (size_t)((2 * nbins + 1 + 3) & ~3) * 4;
-  o += (size_t)n * n * n * 16 + QB * 2 * 16 + (size_t)WARPS * 32 * 33 * 4;
-  return o;
+// dense fp32 dbias [B][nQ][nK][4] -> scaled fp16 rows [(b*nQ + q)*4 + h][nK]  (C-ABI helper only)
+__global__ void rpe_dtables_dense_pack_kernel(const float4* __restrict__ ds4, size_t pairs, int nK, __half* __restrict__ dsb,
+                                              const unsigned* absmax_bits) {
+  const float sc = scale_of(*absmax_bits, 1);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 d = __ldg(ds4 + i);
+    const size_t bq = i / nK;
+    const int k = (int)(i - bq * nK);
+    __half* dst = dsb + bq * 4 * (size_t)nK + k;
+    dst[0] = __float2half_rn(d.x * sc);
+    dst[(size_t)nK] = __float2half_rn(d.y * sc);
+    dst[2 * (size_t)nK] = __float2half_rn(d.z * sc);
+    dst[3 * (size_t)nK] = __float2half_rn(d.w * sc);
+  }
 }
 
-}  // namespace v2
+}  // namespace dt3
 
-// ds4 [B][nQp][nKp] float4, xyz4 / geo as produced by vdetr_pack_kernel.  dtables is zeroed here.
-int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const float4* ds4,
-                       float* dtables, cudaStream_t st) {
+// scratch of the dTables pass: query order + one zero-padded private table per CTA
+size_t rpe_dtables_scratch_bytes(const VdetrXattnShape* s) {
+  const int P3 = s->grid_n + 2;
+  return vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024) +
+         vdetr_align_up((size_t)vdetr_num_sms() * 8 * P3 * P3 * P3 * 4 * sizeof(float), 1024);
+}
+
+// dsb: scale * dS as fp16 rows [(b*nQp + q)*4 + h][nKp]; scale derives from *absmax_bits (vdetr_grad_scale, or the
+// dense helper's own rule when dense_scale != 0).  dtables [8][n][n][n][4] is fully overwritten.
+int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const __half* dsb,
+                       const unsigned* absmax_bits, int dense_scale, float* dtables, void* scratch, size_t scratch_bytes,
+                       cudaStream_t st) {
   const int n = s->grid_n;
-  const size_t tbytes = (size_t)8 * n * n * n * 4 * sizeof(float);
-  VDETR_CUDA_TRY(cudaMemsetAsync(dtables, 0, tbytes, st));
-  if (s->B == 0 || s->nQ == 0 || s->nK == 0) return 0;
-  DtParams P = {};
-  P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = nQp; P.nKp = nKp; P.n = n;
+  if (s->B == 0 || s->nQ == 0 || s->nK == 0) {
+    VDETR_CUDA_TRY(cudaMemsetAsync(dtables, 0, (size_t)8 * n * n * n * 4 * sizeof(float), st));
+    return 0;
+  }
+  if (n < 1 || n > dt3::MAX_N) return VDETR_ERR_UNSUPPORTED;
+  if (!scratch || scratch_bytes < rpe_dtables_scratch_bytes(s)) return VDETR_ERR_WORKSPACE;
+  const size_t smem = dt3::smem_bytes(n);
+  if (smem > 232448) return VDETR_ERR_UNSUPPORTED;
+  uint8_t* w = reinterpret_cast<uint8_t*>(scratch);
+  int* qperm = reinterpret_cast<int*>(w);
+  float* priv = reinterpret_cast<float*>(w + vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024));
+
+  dt3::Params P = {};
+  P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = nQp; P.nKp = nKp; P.n = n; P.R = n + 1; P.P3 = n + 2;
+  P.qblocks = (s->nQ + dt3::QB - 1) / dt3::QB;
+  P.kchunks = (s->nK + dt3::KC - 1) / dt3::KC;
+  P.units = s->B * P.qblocks * P.kchunks;
+  P.dense_scale = dense_scale;
   P.log_scale = s->log_scale;
   P.c1 = (float)n / (2.0f * 3.0f * s->max_value);
   P.c0 = 0.5f * (float)(n - 1);
-  P.xyz4 = xyz4; P.geo = geo; P.ds4 = ds4; P.dtables = dtables;
-  const char* force = getenv("VDETR_DT_IMPL");
-  const size_t smem2 = v2::smem_bytes(n);
-  if (smem2 <= 232448 && (n + 1) * (n + 1) * (n + 1) < 0xFFFF && !(force && force[0] == '1')) {
-    v2::Params Q = {};
-    Q.B = s->B; Q.nQ = s->nQ; Q.nK = s->nK; Q.nQp = nQp; Q.nKp = nKp; Q.n = n; Q.R = n + 1;
-    Q.qblocks = (s->nQ + v2::QB - 1) / v2::QB;
-    Q.kchunks = (s->nK + v2::KC - 1) / v2::KC;
-    Q.units = 8 * s->B * Q.qblocks * Q.kchunks;
-    Q.log_scale = P.log_scale; Q.c1 = P.c1; Q.c0 = P.c0;
-    Q.xyz4 = xyz4; Q.geo = geo; Q.ds4 = ds4; Q.dtables = dtables;
-    VDETR_CUDA_TRY(cudaFuncSetAttribute(v2::rpe_dtables_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    const int grid2 = Q.units < vdetr_num_sms() ? Q.units : vdetr_num_sms();
-    {
-      VdetrTimingScope timing(VDETR_T_DTABLES, st);
-      v2::rpe_dtables_sorted_kernel<<<grid2, v2::THREADS, smem2, st>>>(Q);
-    }
-    VDETR_LAUNCH_CHECK();
-    return 0;
-  }
-  const size_t smem = tbytes + (size_t)DT_WARPS * 32 * 33 * sizeof(float);
-  if (smem > 232448) return VDETR_ERR_UNSUPPORTED;
-  VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_dtables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long tasks = (long)s->B * s->nQ * 8;
-  long want = (tasks + DT_WARPS - 1) / DT_WARPS;
-  int grid = (int)(want < vdetr_num_sms() ? want : vdetr_num_sms());
-  {
-    VdetrTimingScope timing(VDETR_T_DTABLES, st);
-    rpe_dtables_kernel<<<grid, DT_THREADS, smem, st>>>(P);
-  }
+  P.xyz4 = xyz4; P.geo = geo; P.dsb = dsb; P.qperm = qperm; P.absmax_bits = absmax_bits; P.priv = priv;
+  const int grid = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
+  const size_t copy_bytes = (size_t)8 * P.P3 * P.P3 * P.P3 * 4 * sizeof(float);
+
+  VdetrTimingScope timing(VDETR_T_DTABLES, st);
+  VDETR_CUDA_TRY(cudaMemsetAsync(priv, 0, copy_bytes * grid, st));
+  dt3::rpe_dtables_qorder_kernel<<<s->B, 1024, 0, st>>>(geo, s->nQ, nQp, qperm);
+  VDETR_LAUNCH_CHECK();
+  VDETR_CUDA_TRY(cudaFuncSetAttribute(dt3::rpe_dtables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dt3::rpe_dtables_kernel<<<grid, dt3::THREADS, smem, st>>>(P);
+  VDETR_LAUNCH_CHECK();
+  const int total = 8 * n * n * n * 4;
+  dt3::rpe_dtables_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(priv, grid, n, P.P3, dtables, absmax_bits, dense_scale);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
 
-// C-ABI helper behind vdetr_rpe_dtables: dense dS [B,nQ,nK,4] -> dTables (packs xyz / geometry itself).
+// C-ABI helper behind vdetr_rpe_dtables: dense dS [B,nQ,nK,4] -> dTables (packs xyz / geometry / fp16 dS itself).
 size_t rpe_dtables_workspace(const VdetrXattnShape* s) {
-  return vdetr_align_up((size_t)s->B * s->nK * 16, 1024) + vdetr_align_up((size_t)s->B * s->nQ * 9 * 16, 1024);
+  return vdetr_align_up((size_t)s->B * s->nK * 16, 1024) + vdetr_align_up((size_t)s->B * s->nQ * 9 * 16, 1024) +
+         vdetr_align_up((size_t)s->B * s->nQ * 4 * s->nK * 2, 1024) + 1024 + rpe_dtables_scratch_bytes(s);
 }
 int rpe_dtables_dense(const VdetrXattnShape* s, const float* xyz, const float* ref, const float* ang, const float* ds4,
                       float* dtables, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -516,9 +604,20 @@ int rpe_dtables_dense(const VdetrXattnShape* s, const float* xyz, const float* r
   VdetrPack pk = {};
   pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = s->nQ; pk.nKp = s->nK; pk.kvh = 1; pk.has_bias = 1;
   pk.xyz = xyz; pk.ref = ref; pk.ang = s->rotate ? ang : nullptr;
-  pk.xyz4 = reinterpret_cast<float4*>(w);
-  pk.geo = reinterpret_cast<float4*>(w + vdetr_align_up((size_t)s->B * s->nK * 16, 1024));
+  size_t o = 0;
+  pk.xyz4 = reinterpret_cast<float4*>(w + o); o += vdetr_align_up((size_t)s->B * s->nK * 16, 1024);
+  pk.geo = reinterpret_cast<float4*>(w + o); o += vdetr_align_up((size_t)s->B * s->nQ * 9 * 16, 1024);
+  __half* dsb = reinterpret_cast<__half*>(w + o); o += vdetr_align_up((size_t)s->B * s->nQ * 4 * s->nK * 2, 1024);
+  unsigned* absmax = reinterpret_cast<unsigned*>(w + o); o += 1024;
+  if (s->B == 0 || s->nQ == 0 || s->nK == 0)
+    return rpe_dtables_launch(s, s->nQ, s->nK, nullptr, nullptr, nullptr, nullptr, 1, dtables, w + o, ws_bytes - o, st);
   vdetr_pack_kernel<<<vdetr_num_sms(), 256, 0, st>>>(pk);
   VDETR_LAUNCH_CHECK();
-  return rpe_dtables_launch(s, s->nQ, s->nK, pk.xyz4, pk.geo, reinterpret_cast<const float4*>(ds4), dtables, st);
+  const size_t pairs = (size_t)s->B * s->nQ * s->nK;
+  VDETR_CUDA_TRY(cudaMemsetAsync(absmax, 0, 4, st));
+  vdetr_absmax_kernel<<<vdetr_num_sms() * 2, 256, 0, st>>>(ds4, pairs * 4, absmax);
+  VDETR_LAUNCH_CHECK();
+  dt3::rpe_dtables_dense_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(reinterpret_cast<const float4*>(ds4), pairs, s->nK, dsb, absmax);
+  VDETR_LAUNCH_CHECK();
+  return rpe_dtables_launch(s, s->nQ, s->nK, pk.xyz4, pk.geo, dsb, absmax, 1, dtables, w + o, ws_bytes - o, st);
 }

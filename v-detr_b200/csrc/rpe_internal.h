@@ -59,8 +59,10 @@ __device__ __forceinline__ float vdetr_grad_scale(unsigned absmax_bits) {
 }
 
 // dTables (rpe_dtables.cu)
-int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const float4* ds4,
-                       float* dtables, cudaStream_t st);
+size_t rpe_dtables_scratch_bytes(const VdetrXattnShape* s);
+int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const __half* dsb,
+                       const unsigned* absmax_bits, int dense_scale, float* dtables, void* scratch, size_t scratch_bytes,
+                       cudaStream_t st);
 size_t rpe_dtables_workspace(const VdetrXattnShape* s);
 int rpe_dtables_dense(const VdetrXattnShape* s, const float* xyz, const float* ref, const float* ang, const float* ds4,
                       float* dtables, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -3,10 +3,10 @@
 // Pass 1 (this file's kernel, tcgen05 + TMA, same tiling / warp roles as the forward):
 //     S  = Q K^T + rpe            (bias recomputed, never read from memory)
 //     P  = exp(S - LSE)           dP = dO V^T          dS = P * (dP - D),   D = rowsum(dO * O)
-//   written once as  P (fp16), g*dS (fp16) [rows][nKp]  and  dS4 (fp32, 4 heads of a (query,key) pair together);
+//   written once as  P (fp16) and g*dS (fp16), both [rows][nKp];
 //   g is the per-call power-of-two gradient scale (rpe_internal.h).
 // Pass 2: the three plain GEMMs   dQ = dS K,  dK = dS^T Q,  dV = P^T dO   (cuBLAS, fp16 in / fp32 out).
-// Pass 3: dTables from dS4 (rpe_dtables.cu).
+// Pass 3: dTables from the same g*dS (rpe_dtables.cu).
 #include <cublas_v2.h>
 #include "rpe_internal.h"
 #include "tc_common.cuh"
@@ -38,7 +38,6 @@ struct BwdParams {
   const unsigned* absmax_bits; // bits of max|dout| -> gradient scale
   __half* pb;                  // [rows][nKp]  P
   __half* dsb;                 // [rows][nKp]  g * dS
-  float4* ds4;                 // [B][nQp][nKp]   (HAS_BIAS)
 };
 
 struct SmemLayout {
@@ -108,7 +107,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tS0 = tmem_base, tdP0 = tmem_base + 128;
   const uint32_t idesc_s = umma_idesc_f16(BM, BN);     // S  = Q K^T : fp16 operands, exactly as the forward
   const uint32_t idesc_d = umma_idesc_f16(BM, BN);     // g*dP = (g dO) V^T: scaled fp16
-  const float gscale = vdetr_grad_scale(*P.absmax_bits), ginv = 1.0f / gscale;
+  const float gscale = vdetr_grad_scale(*P.absmax_bits);
 
   uint32_t g = 0, it = 0;
   for (int item = blockIdx.x; item < P.items; item += gridDim.x, ++it) {
@@ -222,7 +221,6 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float p = ex2_approx(s * LOG2E - lse2);
             if (key0 + slice * 16 + c + e >= P.nK) p = 0.f;
             const float ds = p * (__uint_as_float(dr[c + e]) - Drow);        // = g * dS
-            if (HAS_BIAS) brow[(c + e) * 4] = ds * ginv;   // same slot the bias came from: owned by this thread
             pv[e] = p; dv[e] = ds;
           }
           pk[c >> 1] = pack_f16x2(pv[0], pv[1]);
@@ -234,15 +232,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           dstp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dstp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
         }
-        if (HAS_BIAS) {
-          named_bar_sync(2, NCOMPUTE);                     // (b) dS tile complete in the staging buffer
-          float4* dst = P.ds4 + ((size_t)b * P.nQp + q0) * P.nKp + key0;
-          for (int i = tid; i < QT * BN; i += NCOMPUTE) {
-            const int qq = i >> 6, kk = i & 63;
-            dst[(size_t)qq * P.nKp + kk] = sBias[qq * BIAS_STRIDE_F4 + kk];
-          }
-          named_bar_sync(1, NCOMPUTE);                     // (c) staging buffer free again
-        }
+        if (HAS_BIAS) named_bar_sync(2, NCOMPUTE);         // (b) every thread has read its bias: the tile may be rewritten
       }
       named_bar_sync(2, NCOMPUTE);                         // sRow / sGeo reusable by the next item
     }
@@ -288,7 +278,7 @@ __global__ void bwd_unpack_kernel(UnpackParams U) {
 
 struct BwdPlan {
   int nQp, nKp, mtiles, splits, tiles_per_split, items;
-  size_t off_qp, off_dop, off_kp, off_vp, off_max, off_xyz, off_geo, off_pb, off_dsb, off_ds4, off_dqp, off_dkp, off_dvp, total;
+  size_t off_qp, off_dop, off_kp, off_vp, off_max, off_xyz, off_geo, off_pb, off_dsb, off_dt, off_dqp, off_dkp, off_dvp, total;
 };
 BwdPlan make_plan(const VdetrXattnShape* s) {
   BwdPlan p;
@@ -326,7 +316,7 @@ BwdPlan make_plan(const VdetrXattnShape* s) {
   p.off_geo = take(s->has_bias ? (size_t)s->B * p.nQp * GEO_F4 * 16 : 0);
   p.off_pb = take(rows * p.nKp * 2);
   p.off_dsb = take(rows * p.nKp * 2);
-  p.off_ds4 = take(s->has_bias ? (size_t)s->B * p.nQp * p.nKp * 16 : 0);
+  p.off_dt = take(s->has_bias ? rpe_dtables_scratch_bytes(s) : 0);
   p.off_dqp = take(rows * 64 * 4);
   p.off_dkp = take(krows * 64 * 4);
   p.off_dvp = take(krows * 64 * 4);
@@ -353,9 +343,6 @@ int gemm_rm(cublasHandle_t hnd, bool ta, bool tb, int M, int N, int K, const __h
 }
 
 }  // namespace
-
-int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const float4* ds4,
-                       float* dtables, cudaStream_t st);
 
 size_t tc_xattn_bwd_workspace(const VdetrXattnShape* s) { return make_plan(s).total; }
 
@@ -407,7 +394,6 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   P.absmax_bits = absmax;
   P.pb = reinterpret_cast<__half*>(w + pl.off_pb);
   P.dsb = reinterpret_cast<__half*>(w + pl.off_dsb);
-  P.ds4 = reinterpret_cast<float4*>(w + pl.off_ds4);
 
   const int table_bytes = s->has_bias ? rpe::pair_table_bytes(s->grid_n) : 0;
   const SmemLayout L = smem_layout(table_bytes);
@@ -448,7 +434,9 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
 
   // ---- pass 3: dTables
   if (s->has_bias) {
-    if ((rc = rpe_dtables_launch(s, pl.nQp, pl.nKp, pk.xyz4, pk.geo, P.ds4, dtables, st))) return rc;
+    if ((rc = rpe_dtables_launch(s, pl.nQp, pl.nKp, pk.xyz4, pk.geo, P.dsb, absmax, 0, dtables, w + pl.off_dt,
+                                 rpe_dtables_scratch_bytes(s), st)))
+      return rc;
   }
   return 0;
 }
