@@ -30,7 +30,6 @@ constexpr int THREADS = 512, WARPS = THREADS / 32;
 constexpr int TINY = 8;                              // segments shorter than this use the broadcast mode
 constexpr int MAX_N = 12;                            // cell index + 1 must fit 4 bits with 15 = invalid
 constexpr unsigned FULL = 0xffffffffu;
-constexpr float FRAC_Q = 65535.0f, FRAC_INV = 1.0f / 65535.0f;
 static_assert(KC == THREADS, "phase A maps one thread to one key of the chunk");
 
 struct Params {
@@ -64,7 +63,7 @@ __device__ __forceinline__ void axis_rec(float d, float ls, float c1, float c0, 
   const float f = p - (r - rpe::MAGIC);
   const int n0 = __float_as_int(r) - rpe::MAGIC_BITS;
   nib = ((unsigned)(n0 + 1) <= (unsigned)n) ? (unsigned)(n0 + 1) : 15u;
-  frac = __float2uint_rn(fminf(fmaxf(f, 0.f), 1.f) * FRAC_Q);
+  frac = min(__float2uint_rn(fminf(fmaxf(f, 0.f), 1.f) * 65536.0f), 65535u);      // fraction in units of 2^-16
 }
 
 // vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4:(+,+,+) 5:(+,-,+) 6:(-,-,+) 7:(-,+,+)
@@ -79,8 +78,8 @@ struct Smem {
   uint4* recs;        // [NP]  x: fx+ | fx- << 16   y: fy+ | fy-   z: fz+ | fz-   w: nibbles x+,x-,y+,y-,z+,z- (4 bits each)
   uint2* dsv;         // [NP]  4 x fp16 scaled dS
   uint16_t* sorted;   // [NP]
-  int* hist;          // [nbins]   counts, then scatter cursors      } this region doubles as the key xyz
-  int* offs;          // [nbins+1] exclusive scan                    } staging buffer during phase A
+  int* hist;          // [nbins]   counts, then scatter cursors      } this region (+ costp[nbins+1]) doubles as
+  int* offs;          // [nbins+1] exclusive scan                    } the key xyz staging buffer during phase A
   float4* sxyz;       // [KC] (aliases hist/offs)
   float4* sgeo;       // [QB][2]
   int* sq;            // [QB] query index (or -1), [QB] slow flags, misc
@@ -88,11 +87,11 @@ struct Smem {
 
 __host__ __device__ inline size_t region_bytes(int n) {
   const size_t nbins = (size_t)(n + 1) * (n + 1) * (n + 1);
-  size_t r = (2 * nbins + 1 + 3) / 4 * 16;
+  size_t r = (3 * nbins + 2 + 3) / 4 * 16;
   return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
 }
 __host__ __device__ inline size_t smem_bytes(int n) {
-  return (size_t)NP * 16 + (size_t)NP * 8 + (size_t)NP * 2 + region_bytes(n) + QB * 2 * 16 + 64 * 4;
+  return (size_t)NP * 16 + (size_t)NP * 8 + (size_t)NP * 2 + region_bytes(n) + QB * 2 * 16 + 96 * 4;
 }
 
 // transposed reduction: on return lane j holds sum over lanes of acc[j]
@@ -144,6 +143,10 @@ __device__ __forceinline__ float2 ffma2(float w, float2 d, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
+// rough instruction cost of accumulating a segment of c pairs (units of half warp-instructions): register mode pays
+// ~4.5 per pair plus a flush, broadcast mode ~16 per pair
+__device__ __forceinline__ int seg_cost(int c) { return c == 0 ? 0 : (c < TINY ? 32 * c + 90 : 9 * c + 280); }
+
 // run-aggregated shared-memory counter update: lanes with equal, adjacent `bin` form a run; the run head adds the
 // run length.  Returns the value before the add (broadcast to the run) and this lane's rank inside its run.
 __device__ __forceinline__ int run_add(int* counters, int bin, int lane, int& rank, bool want_old) {
@@ -175,7 +178,9 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
   S.sgeo = reinterpret_cast<float4*>(region + region_bytes(P.n));
   S.sq = reinterpret_cast<int*>(S.sgeo + QB * 2);
   int* s_slow = S.sq + QB;          // [QB]
-  int* s_misc = S.sq + 2 * QB;      // [1] number of sorted entries, [2..2+WARPS] scan scratch
+  int* s_misc = S.sq + 2 * QB;      // [2..2+2*WARPS) scan scratch
+  int* s_start = s_misc + 2 + 2 * WARPS;   // [WARPS+1] first sorted entry of every warp's share
+  int* costp = S.offs + nbins + 1;  // [nbins+1] exclusive scan of the per-cell cost estimate
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cells_pad = P.P3 * P.P3 * P.P3;
@@ -300,85 +305,127 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
       }
       __syncthreads();
 
-      // ---- B2: exclusive scan of the histogram (all threads, contiguous slices of bins)
+      // ---- B2: exclusive scan of the histogram (all threads, contiguous slices of bins) and of a per-cell cost
+      // estimate that balances the accumulation phase over the warps
       {
         const int per = (nbins + THREADS - 1) / THREADS;
         const int lo = tid * per, hi = min(nbins, lo + per);
-        int mine = 0;
-        for (int i = lo; i < hi; ++i) mine += S.hist[i];
-        int x = mine;
+        int mine = 0, minec = 0;
+        for (int i = lo; i < hi; ++i) { const int c = S.hist[i]; mine += c; minec += seg_cost(c); }
+        int x = mine, xc = minec;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(FULL, x, o);
-          if (lane >= o) x += y;
+          const int y = __shfl_up_sync(FULL, x, o), yc = __shfl_up_sync(FULL, xc, o);
+          if (lane >= o) { x += y; xc += yc; }
         }
-        if (lane == 31) s_misc[2 + warp] = x;
+        if (lane == 31) { s_misc[2 + warp] = x; s_misc[2 + WARPS + warp] = xc; }
         __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += s_misc[2 + w];
-        int run = wbase + x - mine;
-        for (int i = lo; i < hi; ++i) { const int c = S.hist[i]; S.hist[i] = run; S.offs[i] = run; run += c; }
-        if (tid == THREADS - 1) { S.offs[nbins] = run; s_misc[1] = run; }
+        int wbase = 0, wbasec = 0;
+        for (int w = 0; w < warp; ++w) { wbase += s_misc[2 + w]; wbasec += s_misc[2 + WARPS + w]; }
+        int run = wbase + x - mine, runc = wbasec + xc - minec;
+        for (int i = lo; i < hi; ++i) {
+          const int c = S.hist[i];
+          S.hist[i] = run | ((c < TINY) ? (int)0x80000000 : 0);      // scatter cursor; bit 31 marks a tiny segment
+          S.offs[i] = run; costp[i] = runc;
+          run += c; runc += seg_cost(c);
+        }
+        if (tid == THREADS - 1) { S.offs[nbins] = run; costp[nbins] = runc; }
       }
       __syncthreads();
 
-      // ---- B3: counting-sort scatter of the pair ids
+      // ---- B3: every warp finds where its equal-cost share of the sorted list starts, then the counting-sort scatter
+      {
+        const int totalc = costp[nbins];
+        const int target = (int)(((long long)totalc * warp) / WARPS);
+        int lo = 0, hi = nbins;                       // costp[lo] <= target < costp[hi] (if totalc > 0)
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (costp[mid] <= target) lo = mid; else hi = mid;
+        }
+        const int c = S.offs[lo + 1] - S.offs[lo], cb = costp[lo + 1] - costp[lo];
+        int start = S.offs[lo];
+        if (cb > 0) start += min(c, (int)(((long long)(target - costp[lo]) * c) / cb));
+        if (lane == 0) { s_start[warp] = start; if (warp == 0) s_start[WARPS] = S.offs[nbins]; }
+      }
 #pragma unroll
       for (int ql = 0; ql < QB; ++ql) {
         const int bin = mybin[ql];
         int rank;
         const int base = run_add(S.hist, bin, lane, rank, true);
-        if (bin >= 0) S.sorted[base + rank] = (uint16_t)(ql * KC + tid);
+        if (bin >= 0) S.sorted[(base & 0x7fffffff) + rank] = (uint16_t)((ql * KC + tid) | ((base >> 16) & 0x8000));
       }
       __syncthreads();
 
       // ---- B4: accumulate.  Warp w owns sorted[c0, c1).
       {
-        const int total = s_misc[1];
-        const int csz = (((total + WARPS - 1) / WARPS) + 31) & ~31;
-        const int c0 = warp * csz, c1 = min(total, c0 + csz);
+        const int c0 = s_start[warp], c1 = s_start[warp + 1];
         float* tab = my_priv + (size_t)vert * cells_pad * 4;
         float2 acc[16];                   // [corner][head pair]
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
-        int cur_bin = -1;
+        int cur_key = -1;                 // nz << 8 | ny << 4 | nx of the cell being accumulated
 
-        auto cell_addr = [&](int bin) -> float* {
-          const int nx = bin % P.R, ny = (bin / P.R) % P.R, nz = bin / (P.R * P.R);
+        auto cell_addr = [&](int key) -> float* {
+          const int nx = key & 15, ny = (key >> 4) & 15, nz = key >> 8;
           return tab + ((((nz + cz) * P.P3 + (ny + cy)) * P.P3 + (nx + cx)) << 2) + hsel;
         };
-        auto flush = [&](int bin) {
+        auto flush = [&](int key) {
           float a[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { a[2 * j] = acc[j].x; a[2 * j + 1] = acc[j].y; acc[j] = make_float2(0.f, 0.f); }
           // a[corner * 4 + head] with head pairs (0,1) (2,3): index = corner*4 + hp*2 + e == lane's (corner, hsel)
           const float tot = transpose_reduce(a, lane);
-          if (tot != 0.f) atomicAdd(cell_addr(bin), tot);
+          if (tot != 0.f) atomicAdd(cell_addr(key), tot);
         };
 
+        // software pipeline: the entry / record / dS of step s+1 are loaded while step s is accumulated
+        bool live_n = c0 + lane < c1;
+        unsigned ent_n = live_n ? S.sorted[c0 + lane] : 0u;
+        uint4 rec_n = S.recs[ent_n & 0x1FFFu];
+        uint2 dv_n = S.dsv[ent_n & 0x1FFFu];
         for (int p0 = c0; p0 < c1; p0 += 32) {
-          const int p = p0 + lane;
-          const bool live = p < c1;
-          const int id = live ? S.sorted[p] : S.sorted[c0];
-          const uint4 rec = S.recs[id];
-          const uint2 dv = S.dsv[id];
-          const int nx = (rec.w >> nbx) & 15, ny = (rec.w >> nby) & 15, nz = (rec.w >> nbz) & 15;
-          const int bin = live ? (nz * P.R + ny) * P.R + nx : -1;
-          const float fx = (float)((rec.x >> shx) & 0xFFFFu) * FRAC_INV;
-          const float fy = (float)((rec.y >> shy) & 0xFFFFu) * FRAC_INV;
-          const float fz = (float)((rec.z >> shz) & 0xFFFFu) * FRAC_INV;
-
-          unsigned todo = __ballot_sync(FULL, live);
-          bool weights_ready = false;
+          const bool live = live_n;
+          const unsigned ent = ent_n;
+          const uint4 rec = rec_n;
+          const uint2 dv = dv_n;
+          {
+            const int pn = p0 + 32 + lane;
+            live_n = pn < c1;
+            ent_n = live_n ? S.sorted[pn] : 0u;
+            rec_n = S.recs[ent_n & 0x1FFFu];
+            dv_n = S.dsv[ent_n & 0x1FFFu];
+          }
+          const int key = live ? (int)(((rec.w >> nbx) & 15u) | (((rec.w >> nby) & 15u) << 4) | (((rec.w >> nbz) & 15u) << 8)) : -2;
+          // fraction u / 65536 without I2F: (2^23 + u) * 2^-16 - 128
+          const float fx = fmaf(__uint_as_float(((rec.x >> shx) & 0xFFFFu) | 0x4B000000u), 0x1p-16f, -128.f);
+          const float fy = fmaf(__uint_as_float(((rec.y >> shy) & 0xFFFFu) | 0x4B000000u), 0x1p-16f, -128.f);
+          const float fz = fmaf(__uint_as_float(((rec.z >> shz) & 0xFFFFu) | 0x4B000000u), 0x1p-16f, -128.f);
           float w[8];
-          float2 d01 = make_float2(0.f, 0.f), d23 = d01;
+          {
+            const float wz0 = 1.f - fz, wy0 = 1.f - fy, wx0 = 1.f - fx;
+            const float a00 = wz0 * wy0, a01 = wz0 * fy, a10 = fz * wy0, a11 = fz * fy;
+            w[0] = a00 * wx0; w[1] = a00 * fx; w[2] = a01 * wx0; w[3] = a01 * fx;
+            w[4] = a10 * wx0; w[5] = a10 * fx; w[6] = a11 * wx0; w[7] = a11 * fx;
+          }
+          const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv.x));
+          const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv.y));
+
+          if (__all_sync(FULL, key == cur_key)) {          // the common step: 32 more pairs of the current cell
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              acc[2 * c] = ffma2(w[c], d01, acc[2 * c]);
+              acc[2 * c + 1] = ffma2(w[c], d23, acc[2 * c + 1]);
+            }
+            continue;
+          }
+          unsigned todo = __ballot_sync(FULL, live);
           while (todo) {
             const int leader = __ffs(todo) - 1;
-            const int bsel = __shfl_sync(FULL, bin, leader);
-            const unsigned grp = __ballot_sync(FULL, bin == bsel) & todo;
+            const int ksel = __shfl_sync(FULL, key, leader);
+            const bool tiny = (__shfl_sync(FULL, ent, leader) & 0x8000u) != 0u;
+            const unsigned grp = __ballot_sync(FULL, key == ksel);
             todo &= ~grp;
-            const int seg = S.offs[bsel + 1] - S.offs[bsel];
-            if (bsel != cur_bin && seg < TINY) {
+            if (ksel != cur_key && tiny) {
               // broadcast mode: lane = (corner, head); the pairs of the run are visited one by one
               float t = 0.f;
               unsigned g2 = grp;
@@ -392,21 +439,12 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
                 const float wz = fmaf(ez, mzs, mzo), wy = fmaf(ey, mys, myo), wx = fmaf(ex, mxs, mxo);
                 t = fmaf(wz * wy * wx, dval, t);
               }
-              if (t != 0.f) atomicAdd(cell_addr(bsel), t);
+              if (t != 0.f) atomicAdd(cell_addr(ksel), t);
               continue;
             }
-            if (bsel != cur_bin) {
-              if (cur_bin >= 0) flush(cur_bin);
-              cur_bin = bsel;
-            }
-            if (!weights_ready) {
-              const float wz1 = fz, wz0 = 1.f - fz, wy1 = fy, wy0 = 1.f - fy, wx1 = fx, wx0 = 1.f - fx;
-              const float a00 = wz0 * wy0, a01 = wz0 * wy1, a10 = wz1 * wy0, a11 = wz1 * wy1;
-              w[0] = a00 * wx0; w[1] = a00 * wx1; w[2] = a01 * wx0; w[3] = a01 * wx1;
-              w[4] = a10 * wx0; w[5] = a10 * wx1; w[6] = a11 * wx0; w[7] = a11 * wx1;
-              d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv.x));
-              d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv.y));
-              weights_ready = true;
+            if (ksel != cur_key) {
+              if (cur_key >= 0) flush(cur_key);
+              cur_key = ksel;
             }
             if ((grp >> lane) & 1u) {
 #pragma unroll
@@ -417,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
             }
           }
         }
-        if (cur_bin >= 0) flush(cur_bin);
+        if (cur_key >= 0) flush(cur_key);
       }
       __syncthreads();                    // hist / offs / sorted are rewritten by the next vertex
     }
