@@ -150,6 +150,16 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 FMA (FFMA2 on sm_100): (w, w) * d + c for two lanes of a float2 in one instruction
+__device__ __forceinline__ float2 ffma2_scalar(float w, float2 d, float2 c) {
+  unsigned long long rd, ra, rb, rc;
+  const float2 ww = make_float2(w, w);
+  ra = *reinterpret_cast<const unsigned long long*>(&ww);
+  rb = *reinterpret_cast<const unsigned long long*>(&d);
+  rc = *reinterpret_cast<const unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -65,12 +65,11 @@ def box_corners_camera(center, size, angle):
     cam = torch.stack((center[..., 0], -center[..., 2], center[..., 1]), dim=-1)
     hl, hw, hh = size[..., 0:1] * 0.5, size[..., 1:2] * 0.5, size[..., 2:3] * 0.5
     sx, sy, sz = _corner_signs(size)
-    local = torch.stack((hl * sx, hh * sy, hw * sz), dim=-1)
-    c, s = torch.cos(angle), torch.sin(angle)
-    zero, one = torch.zeros_like(c), torch.ones_like(c)
-    rot = torch.stack((torch.stack((c, zero, s), -1), torch.stack((zero, one, zero), -1),
-                       torch.stack((-s, zero, c), -1)), -2)
-    return torch.matmul(local, rot.transpose(-1, -2)) + cam.unsqueeze(-2)
+    lx, ly, lz = hl * sx, hh * sy, hw * sz
+    c, s = torch.cos(angle).unsqueeze(-1), torch.sin(angle).unsqueeze(-1)
+    # local @ roty(angle)^T written out (utils/box_util.py:304-317,352-356): a [.,8,3]x[.,3,3] batched matmul per box
+    # costs a full GEMM launch per call and would run in TF32 when the caller allows it
+    return torch.stack((c * lx + s * lz, ly, c * lz - s * lx), dim=-1) + cam.unsqueeze(-2)
 
 
 class ScanNetBoxConfig:
