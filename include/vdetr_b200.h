@@ -95,23 +95,30 @@ typedef struct VdetrXattnShape {
  *   tables  [8,grid_n,grid_n,grid_n,H] f32 = cpb_mlps[i](relative_coords_table), a=z,b=y,c=x (:725)
  *   out     [B,nQ,H,hd] f32  (heads concatenated h-major = the input of `proj`, :755)
  *   lse     [B,H,nQ] f32 natural-log-sum-exp of the logits (saved for backward)
+ *   bias_save  optional (may be NULL): vdetr_xattn_bias_save_bytes(&shape, impl) bytes in which the fused kernel
+ *           leaves the fp32 bias of every (query,key) pair for the backward, which then streams it back instead
+ *           of recomputing it (training: 16 B per pair of activation memory buys ~5x on the backward pass-1
+ *           kernel; the reference keeps ~2.4 GB of autograd intermediates per layer-scene for the same purpose).
  * impl: 0 = tcgen05/TMA fused kernel (product path), 1 = SIMT validation kernel.
  * workspace: vdetr_xattn_fwd_workspace_bytes(&shape, impl). */
 size_t vdetr_xattn_fwd_workspace_bytes(const VdetrXattnShape* s, int impl);
+size_t vdetr_xattn_bias_save_bytes(const VdetrXattnShape* s, int impl);   /* 0 when the option does not apply */
 int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v,
                     const float* xyz, const float* ref_pts, const float* ref_angle, const float* tables,
-                    float* out, float* lse, void* workspace, size_t workspace_bytes, int impl,
+                    float* out, float* lse, float* bias_save, void* workspace, size_t workspace_bytes, int impl,
                     void* stream);
 
 /* Backward of the same op (dropout disabled):
- *   in : q,k,v,xyz,ref_pts,ref_angle,tables as forward; out, lse from forward; dout [B,nQ,H,hd]
+ *   in : q,k,v,xyz,ref_pts,ref_angle,tables as forward; out, lse from forward; dout [B,nQ,H,hd];
+ *        bias_saved = the forward's bias_save buffer or NULL (NULL: the bias is recomputed)
  *   out: dq [B,nQ,H,hd], dk, dv [B,nK,kv_heads,hd], dtables [8,n,n,n,H]  -- all fully overwritten.
  *   No gradient is produced for xyz / ref_pts (detached in the reference, vdetr_transformer.py:369-412). */
 size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl);
 int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v,
                     const float* xyz, const float* ref_pts, const float* ref_angle, const float* tables,
-                    const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv,
-                    float* dtables, void* workspace, size_t workspace_bytes, int impl, void* stream);
+                    const float* out, const float* lse, const float* dout, const float* bias_saved, float* dq,
+                    float* dk, float* dv, float* dtables, void* workspace, size_t workspace_bytes, int impl,
+                    void* stream);
 
 /* Bias only (debug / return_attn_weights path): rpe [B,H,nQ,nK] f32  (vdetr_transformer.py:708-731). */
 int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,

@@ -190,3 +190,17 @@ def test_dtables_op_matches_oracle():
                                    torch.from_numpy(Ir["angle"]).cuda(), torch.from_numpy(Ir["tables"]).cuda(),
                                    torch.from_numpy(ds).cuda()).cpu().numpy()
     _cmp(got, want, 5e-4, 1e-6, "dtables rotated")
+
+
+@pytest.mark.parametrize("seed,B,nQ,nK,rot", [(51, 2, 70, 333, False), (52, 1, 33, 200, True)])
+def test_saved_bias_backward_equals_recompute(seed, B, nQ, nK, rot, monkeypatch):
+    """Training keeps the forward's per-pair bias (16 B / pair) and the backward streams it back; with
+    VDETR_B200_SAVE_BIAS=0 the backward recomputes it.  Same fp32 values either way: identical gradients."""
+    I = _core_inputs(seed, B, nQ, nK, 1, rot)
+    monkeypatch.setenv("VDETR_B200_SAVE_BIAS", "1")
+    a = _run(I, impl=0)
+    monkeypatch.setenv("VDETR_B200_SAVE_BIAS", "0")
+    b = _run(I, impl=0)
+    for name in ("o", "dq", "dk", "dv"):
+        assert np.array_equal(a[name], b[name]), name
+    _cmp(a["dT"], b["dT"], 1e-5, 1e-7, "dtables (fp32 atomics: order may differ)")

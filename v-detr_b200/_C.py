@@ -35,9 +35,10 @@ _SIGS = {
     "vdetr_pn2_group": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vdetr_pn2_group_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vdetr_xattn_fwd_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
-    "vdetr_xattn_fwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 9 + [c_void_p, c_size_t, c_int, c_void_p]),
+    "vdetr_xattn_bias_save_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
+    "vdetr_xattn_fwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 10 + [c_void_p, c_size_t, c_int, c_void_p]),
     "vdetr_xattn_bwd_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
-    "vdetr_xattn_bwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 14 + [c_void_p, c_size_t, c_int, c_void_p]),
+    "vdetr_xattn_bwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 15 + [c_void_p, c_size_t, c_int, c_void_p]),
     "vdetr_rpe_bias": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p]),
     "vdetr_timing_enable": (c_int, [c_int]),
     "vdetr_timing_read": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int)]),

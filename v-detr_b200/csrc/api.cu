@@ -74,9 +74,14 @@ size_t vdetr_xattn_fwd_workspace_bytes(const VdetrXattnShape* s, int impl) {
   return impl == 0 ? tc_xattn_fwd_workspace(s) : 0;
 }
 
+size_t vdetr_xattn_bias_save_bytes(const VdetrXattnShape* s, int impl) {
+  if (vdetr_check_shape(s) != 0 || impl != 0) return 0;
+  return tc_xattn_bias_save_bytes(s);
+}
+
 int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                     const float* ref_pts, const float* ref_angle, const float* tables, float* out, float* lse,
-                    void* workspace, size_t workspace_bytes, int impl, void* stream) {
+                    float* bias_save, void* workspace, size_t workspace_bytes, int impl, void* stream) {
   int rc = vdetr_check_shape(s);
   if (rc) return rc;
   if (s->B == 0 || s->nQ == 0) return 0;
@@ -85,7 +90,8 @@ int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, co
   if (s->has_bias && (!xyz || !ref_pts || !tables)) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) return simt_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, st);
-  if (impl == 0) return tc_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, workspace, workspace_bytes, st);
+  if (impl == 0)
+    return tc_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save, workspace, workspace_bytes, st);
   return VDETR_ERR_BAD_ARG;
 }
 
@@ -96,8 +102,8 @@ size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl) {
 
 int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                     const float* ref_pts, const float* ref_angle, const float* tables, const float* out,
-                    const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dtables,
-                    void* workspace, size_t workspace_bytes, int impl, void* stream) {
+                    const float* lse, const float* dout, const float* bias_saved, float* dq, float* dk, float* dv,
+                    float* dtables, void* workspace, size_t workspace_bytes, int impl, void* stream) {
   int rc = vdetr_check_shape(s);
   if (rc) return rc;
   if (s->B == 0 || s->nQ == 0 || s->nK == 0) return (s->nK == 0 && s->B && s->nQ) ? VDETR_ERR_BAD_ARG : 0;
@@ -106,8 +112,8 @@ int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, co
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) return simt_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, dq, dk, dv, dtables, st);
   if (impl == 0)
-    return tc_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, dq, dk, dv, dtables, workspace,
-                        workspace_bytes, st);
+    return tc_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, bias_saved, dq, dk, dv, dtables,
+                        workspace, workspace_bytes, st);
   return VDETR_ERR_BAD_ARG;
 }
 

@@ -19,13 +19,15 @@ int rpe_bias_launch(const VdetrXattnShape* s, const float* xyz, const float* ref
 // impl = 0 (product kernels: tcgen05 + TMA, rpe_xattn_fwd.cu / rpe_xattn_bwd.cu)
 size_t tc_xattn_fwd_workspace(const VdetrXattnShape* s);
 int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
-                 const float* ref, const float* ang, const float* tables, float* out, float* lse, void* ws, size_t ws_bytes,
-                 cudaStream_t st);
+                 const float* ref, const float* ang, const float* tables, float* out, float* lse, float* bias_save,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
+// bytes of the optional per-pair bias buffer the forward can leave for the backward ([B][nQp][nKp] float4; 0 = n/a)
+size_t tc_xattn_bias_save_bytes(const VdetrXattnShape* s);
 size_t tc_xattn_bwd_workspace(const VdetrXattnShape* s);
 int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                  const float* ref, const float* ang, const float* tables, const float* out, const float* lse,
-                 const float* dout, float* dq, float* dk, float* dv, float* dtables, void* ws, size_t ws_bytes,
-                 cudaStream_t st);
+                 const float* dout, const float* bias_saved, float* dq, float* dk, float* dv, float* dtables, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
 
 // Operand packing shared by the product forward / backward kernels (rpe_xattn_fwd.cu):
 //   qp   bf16 [rows][64]   MQA rows = (b*nQp + q)*4 + h        MHA rows = (b*4 + h)*nQp + q     (zero padded)

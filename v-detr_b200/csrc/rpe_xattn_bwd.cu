@@ -38,12 +38,13 @@ struct BwdParams {
   const unsigned* absmax_bits; // bits of max|dout| -> gradient scale
   __half* pb;                  // [rows][nKp]  P
   __half* dsb;                 // [rows][nKp]  g * dS
+  const float4* bias_in;       // [B][nQp][nKp] bias saved by the forward (SAVED), else null
 };
 
 struct SmemLayout {
   uint32_t q, dO, k, v, tables, bias, xyz, geo, rowbuf, bars, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
+__host__ __device__ inline SmemLayout smem_layout(int table_bytes, int bias_bufs = 1) {
   SmemLayout L;
   uint32_t o = 0;
   L.q = o;      o += BM * 128;
@@ -51,7 +52,7 @@ __host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
   L.k = o;      o += BN * 128;
   L.v = o;      o += BN * 128;
   L.tables = o; o += (uint32_t)((table_bytes + 1023) / 1024 * 1024);
-  L.bias = o;   o += QT * BIAS_STRIDE_F4 * 16;
+  L.bias = o;   o += bias_bufs * QT * BIAS_STRIDE_F4 * 16;
   L.xyz = o;    o += 2 * BN * 16;
   L.geo = o;    o += QT * GEO_F4 * 16;
   L.rowbuf = o; o += BM * 4 * 4;
@@ -60,13 +61,15 @@ __host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
   return L;
 }
 
-template <bool HAS_BIAS, bool MQA>
+// SAVED: the bias of every pair was stored by the forward; it is streamed back with bulk copies (double buffered)
+// instead of being recomputed, and the kernel needs neither tables nor query geometry.
+template <bool HAS_BIAS, bool MQA, bool SAVED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = smem_layout(HAS_BIAS ? rpe::pair_table_bytes(P.grid_n) : 0);
+  const SmemLayout L = smem_layout((HAS_BIAS && !SAVED) ? rpe::pair_table_bytes(P.grid_n) : 0, SAVED ? 2 : 1);
   uint8_t* sQ = smem + L.q;
   uint8_t* sdO = smem + L.dO;
   uint8_t* sK = smem + L.k;
@@ -96,7 +99,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     __syncwarp();
     tmem_alloc<TMEM_COLS>(tmem_slot);
-  } else if (HAS_BIAS) {
+  } else if (HAS_BIAS && !SAVED) {
     // tables -> shared memory as fp16 x-pairs, once per (persistent) CTA
     rpe::load_pair_tables(reinterpret_cast<uint4*>(smem + L.tables), P.tables, P.grid_n, tid, NCOMPUTE);
   }
@@ -128,7 +131,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_arrive_expect_tx(bar_q, 2 * BM * 128);
         tma_load_2d(sQ, &tmQ, 0, qrow0, bar_q);
         tma_load_2d(sdO, &tmdO, 0, qrow0, bar_q);
-        const uint32_t kbytes = 2 * BN * 128 + (HAS_BIAS ? BN * 16 : 0);
+        const uint32_t kbytes = 2 * BN * 128 + (HAS_BIAS ? (SAVED ? QT * BN * 16 : BN * 16) : 0);
         for (int j = 0; j < T; ++j) {
           const uint32_t gj = g + j;
           uint64_t* bk = bar_k + (gj & 1);
@@ -138,7 +141,12 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_arrive_expect_tx(bk, kbytes);
           tma_load_2d(sK, &tmK, 0, krow0 + (tile_begin + j) * BN, bk);
           tma_load_2d(sV, &tmV, 0, krow0 + (tile_begin + j) * BN, bk);
-          if (HAS_BIAS) bulk_load_1d(sXyz + (gj & 1) * BN, P.xyz4 + (size_t)b * P.nKp + (tile_begin + j) * BN, BN * 16, bk);
+          if (HAS_BIAS && !SAVED) bulk_load_1d(sXyz + (gj & 1) * BN, P.xyz4 + (size_t)b * P.nKp + (tile_begin + j) * BN, BN * 16, bk);
+          if (HAS_BIAS && SAVED) {
+            const float4* src = P.bias_in + ((size_t)b * P.nQp + q0) * P.nKp + (tile_begin + j) * BN;
+            float4* dstb = sBias + (gj & 1) * (QT * BIAS_STRIDE_F4);
+            for (int qq = 0; qq < QT; ++qq) bulk_load_1d(dstb + qq * BIAS_STRIDE_F4, src + (size_t)qq * P.nKp, BN * 16, bk);
+          }
           if (j == 0) mbar_wait(bar_q, it & 1);
           mbar_wait(bk, (gj >> 1) & 1);
           tc_fence_after();
@@ -163,7 +171,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
       const int q = MQA ? q0 + (row >> 2) : q0 + row;
       const int h = MQA ? (row & 3) : hsel;
-      if (HAS_BIAS) {
+      if (HAS_BIAS && !SAVED) {
         const float4* src = P.geo + ((size_t)b * P.nQp + q0) * GEO_F4;
         for (int i = tid; i < QT * GEO_F4; i += NCOMPUTE) sGeo[i] = __ldg(src + i);
       }
@@ -188,7 +196,8 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < T; ++j) {
         const uint32_t gj = g + j;
         const int key0 = (tile_begin + j) * BN;
-        if (HAS_BIAS) {
+        if (HAS_BIAS && SAVED) mbar_wait(bar_k + (gj & 1), (gj >> 1) & 1);     // the bias tile has landed
+        if (HAS_BIAS && !SAVED) {
           mbar_wait(bar_k + (gj & 1), (gj >> 1) & 1);
           const int kg = warp & 1;
           const float4 kx = sXyz[(gj & 1) * BN + kg * 32 + lane];
@@ -207,9 +216,11 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld16(tdP0 + (gj & 1) * BN + lane_addr + slice * 16, dr);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bar_p + (gj & 1));                     // TMEM buffers of this tile may be overwritten
-        float* brow = nullptr;
-        if (HAS_BIAS) brow = reinterpret_cast<float*>(sBias + (row >> 2) * BIAS_STRIDE_F4 + slice * 16) + (row & 3);
+        if (!SAVED) mbar_arrive(bar_p + (gj & 1));         // TMEM buffers of this tile may be overwritten
+        const float* brow = nullptr;
+        if (HAS_BIAS)
+          brow = reinterpret_cast<const float*>(sBias + (SAVED ? (gj & 1) * (QT * BIAS_STRIDE_F4) : 0) + (row >> 2) * BIAS_STRIDE_F4 +
+                                                slice * 16) + (row & 3);
         uint32_t pk[8], dk_[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
@@ -226,13 +237,14 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[c >> 1] = pack_f16x2(pv[0], pv[1]);
           dk_[c >> 1] = pack_f16x2(dv[0], dv[1]);
         }
+        if (SAVED) mbar_arrive(bar_p + (gj & 1));          // ... and (SAVED) this tile's bias buffer as well
         {
           uint4* dstp = reinterpret_cast<uint4*>(P.pb + grow + key0 + slice * 16);
           uint4* dstd = reinterpret_cast<uint4*>(P.dsb + grow + key0 + slice * 16);
           dstp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dstp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
         }
-        if (HAS_BIAS) named_bar_sync(2, NCOMPUTE);         // (b) every thread has read its bias: the tile may be rewritten
+        if (HAS_BIAS && !SAVED) named_bar_sync(2, NCOMPUTE);   // (b) every thread has read its bias: the tile may be rewritten
       }
       named_bar_sync(2, NCOMPUTE);                         // sRow / sGeo reusable by the next item
     }
@@ -348,8 +360,8 @@ size_t tc_xattn_bwd_workspace(const VdetrXattnShape* s) { return make_plan(s).to
 
 int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                  const float* ref, const float* ang, const float* tables, const float* out, const float* lse,
-                 const float* dout, float* dq, float* dk, float* dv, float* dtables, void* ws, size_t ws_bytes,
-                 cudaStream_t st) {
+                 const float* dout, const float* bias_saved, float* dq, float* dk, float* dv, float* dtables, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
   const bool mqa = s->kv_heads == 1;
   if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
   const BwdPlan pl = make_plan(s);
@@ -394,23 +406,28 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   P.absmax_bits = absmax;
   P.pb = reinterpret_cast<__half*>(w + pl.off_pb);
   P.dsb = reinterpret_cast<__half*>(w + pl.off_dsb);
+  const bool saved = s->has_bias && bias_saved != nullptr;
+  P.bias_in = saved ? reinterpret_cast<const float4*>(bias_saved) : nullptr;
 
-  const int table_bytes = s->has_bias ? rpe::pair_table_bytes(s->grid_n) : 0;
-  const SmemLayout L = smem_layout(table_bytes);
+  const int table_bytes = (s->has_bias && !saved) ? rpe::pair_table_bytes(s->grid_n) : 0;
+  const SmemLayout L = smem_layout(table_bytes, saved ? 2 : 1);
   if (L.total + 1024 > 232448) return VDETR_ERR_UNSUPPORTED;
   const size_t smem = L.total + 1024;
   const int grid = pl.items < vdetr_num_sms() ? pl.items : vdetr_num_sms();
   {
   VdetrTimingScope timing(s->has_bias ? VDETR_T_BWD : VDETR_T_COUNT, st);
-  if (s->has_bias) {
-    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rpe_xattn_bwd_kernel<true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
+  if (saved) {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_bwd_kernel<true, true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
+  } else if (s->has_bias) {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_bwd_kernel<true, true, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
   } else if (mqa) {
-    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rpe_xattn_bwd_kernel<false, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_bwd_kernel<false, true, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
   } else {
-    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rpe_xattn_bwd_kernel<false, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_bwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rpe_xattn_bwd_kernel<false, false, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmdO, tmK, tmV, P);
   }
   }
   VDETR_LAUNCH_CHECK();

@@ -51,6 +51,7 @@ struct FwdParams {
   float* lse;                   // [B,4,nQ]
   float* part_o;                // [items][128][64]   (splits > 1)
   float2* part_ml;              // [items][128] (m in log2 units, l)
+  float4* bias_out;             // [B][nQp][nKp] bias of the 4 heads per pair, or null (saved for the backward)
 };
 
 struct SmemLayout {
@@ -226,6 +227,7 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int q = (warp >> 1) + 8 * u;
             const float4 bias = rpe_bias_pair(sGeo + q * GEO_F4, kx.x, kx.y, kx.z, sTab, P.grid_n, P.log_scale, P.c1, P.c0);
             sBias[q * BIAS_STRIDE_F4 + kg * 32 + lane] = bias;
+            if (P.bias_out) P.bias_out[((size_t)b * P.nQp + q0 + q) * P.nKp + key0 + kg * 32 + lane] = bias;
           }
         }
         named_bar_sync(1, NCOMPUTE);                         // (a) bias tile complete (and previous smax reads done)
@@ -517,11 +519,16 @@ FwdPlan make_plan(const VdetrXattnShape* s) {
 
 }  // namespace
 
+size_t tc_xattn_bias_save_bytes(const VdetrXattnShape* s) {
+  if (!s->has_bias || s->kv_heads != 1) return 0;
+  const FwdPlan pl = make_plan(s);
+  return (size_t)s->B * pl.nQp * pl.nKp * 16;
+}
 size_t tc_xattn_fwd_workspace(const VdetrXattnShape* s) { return make_plan(s).total; }
 
 int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
-                 const float* ref, const float* ang, const float* tables, float* out, float* lse, void* ws, size_t ws_bytes,
-                 cudaStream_t st) {
+                 const float* ref, const float* ang, const float* tables, float* out, float* lse, float* bias_save,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool mqa = s->kv_heads == 1;
   if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
   const FwdPlan pl = make_plan(s);
@@ -555,6 +562,7 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   P.c0 = s->has_bias ? 0.5f * (float)(s->grid_n - 1) : 0.f;
   P.xyz4 = pk.xyz4; P.geo = pk.geo; P.tables = reinterpret_cast<const float4*>(tables);
   P.out = out; P.lse = lse;
+  P.bias_out = s->has_bias ? reinterpret_cast<float4*>(bias_save) : nullptr;
   P.part_o = reinterpret_cast<float*>(w + pl.off_po);
   P.part_ml = reinterpret_cast<float2*>(w + pl.off_pml);
 

@@ -21,6 +21,11 @@ def default_impl() -> int:
     return int(os.environ.get("VDETR_B200_IMPL", IMPL_TCGEN05))
 
 
+def save_bias_enabled() -> bool:
+    """VDETR_B200_SAVE_BIAS=0 trades the 16 B / pair of saved bias for a recompute in the backward."""
+    return os.environ.get("VDETR_B200_SAVE_BIAS", "1") != "0"
+
+
 def _shape(q, k, tables, log_scale, max_value, rotate, has_bias):
     B, nQ, H, hd = q.shape
     nK, kvh = k.shape[1], k.shape[2]
@@ -43,18 +48,25 @@ class _RpeAttention(Function):
         out = torch.empty_like(q)
         lse = torch.empty(s.B, s.H, s.nQ, dtype=torch.float32, device=q.device)
         L = _C.lib()
+        bias_save = None
         with torch.cuda.device(q.device):
             nbytes = L.vdetr_xattn_fwd_workspace_bytes(s, impl)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device) if nbytes else None
+            # training: keep the per-pair bias (16 B / pair) so that the backward streams it instead of recomputing it
+            if has_bias and impl == impl_bwd == IMPL_TCGEN05 and any(ctx.needs_input_grad) and save_bias_enabled():
+                nsave = L.vdetr_xattn_bias_save_bytes(s, impl)
+                if nsave:
+                    bias_save = torch.empty(nsave, dtype=torch.uint8, device=q.device)
             _C.check(L.vdetr_xattn_fwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
-                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
-        ctx.save_for_backward(q, k, v, xyz, ref_pts, ref_angle, tables, out, lse)
+                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(bias_save), _C.ptr(ws), nbytes, impl,
+                                       _C.stream_ptr()))
+        ctx.save_for_backward(q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save)
         ctx.meta = (log_scale, max_value, impl_bwd, has_bias)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, xyz, ref_pts, ref_angle, tables, out, lse = ctx.saved_tensors
+        q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save = ctx.saved_tensors
         log_scale, max_value, impl, has_bias = ctx.meta
         dout = dout.contiguous()
         s = _shape(q, k, tables, log_scale, max_value, ref_angle is not None, has_bias)
@@ -65,8 +77,8 @@ class _RpeAttention(Function):
             nbytes = L.vdetr_xattn_bwd_workspace_bytes(s, impl)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device) if nbytes else None
             _C.check(L.vdetr_xattn_bwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
-                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(dout), _C.ptr(dq), _C.ptr(dk),
-                                       _C.ptr(dv), _C.ptr(dtab), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
+                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(dout), _C.ptr(bias_save), _C.ptr(dq),
+                                       _C.ptr(dk), _C.ptr(dv), _C.ptr(dtab), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
         return dq, dk, dv, None, None, None, dtab, None, None, None, None
 
 
