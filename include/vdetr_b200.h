@@ -138,6 +138,11 @@ size_t vdetr_rpe_dtables_workspace_bytes(const VdetrXattnShape* s);
 int vdetr_rpe_dtables(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
                       const float* dbias, float* dtables, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
+ * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call
+ * copies the 8 counters to the host and clears them (synchronises the device). */
+int vdetr_debug_dt_clocks(unsigned long long* out8);
+
 #ifdef __cplusplus
 }
 #endif

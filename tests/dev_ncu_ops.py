@@ -32,3 +32,10 @@ for it in range(5):
         o.backward(torch.ones_like(o) * 1e-3)
 b.record(); torch.cuda.synchronize()
 print(mode, "B", B, "ms per call", a.elapsed_time(b) / 5)
+if os.environ.get("VDETR_DT_CLOCKS") == "1":
+    import ctypes
+    from vdetr_b200 import _C
+    buf = (ctypes.c_ulonglong * 8)()
+    _C.check(_C.lib().vdetr_debug_dt_clocks(buf))
+    tot = sum(buf) or 1
+    print("dT phase cycles (sum over CTAs, 7 calls):", [f"{n}:{100 * v / tot:.1f}%" for n, v in zip(["A", "zero/B0", "B1", "B2", "B3", "B4", "B4 warp mean", "B4 warp max"], buf)], "total", tot)

@@ -22,15 +22,25 @@
 // 3 transforms are recomputed per vertex into the slots that vertex reads (phase B0).
 #include "rpe_internal.h"
 #include "rpe_fast.cuh"
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace dt3 {
 
-constexpr int QB = 16, KC = 512, NP = QB * KC;       // pairs per unit
-constexpr int THREADS = 512, WARPS = THREADS / 32;
-constexpr int TINY = 8;                              // segments shorter than this use the broadcast mode
+#ifndef VDETR_DT_THREADS
+#define VDETR_DT_THREADS 512
+#define VDETR_DT_QB 16
+#endif
+constexpr int QB = VDETR_DT_QB, KC = 512, NP = QB * KC;       // pairs per unit
+constexpr int THREADS = VDETR_DT_THREADS, WARPS = THREADS / 32;
+constexpr int ITEMS = NP / THREADS;                  // pairs per thread in the per-pair phases (thread-strided)
+static_assert(NP % THREADS == 0 && (NP / 4) % THREADS == 0 && KC % 128 == 0 && NP <= 8192, "unit shape");
+#ifndef VDETR_DT_TINY
+#define VDETR_DT_TINY 8
+#endif
+constexpr int TINY = VDETR_DT_TINY;                              // segments shorter than this use the broadcast mode
 constexpr int MAX_N = 12;                            // cell index + 1 must fit 4 bits with 15 = invalid
 constexpr unsigned FULL = 0xffffffffu;
-static_assert(KC == THREADS, "phase A maps one thread to one key of the chunk");
 
 struct Params {
   int B, nQ, nK, nQp, nKp, n, R, P3;      // R = n + 1 base cells per axis, P3 = n + 2 padded table points per axis
@@ -42,6 +52,8 @@ struct Params {
   const int* qperm;                       // [B][nQ] Morton order of the queries
   const unsigned* absmax_bits;            // -> scale
   float* priv;                            // [gridDim.x][8][P3^3][4]
+  int4 cost;                              // per-segment cost model of the accumulation phase (see seg_cost)
+  unsigned long long* phase_clocks;       // [8] optional (developer): cycles per phase summed over CTAs, else null
 };
 
 __device__ __forceinline__ float scale_of(unsigned bits, int dense) {
@@ -91,7 +103,7 @@ __host__ __device__ inline size_t region_bytes(int n) {
   return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
 }
 __host__ __device__ inline size_t smem_bytes(int n) {
-  return (size_t)NP * 16 + (size_t)NP * 8 + (size_t)NP * 2 + region_bytes(n) + QB * 2 * 16 + 96 * 4;
+  return (size_t)NP * 16 + (size_t)NP * 8 + (size_t)NP * 2 + region_bytes(n) + QB * 2 * 16 + 160 * 4;
 }
 
 // transposed reduction: on return lane j holds sum over lanes of acc[j]
@@ -145,11 +157,15 @@ __device__ __forceinline__ float2 ffma2(float w, float2 d, float2 c) {
 
 // rough instruction cost of accumulating a segment of c pairs (units of half warp-instructions): register mode pays
 // ~4.5 per pair plus a flush, broadcast mode ~16 per pair
-__device__ __forceinline__ int seg_cost(int c) { return c == 0 ? 0 : (c < TINY ? 32 * c + 90 : 9 * c + 280); }
+__device__ __forceinline__ int seg_cost(int c, const int4 k) { return c == 0 ? 0 : (c < TINY ? k.x * c + k.y : k.z * c + k.w); }
 
-// run-aggregated shared-memory counter update: lanes with equal, adjacent `bin` form a run; the run head adds the
-// run length.  Returns the value before the add (broadcast to the run) and this lane's rank inside its run.
-__device__ __forceinline__ int run_add(int* counters, int bin, int lane, int& rank, bool want_old) {
+// Run-aggregated shared-memory counter updates.  Lanes with equal, adjacent `bin` form a run (a warp holds 32
+// consecutive keys of one query, so there are few runs); the head of a run adds the run length.  The run structure
+// found for the histogram is packed into one word per pair and reused by the scatter:
+//   bits [0,12) bin + 1 (0 = pair outside the table)   [12,17) rank inside the run   [17,23) run length
+__device__ __forceinline__ unsigned run_pack(int bin, int lane) {
+  // (straight-line on purpose: a warp-uniform early exit for the single-run case stops the compiler from
+  // interleaving the unrolled per-pair chains and made the histogram phase 50 % slower)
   const int prev = __shfl_up_sync(FULL, bin, 1);
   const bool head = lane == 0 || bin != prev;
   const unsigned heads = __ballot_sync(FULL, head);
@@ -157,11 +173,7 @@ __device__ __forceinline__ int run_add(int* counters, int bin, int lane, int& ra
   const int hl = 31 - __clz(below);
   const unsigned above = (hl == 31) ? 0u : (heads & ~((2u << hl) - 1u));
   const int end = above ? (__ffs(above) - 1) : 32;
-  rank = lane - hl;
-  int old = 0;
-  if (head && bin >= 0) old = atomicAdd(counters + bin, end - hl);
-  if (want_old) old = __shfl_sync(FULL, old, hl);
-  return old;
+  return (unsigned)(bin + 1) | ((unsigned)(lane - hl) << 12) | ((unsigned)(end - hl) << 17);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P) {
@@ -180,9 +192,18 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
   int* s_slow = S.sq + QB;          // [QB]
   int* s_misc = S.sq + 2 * QB;      // [2..2+2*WARPS) scan scratch
   int* s_start = s_misc + 2 + 2 * WARPS;   // [WARPS+1] first sorted entry of every warp's share
+  int* s_warpclk = s_start + WARPS + 1;    // [WARPS] developer clocks
   int* costp = S.offs + nbins + 1;  // [nbins+1] exclusive scan of the per-cell cost estimate
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long t_prev = clock64();
+  auto tick = [&](int phase) {      // call right after a __syncthreads(): time since the previous tick -> phase
+    if (P.phase_clocks && tid == 0) {
+      const long long t = clock64();
+      atomicAdd(P.phase_clocks + phase, (unsigned long long)(t - t_prev));
+      t_prev = t;
+    }
+  };
   const int cells_pad = P.P3 * P.P3 * P.P3;
   float* my_priv = P.priv + (size_t)blockIdx.x * 8 * cells_pad * 4;
   const int corner = lane >> 2, hsel = lane & 3;
@@ -213,50 +234,65 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
       S.sgeo[tid * 2] = hi; S.sgeo[tid * 2 + 1] = lo;
       S.sq[tid] = q; s_slow[tid] = slow;
     }
-    {
+    for (int i = tid; i < KC; i += THREADS) {
       float4 kx = make_float4(1e9f, 1e9f, 1e9f, 0.f);
-      if (k0 + tid < P.nK) kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + tid);
-      S.sxyz[tid] = kx;
+      if (k0 + i < P.nK) kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + i);
+      S.sxyz[i] = kx;
     }
     __syncthreads();
     bool any_slow = false;
 #pragma unroll
     for (int ql = 0; ql < QB; ++ql) any_slow = any_slow || (s_slow[ql] != 0 && S.sq[ql] >= 0);
 
-    // ---- phase A: records.  One query row (512 keys) per iteration, thread = key.
+    // ---- phase A: records.  A thread takes 4 consecutive keys of one query at a time so that the scaled-fp16 dS of
+    // the 4 heads arrives as four 8-byte loads (64 loads of 2 bytes per thread left the phase latency bound).
     {
-      const float4 kx = S.sxyz[tid];
-      const bool kvalid = k0 + tid < P.nK;
-#pragma unroll 2
-      for (int ql = 0; ql < QB; ++ql) {
+      constexpr int KG = KC / 4, GI = NP / 4 / THREADS;
+#pragma unroll 1
+      for (int gi = 0; gi < GI; ++gi) {
+        const int g = gi * THREADS + tid, ql = g / KG, kl0 = (g % KG) * 4;
         const int q = S.sq[ql];
-        uint4 rec = make_uint4(0u, 0u, 0u, 0x00FFFFFFu);
-        uint2 dv = make_uint2(0u, 0u);
-        if (q >= 0 && kvalid) {
-          const __half* dp = P.dsb + ((size_t)b * P.nQp + q) * 4 * P.nKp + k0 + tid;
-          const unsigned short d0 = __ldg(reinterpret_cast<const unsigned short*>(dp));
-          const unsigned short d1 = __ldg(reinterpret_cast<const unsigned short*>(dp + P.nKp));
-          const unsigned short d2 = __ldg(reinterpret_cast<const unsigned short*>(dp + 2 * (size_t)P.nKp));
-          const unsigned short d3 = __ldg(reinterpret_cast<const unsigned short*>(dp + 3 * (size_t)P.nKp));
-          dv = make_uint2((unsigned)d0 | ((unsigned)d1 << 16), (unsigned)d2 | ((unsigned)d3 << 16));
-          if (!s_slow[ql]) {
-            const float4 hi = S.sgeo[ql * 2], lo = S.sgeo[ql * 2 + 1];
-            unsigned nxp, nxm, nyp, nym, nzp, nzm, fxp, fxm, fyp, fym, fzp, fzm;
-            axis_rec(hi.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxp, fxp);
-            axis_rec(lo.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxm, fxm);
-            axis_rec(hi.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nyp, fyp);
-            axis_rec(lo.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nym, fym);
-            axis_rec(hi.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzp, fzp);
-            axis_rec(lo.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzm, fzm);
-            rec.x = fxp | (fxm << 16); rec.y = fyp | (fym << 16); rec.z = fzp | (fzm << 16);
-            rec.w = nxp | (nxm << 4) | (nyp << 8) | (nym << 12) | (nzp << 16) | (nzm << 20);
-          }
+        uint2 hd[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) hd[h] = make_uint2(0u, 0u);
+        const bool any = q >= 0 && k0 + kl0 < P.nK;
+        if (any) {
+          const __half* dp = P.dsb + ((size_t)b * P.nQp + q) * 4 * P.nKp + k0 + kl0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) hd[h] = __ldg(reinterpret_cast<const uint2*>(dp + (size_t)h * P.nKp));
         }
-        S.recs[ql * KC + tid] = rec;
-        S.dsv[ql * KC + tid] = dv;
+        const bool fast = any && !s_slow[ql];
+        const float4 hi = S.sgeo[ql * 2], lo = S.sgeo[ql * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kl = kl0 + j, p = ql * KC + kl;
+          uint4 rec = make_uint4(0u, 0u, 0u, 0x00FFFFFFu);
+          uint2 dv = make_uint2(0u, 0u);
+          if (any && k0 + kl < P.nK) {
+            const int sh = 16 * (j & 1);
+            const unsigned w0 = (j < 2) ? hd[0].x : hd[0].y, w1 = (j < 2) ? hd[1].x : hd[1].y;
+            const unsigned w2 = (j < 2) ? hd[2].x : hd[2].y, w3 = (j < 2) ? hd[3].x : hd[3].y;
+            dv = make_uint2(((w0 >> sh) & 0xFFFFu) | (((w1 >> sh) & 0xFFFFu) << 16), ((w2 >> sh) & 0xFFFFu) | (((w3 >> sh) & 0xFFFFu) << 16));
+            if (fast) {
+              const float4 kx = S.sxyz[kl];
+              unsigned nxp, nxm, nyp, nym, nzp, nzm, fxp, fxm, fyp, fym, fzp, fzm;
+              axis_rec(hi.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxp, fxp);
+              axis_rec(lo.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxm, fxm);
+              axis_rec(hi.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nyp, fyp);
+              axis_rec(lo.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nym, fym);
+              axis_rec(hi.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzp, fzp);
+              axis_rec(lo.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzm, fzm);
+              rec.x = fxp | (fxm << 16); rec.y = fyp | (fym << 16); rec.z = fzp | (fzm << 16);
+              rec.w = nxp | (nxm << 4) | (nyp << 8) | (nym << 12) | (nzp << 16) | (nzm << 20);
+            }
+          }
+          S.recs[p] = rec;
+          S.dsv[p] = dv;
+        }
       }
     }
     __syncthreads();                      // records complete; the xyz staging area becomes hist / offs
+    tick(0);
 
     for (int vert = 0; vert < 8; ++vert) {
       int xs, ys, zs;
@@ -266,44 +302,45 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
 
       // ---- B0: boxes that are not axis aligned: this vertex's own 3 transforms go into the slots it reads
       if (any_slow) {
-        for (int ql = 0; ql < QB; ++ql) {
-          if (!s_slow[ql] || S.sq[ql] < 0) continue;                         // block-uniform
-          if (k0 + tid < P.nK) {
-            const float4* g = P.geo + ((size_t)b * P.nQp + S.sq[ql]) * 9;
-            const float* vv = reinterpret_cast<const float*>(g + 2);
-            const float4 rot = __ldg(g + 8);
-            const float4 kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + tid);
-            const float dx = __ldg(vv + vert * 3) - kx.x, dy = __ldg(vv + vert * 3 + 1) - kx.y, dz = __ldg(vv + vert * 3 + 2) - kx.z;
-            const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
-            unsigned nx, ny, nz, fx, fy, fz;
-            axis_rec(tx, P.log_scale, P.c1, P.c0, P.n, nx, fx);
-            axis_rec(ty, P.log_scale, P.c1, P.c0, P.n, ny, fy);
-            axis_rec(dz, P.log_scale, P.c1, P.c0, P.n, nz, fz);
-            uint4 rec = S.recs[ql * KC + tid];
-            rec.x = (rec.x & ~(0xFFFFu << shx)) | (fx << shx);
-            rec.y = (rec.y & ~(0xFFFFu << shy)) | (fy << shy);
-            rec.z = (rec.z & ~(0xFFFFu << shz)) | (fz << shz);
-            rec.w = (rec.w & ~((15u << nbx) | (15u << nby) | (15u << nbz))) | (nx << nbx) | (ny << nby) | (nz << nbz);
-            S.recs[ql * KC + tid] = rec;
-          }
+        for (int it = 0; it < ITEMS; ++it) {
+          const int p = it * THREADS + tid, ql = p / KC, kl = p % KC;          // ql is warp-uniform
+          if (!s_slow[ql] || S.sq[ql] < 0 || k0 + kl >= P.nK) continue;
+          const float4* g = P.geo + ((size_t)b * P.nQp + S.sq[ql]) * 9;
+          const float* vv = reinterpret_cast<const float*>(g + 2);
+          const float4 rot = __ldg(g + 8);
+          const float4 kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + kl);
+          const float dx = __ldg(vv + vert * 3) - kx.x, dy = __ldg(vv + vert * 3 + 1) - kx.y, dz = __ldg(vv + vert * 3 + 2) - kx.z;
+          const float tx = rot.x * dx - rot.y * dy, ty = rot.y * dx + rot.x * dy;
+          unsigned nx, ny, nz, fx, fy, fz;
+          axis_rec(tx, P.log_scale, P.c1, P.c0, P.n, nx, fx);
+          axis_rec(ty, P.log_scale, P.c1, P.c0, P.n, ny, fy);
+          axis_rec(dz, P.log_scale, P.c1, P.c0, P.n, nz, fz);
+          uint4 rec = S.recs[p];
+          rec.x = (rec.x & ~(0xFFFFu << shx)) | (fx << shx);
+          rec.y = (rec.y & ~(0xFFFFu << shy)) | (fy << shy);
+          rec.z = (rec.z & ~(0xFFFFu << shz)) | (fz << shz);
+          rec.w = (rec.w & ~((15u << nbx) | (15u << nby) | (15u << nbz))) | (nx << nbx) | (ny << nby) | (nz << nbz);
+          S.recs[p] = rec;
         }
       }
       for (int i = tid; i < nbins; i += THREADS) S.hist[i] = 0;
       __syncthreads();
+      tick(1);
 
       // ---- B1: histogram of the cells
-      int mybin[QB];
+      unsigned myrun[ITEMS];
 #pragma unroll
-      for (int ql = 0; ql < QB; ++ql) {
-        const unsigned w = S.recs[ql * KC + tid].w;
+      for (int it = 0; it < ITEMS; ++it) {
+        const unsigned w = S.recs[it * THREADS + tid].w;
         const int nx = (w >> nbx) & 15, ny = (w >> nby) & 15, nz = (w >> nbz) & 15;
         int bin = (nz * P.R + ny) * P.R + nx;
         if (max(nx, max(ny, nz)) == 15) bin = -1;
-        mybin[ql] = bin;
-        int rank;
-        run_add(S.hist, bin, lane, rank, false);
+        const unsigned r = run_pack(bin, lane);
+        myrun[it] = r;
+        if ((r & 0x1F000u) == 0u && bin >= 0) atomicAdd(S.hist + bin, (int)(r >> 17));        // run head
       }
       __syncthreads();
+      tick(2);
 
       // ---- B2: exclusive scan of the histogram (all threads, contiguous slices of bins) and of a per-cell cost
       // estimate that balances the accumulation phase over the warps
@@ -311,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
         const int per = (nbins + THREADS - 1) / THREADS;
         const int lo = tid * per, hi = min(nbins, lo + per);
         int mine = 0, minec = 0;
-        for (int i = lo; i < hi; ++i) { const int c = S.hist[i]; mine += c; minec += seg_cost(c); }
+        for (int i = lo; i < hi; ++i) { const int c = S.hist[i]; mine += c; minec += seg_cost(c, P.cost); }
         int x = mine, xc = minec;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -327,11 +364,12 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
           const int c = S.hist[i];
           S.hist[i] = run | ((c < TINY) ? (int)0x80000000 : 0);      // scatter cursor; bit 31 marks a tiny segment
           S.offs[i] = run; costp[i] = runc;
-          run += c; runc += seg_cost(c);
+          run += c; runc += seg_cost(c, P.cost);
         }
         if (tid == THREADS - 1) { S.offs[nbins] = run; costp[nbins] = runc; }
       }
       __syncthreads();
+      tick(3);
 
       // ---- B3: every warp finds where its equal-cost share of the sorted list starts, then the counting-sort scatter
       {
@@ -348,16 +386,20 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
         if (lane == 0) { s_start[warp] = start; if (warp == 0) s_start[WARPS] = S.offs[nbins]; }
       }
 #pragma unroll
-      for (int ql = 0; ql < QB; ++ql) {
-        const int bin = mybin[ql];
-        int rank;
-        const int base = run_add(S.hist, bin, lane, rank, true);
-        if (bin >= 0) S.sorted[(base & 0x7fffffff) + rank] = (uint16_t)((ql * KC + tid) | ((base >> 16) & 0x8000));
+      for (int it = 0; it < ITEMS; ++it) {
+        const unsigned r = myrun[it];
+        const int bin = (int)(r & 0xFFFu) - 1, rank = (int)((r >> 12) & 31u);
+        int base = 0;
+        if (rank == 0 && bin >= 0) base = atomicAdd(S.hist + bin, (int)(r >> 17));
+        base = __shfl_sync(FULL, base, lane - rank);
+        if (bin >= 0) S.sorted[(base & 0x7fffffff) + rank] = (uint16_t)((it * THREADS + tid) | ((base >> 16) & 0x8000));
       }
       __syncthreads();
+      tick(4);
 
       // ---- B4: accumulate.  Warp w owns sorted[c0, c1).
       {
+        const long long t_b4 = P.phase_clocks ? clock64() : 0;
         const int c0 = s_start[warp], c1 = s_start[warp + 1];
         float* tab = my_priv + (size_t)vert * cells_pad * 4;
         float2 acc[16];                   // [corner][head pair]
@@ -456,8 +498,16 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
           }
         }
         if (cur_key >= 0) flush(cur_key);
+        if (P.phase_clocks && lane == 0) s_warpclk[warp] = (int)(clock64() - t_b4);
       }
       __syncthreads();                    // hist / offs / sorted are rewritten by the next vertex
+      tick(5);
+      if (P.phase_clocks && tid == 0) {         // balance of the accumulation phase: mean and max warp time
+        int mx = 0, sum = 0;
+        for (int w = 0; w < WARPS; ++w) { mx = max(mx, s_warpclk[w]); sum += s_warpclk[w]; }
+        atomicAdd(P.phase_clocks + 6, (unsigned long long)(sum / WARPS));
+        atomicAdd(P.phase_clocks + 7, (unsigned long long)mx);
+      }
     }
   }
 }
@@ -561,23 +611,32 @@ __global__ void __launch_bounds__(1024, 1) rpe_dtables_qorder_kernel(const float
   for (int i = tid; i < nQ; i += blockDim.x) out[i] = (int)(keys[i] & 0xffffffffu);
 }
 
-// dense fp32 dbias [B][nQ][nK][4] -> scaled fp16 rows [(b*nQ + q)*4 + h][nK]  (C-ABI helper only)
-__global__ void rpe_dtables_dense_pack_kernel(const float4* __restrict__ ds4, size_t pairs, int nK, __half* __restrict__ dsb,
-                                              const unsigned* absmax_bits) {
+// dense fp32 dbias [B][nQ][nK][4] -> scaled fp16 rows [(b*nQ + q)*4 + h][nKp]  (C-ABI helper only)
+__global__ void rpe_dtables_dense_pack_kernel(const float4* __restrict__ ds4, size_t pairs, int nK, int nKp,
+                                              __half* __restrict__ dsb, const unsigned* absmax_bits) {
   const float sc = scale_of(*absmax_bits, 1);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
     const float4 d = __ldg(ds4 + i);
     const size_t bq = i / nK;
     const int k = (int)(i - bq * nK);
-    __half* dst = dsb + bq * 4 * (size_t)nK + k;
+    __half* dst = dsb + bq * 4 * (size_t)nKp + k;
     dst[0] = __float2half_rn(d.x * sc);
-    dst[(size_t)nK] = __float2half_rn(d.y * sc);
-    dst[2 * (size_t)nK] = __float2half_rn(d.z * sc);
-    dst[3 * (size_t)nK] = __float2half_rn(d.w * sc);
+    dst[(size_t)nKp] = __float2half_rn(d.y * sc);
+    dst[2 * (size_t)nKp] = __float2half_rn(d.z * sc);
+    dst[3 * (size_t)nKp] = __float2half_rn(d.w * sc);
   }
 }
 
 }  // namespace dt3
+
+// developer aid: VDETR_DT_CLOCKS=1 accumulates per-phase cycle counts (read with vdetr_debug_dt_clocks)
+static unsigned long long* g_dt_clocks = nullptr;
+extern "C" int vdetr_debug_dt_clocks(unsigned long long* out8) {
+  if (!g_dt_clocks) return VDETR_ERR_BAD_ARG;
+  VDETR_CUDA_TRY(cudaMemcpy(out8, g_dt_clocks, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  VDETR_CUDA_TRY(cudaMemset(g_dt_clocks, 0, 8 * sizeof(unsigned long long)));
+  return 0;
+}
 
 // scratch of the dTables pass: query order + one zero-padded private table per CTA
 size_t rpe_dtables_scratch_bytes(const VdetrXattnShape* s) {
@@ -597,6 +656,7 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
     return 0;
   }
   if (n < 1 || n > dt3::MAX_N) return VDETR_ERR_UNSUPPORTED;
+  if (nKp % 4 != 0) return VDETR_ERR_BAD_ARG;                // dS rows are read 4 keys (8 bytes) at a time
   if (!scratch || scratch_bytes < rpe_dtables_scratch_bytes(s)) return VDETR_ERR_WORKSPACE;
   const size_t smem = dt3::smem_bytes(n);
   if (smem > 232448) return VDETR_ERR_UNSUPPORTED;
@@ -614,6 +674,18 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   P.c1 = (float)n / (2.0f * 3.0f * s->max_value);
   P.c0 = 0.5f * (float)(n - 1);
   P.xyz4 = xyz4; P.geo = geo; P.dsb = dsb; P.qperm = qperm; P.absmax_bits = absmax_bits; P.priv = priv;
+  static const bool want_clocks = []() { const char* e = getenv("VDETR_DT_CLOCKS"); return e && e[0] == '1'; }();
+  if (want_clocks && !g_dt_clocks) {
+    VDETR_CUDA_TRY(cudaMalloc(&g_dt_clocks, 8 * sizeof(unsigned long long)));
+    VDETR_CUDA_TRY(cudaMemset(g_dt_clocks, 0, 8 * sizeof(unsigned long long)));
+  }
+  P.phase_clocks = want_clocks ? g_dt_clocks : nullptr;
+  static const int4 cost = []() {
+    int4 k = make_int4(60, 200, 5, 600);
+    if (const char* e = getenv("VDETR_DT_COST")) sscanf(e, "%d,%d,%d,%d", &k.x, &k.y, &k.z, &k.w);
+    return k;
+  }();
+  P.cost = cost;
   const int grid = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
   const size_t copy_bytes = (size_t)8 * P.P3 * P.P3 * P.P3 * 4 * sizeof(float);
 
@@ -632,30 +704,35 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
 
 // C-ABI helper behind vdetr_rpe_dtables: dense dS [B,nQ,nK,4] -> dTables (packs xyz / geometry / fp16 dS itself).
 size_t rpe_dtables_workspace(const VdetrXattnShape* s) {
-  return vdetr_align_up((size_t)s->B * s->nK * 16, 1024) + vdetr_align_up((size_t)s->B * s->nQ * 9 * 16, 1024) +
-         vdetr_align_up((size_t)s->B * s->nQ * 4 * s->nK * 2, 1024) + 1024 + rpe_dtables_scratch_bytes(s);
+  const size_t nKp = vdetr_align_up((size_t)s->nK, 64);
+  return vdetr_align_up((size_t)s->B * nKp * 16, 1024) + vdetr_align_up((size_t)s->B * s->nQ * 9 * 16, 1024) +
+         vdetr_align_up((size_t)s->B * s->nQ * 4 * nKp * 2, 1024) + 1024 + rpe_dtables_scratch_bytes(s);
 }
 int rpe_dtables_dense(const VdetrXattnShape* s, const float* xyz, const float* ref, const float* ang, const float* ds4,
                       float* dtables, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!ws || ws_bytes < rpe_dtables_workspace(s)) return VDETR_ERR_WORKSPACE;
   uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  const int nKp = (int)vdetr_align_up((size_t)s->nK, 64);
   VdetrPack pk = {};
-  pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = s->nQ; pk.nKp = s->nK; pk.kvh = 1; pk.has_bias = 1;
+  pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = s->nQ; pk.nKp = nKp; pk.kvh = 1; pk.has_bias = 1;
   pk.xyz = xyz; pk.ref = ref; pk.ang = s->rotate ? ang : nullptr;
   size_t o = 0;
-  pk.xyz4 = reinterpret_cast<float4*>(w + o); o += vdetr_align_up((size_t)s->B * s->nK * 16, 1024);
+  pk.xyz4 = reinterpret_cast<float4*>(w + o); o += vdetr_align_up((size_t)s->B * nKp * 16, 1024);
   pk.geo = reinterpret_cast<float4*>(w + o); o += vdetr_align_up((size_t)s->B * s->nQ * 9 * 16, 1024);
-  __half* dsb = reinterpret_cast<__half*>(w + o); o += vdetr_align_up((size_t)s->B * s->nQ * 4 * s->nK * 2, 1024);
+  __half* dsb = reinterpret_cast<__half*>(w + o);
+  const size_t dsb_bytes = (size_t)s->B * s->nQ * 4 * nKp * 2;
+  o += vdetr_align_up(dsb_bytes, 1024);
   unsigned* absmax = reinterpret_cast<unsigned*>(w + o); o += 1024;
   if (s->B == 0 || s->nQ == 0 || s->nK == 0)
-    return rpe_dtables_launch(s, s->nQ, s->nK, nullptr, nullptr, nullptr, nullptr, 1, dtables, w + o, ws_bytes - o, st);
+    return rpe_dtables_launch(s, s->nQ, nKp, nullptr, nullptr, nullptr, nullptr, 1, dtables, w + o, ws_bytes - o, st);
   vdetr_pack_kernel<<<vdetr_num_sms(), 256, 0, st>>>(pk);
   VDETR_LAUNCH_CHECK();
   const size_t pairs = (size_t)s->B * s->nQ * s->nK;
   VDETR_CUDA_TRY(cudaMemsetAsync(absmax, 0, 4, st));
+  VDETR_CUDA_TRY(cudaMemsetAsync(dsb, 0, dsb_bytes, st));          // padding columns
   vdetr_absmax_kernel<<<vdetr_num_sms() * 2, 256, 0, st>>>(ds4, pairs * 4, absmax);
   VDETR_LAUNCH_CHECK();
-  dt3::rpe_dtables_dense_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(reinterpret_cast<const float4*>(ds4), pairs, s->nK, dsb, absmax);
+  dt3::rpe_dtables_dense_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(reinterpret_cast<const float4*>(ds4), pairs, s->nK, nKp, dsb, absmax);
   VDETR_LAUNCH_CHECK();
-  return rpe_dtables_launch(s, s->nQ, s->nK, pk.xyz4, pk.geo, dsb, absmax, 1, dtables, w + o, ws_bytes - o, st);
+  return rpe_dtables_launch(s, s->nQ, nKp, pk.xyz4, pk.geo, dsb, absmax, 1, dtables, w + o, ws_bytes - o, st);
 }
