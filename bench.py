@@ -316,7 +316,7 @@ def main():
             torch.cuda.synchronize()
         os.makedirs(os.path.dirname(os.path.abspath(a.profile)), exist_ok=True)
         with open(a.profile, "w") as f:
-            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+            f.write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=90, max_name_column_width=110))
         return
     sampler = ClockSampler(local)
     sampler.start()

@@ -10,6 +10,24 @@ import copy
 from functools import partial
 
 import torch.nn as nn
+import torch.nn.functional as F
+
+
+def pointwise_tokens(seq, x):
+    """Apply a Conv1d(k=1)/BatchNorm1d/activation/Dropout stack to token-major features x [T, C_in] -> [T, C_out].
+
+    A kernel-size-1 Conv1d over [B, C, N] is the Linear map of every token, and BatchNorm1d over [B, C, N] and over
+    [B*N, C] normalises the same B*N samples per channel, so the same parameters / running statistics give the same
+    result (up to summation order) -- but as plain GEMMs on contiguous rows instead of cuDNN convolutions on a
+    permuted copy (the cuDNN weight-gradient kernels for the 1/3/18-channel output convolutions alone cost ~80 us
+    per call on a B200).  Used for the box heads (models/helpers.py:74-141) and the query-position MLP (:17-33)."""
+    for m in seq:
+        if isinstance(m, nn.Conv1d):
+            assert m.kernel_size == (1,) and m.stride == (1,) and m.groups == 1
+            x = F.linear(x, m.weight.squeeze(-1), m.bias)
+        else:
+            x = m(x)
+    return x
 
 
 class PositionEmbeddingLearned(nn.Module):
@@ -25,6 +43,12 @@ class PositionEmbeddingLearned(nn.Module):
 
     def forward(self, xyz):
         return self.position_embedding_head(xyz.transpose(1, 2).contiguous())
+
+    def forward_tokens(self, xyz):
+        """[B, N, C_in] -> [N, B, C_out]: what callers build with forward(xyz).permute(2, 0, 1), computed token-major."""
+        B, N, C = xyz.shape
+        out = pointwise_tokens(self.position_embedding_head, xyz.reshape(B * N, C))
+        return out.view(B, N, -1).permute(1, 0, 2)
 
 
 class BatchNormDim1Swap(nn.BatchNorm1d):
@@ -82,6 +106,15 @@ class GenericMLP(nn.Module):
 
     def forward(self, x):
         return self.layers(x)
+
+    def forward_tokens(self, x):
+        """Token-major evaluation of a use_conv=True stack: x [T, C_in] -> [T, C_out] (see pointwise_tokens)."""
+        return pointwise_tokens(self.layers, x)
+
+    @property
+    def supports_tokens(self):
+        return all(isinstance(m, (nn.Conv1d, nn.BatchNorm1d, nn.ReLU, nn.GELU, nn.LeakyReLU, nn.Dropout, nn.Identity))
+                   and not isinstance(m, BatchNormDim1Swap) for m in self.layers)
 
 
 def get_clones(module, N):

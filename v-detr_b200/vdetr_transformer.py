@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 from functools import partial
 from typing import Optional
 
@@ -503,6 +504,8 @@ class TransformerDecoder(nn.Module):
                 nn.init.constant_(hs[name].layers[-1].bias.data, 0.0)
         self.box_processor = BoxProcessor(dataset_config, cls_loss=cls_loss)
         self.sort_keys = True       # Morton-order the key tokens once per forward (see module docstring)
+        self.parallel_heads = os.environ.get("VDETR_B200_PARALLEL_HEADS", "1") != "0"
+        self._head_streams = {}
 
     def _head_factory(self, decoder_dim, mlp_dropout):
         return partial(GenericMLP, norm_fn_name=self.mlp_norm, activation=self.mlp_act, use_conv=True,
@@ -535,26 +538,56 @@ class TransformerDecoder(nn.Module):
             if p.dim() > 1:
                 init(p)
 
+    HEAD_NAMES = ("sem_cls_head", "center_head", "size_head", "angle_cls_head", "angle_residual_head")
+
+    def _run_heads(self, heads, box_features):
+        """box_features [nQ,B,C] -> {head: [B,nQ,out]} (:256-300).  The heads are evaluated token-major (GEMMs on the
+        contiguous [nQ*B, C] rows instead of Conv1d on a permuted copy, see helpers.pointwise_tokens); the 5 heads of
+        a level read the same features and are independent, so on CUDA they are issued on 5 forked streams and
+        joined: their small kernels (and, through autograd's stream bookkeeping, their backward kernels) overlap."""
+        nQ, B, C = box_features.shape
+        tokens = all(heads[n].supports_tokens for n in self.HEAD_NAMES)
+        feats = box_features.reshape(nQ * B, C) if tokens else box_features.permute(1, 2, 0)
+
+        def run(n):
+            if tokens:
+                return heads[n].forward_tokens(feats).view(nQ, B, -1).transpose(0, 1)
+            return heads[n](feats).transpose(1, 2)
+        if not (feats.is_cuda and self.parallel_heads):
+            return {n: run(n) for n in self.HEAD_NAMES}
+        cur = torch.cuda.current_stream(feats.device)
+        key = feats.device.index
+        if key not in self._head_streams:
+            self._head_streams[key] = [torch.cuda.Stream(feats.device) for _ in self.HEAD_NAMES]
+        out = {}
+        for n, st in zip(self.HEAD_NAMES, self._head_streams[key]):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                out[n] = run(n)
+        for st in self._head_streams[key]:
+            cur.wait_stream(st)
+        return out
+
     def get_proposal_box_predictions_refine(self, idx, query_xyz, point_cloud_dims, box_features,
                                             pre_center_normalized=None, pre_size_normalized=None):
         """box_features [nQ,B,C] -> dict of box predictions (:244-333)."""
         assert pre_center_normalized is not None and pre_size_normalized is not None
-        feats = box_features.permute(1, 2, 0)
         heads = self.mlp_heads[idx] if self.mlp_sep else self.mlp_heads
         lo, hi = point_cloud_dims
         scene = (hi - lo).unsqueeze(1)
         origin = lo.unsqueeze(1)
-        cls_logits = heads["sem_cls_head"](feats).transpose(1, 2)
+        raw = self._run_heads(heads, box_features)
+        cls_logits = raw["sem_cls_head"]
         pre_center = pre_center_normalized * scene + origin
         pre_size = pre_size_normalized * scene
-        center_reg = heads["center_head"](feats).transpose(1, 2).contiguous()
+        center_reg = raw["center_head"].contiguous()
         center = center_reg * pre_size + pre_center
         center_norm = (center - origin) / scene
-        size_reg = heads["size_head"](feats).transpose(1, 2).contiguous()
+        size_reg = raw["size_head"].contiguous()
         size = torch.exp(size_reg) * pre_size
         size_norm = size / scene
-        angle_logits = heads["angle_cls_head"](feats).transpose(1, 2)
-        angle_res_norm = heads["angle_residual_head"](feats).transpose(1, 2)
+        angle_logits = raw["angle_cls_head"]
+        angle_res_norm = raw["angle_residual_head"]
         angle_res = angle_res_norm * (np.pi / angle_res_norm.shape[-1])
         angle, angle_prob = self.box_processor.compute_predicted_angle(angle_logits, angle_res)
         corners = self.box_processor.box_parametrization_to_corners(center, size, angle)
@@ -621,7 +654,7 @@ class TransformerDecoder(nn.Module):
                 reference_size = pred["size_unnormalized"].clone().detach()
                 reference_angle = pred["angle_continuous"].clone().detach()
             query_reference = torch.cat([reference_center, reference_size], dim=-1)
-            qpos = self.query_pos_projection[idx](query_reference).permute(2, 0, 1)
+            qpos = self.query_pos_projection[idx].forward_tokens(query_reference)
             if self.pos_for_key:
                 pos = self.key_pos_projection[idx](enc_xyz).permute(2, 0, 1)
             output, attn = layer(output, mem_l, reference_point, reference_angle, xyz_l, point_cloud_dims,
