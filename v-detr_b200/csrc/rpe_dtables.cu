@@ -176,6 +176,15 @@ __device__ __forceinline__ unsigned run_pack(int bin, int lane) {
   return (unsigned)(bin + 1) | ((unsigned)(lane - hl) << 12) | ((unsigned)(end - hl) << 17);
 }
 
+__device__ __forceinline__ float2 fmul2(float w, float2 d) {
+  unsigned long long rd, ra, rb;
+  const float2 ww = make_float2(w, w);
+  ra = *reinterpret_cast<const unsigned long long*>(&ww);
+  rb = *reinterpret_cast<const unsigned long long*>(&d);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P) {
   extern __shared__ __align__(16) uint8_t sm[];
   Smem S;
@@ -405,13 +414,13 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
         float2 acc[16];                   // [corner][head pair]
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
-        int cur_key = -1;                 // nz << 8 | ny << 4 | nx of the cell being accumulated
+        unsigned cur_key = 0xFFFFFFFEu;   // masked nibble word of the cell being accumulated (none yet)
 
-        auto cell_addr = [&](int key) -> float* {
-          const int nx = key & 15, ny = (key >> 4) & 15, nz = key >> 8;
+        auto cell_addr = [&](unsigned key) -> float* {
+          const int nx = (key >> nbx) & 15, ny = (key >> nby) & 15, nz = (key >> nbz) & 15;
           return tab + ((((nz + cz) * P.P3 + (ny + cy)) * P.P3 + (nx + cx)) << 2) + hsel;
         };
-        auto flush = [&](int key) {
+        auto flush = [&](unsigned key) {
           float a[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { a[2 * j] = acc[j].x; a[2 * j + 1] = acc[j].y; acc[j] = make_float2(0.f, 0.f); }
@@ -421,33 +430,34 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
         };
 
         // software pipeline: the entry / record / dS of step s+1 are loaded while step s is accumulated
-        bool live_n = c0 + lane < c1;
-        unsigned ent_n = live_n ? S.sorted[c0 + lane] : 0u;
+        // (reads past c1 stay inside the shared-memory allocation and are masked to valid record ids)
+        const unsigned vmask = (15u << nbx) | (15u << nby) | (15u << nbz);
+        const unsigned selx = xs ? 0x7432u : 0x7410u, sely = ys ? 0x7432u : 0x7410u, selz = zs ? 0x7432u : 0x7410u;
+        const uint16_t* sp = S.sorted + c0 + lane;
+        unsigned ent_n = *sp;
         uint4 rec_n = S.recs[ent_n & 0x1FFFu];
         uint2 dv_n = S.dsv[ent_n & 0x1FFFu];
         for (int p0 = c0; p0 < c1; p0 += 32) {
-          const bool live = live_n;
+          const bool live = p0 + lane < c1;
           const unsigned ent = ent_n;
           const uint4 rec = rec_n;
           const uint2 dv = dv_n;
-          {
-            const int pn = p0 + 32 + lane;
-            live_n = pn < c1;
-            ent_n = live_n ? S.sorted[pn] : 0u;
-            rec_n = S.recs[ent_n & 0x1FFFu];
-            dv_n = S.dsv[ent_n & 0x1FFFu];
-          }
-          const int key = live ? (int)(((rec.w >> nbx) & 15u) | (((rec.w >> nby) & 15u) << 4) | (((rec.w >> nbz) & 15u) << 8)) : -2;
-          // fraction u / 65536 without I2F: (2^23 + u) * 2^-16 - 128
-          const float fx = fmaf(__uint_as_float(((rec.x >> shx) & 0xFFFFu) | 0x4B000000u), 0x1p-16f, -128.f);
-          const float fy = fmaf(__uint_as_float(((rec.y >> shy) & 0xFFFFu) | 0x4B000000u), 0x1p-16f, -128.f);
-          const float fz = fmaf(__uint_as_float(((rec.z >> shz) & 0xFFFFu) | 0x4B000000u), 0x1p-16f, -128.f);
+          sp += 32;
+          ent_n = *sp;
+          rec_n = S.recs[ent_n & 0x1FFFu];
+          dv_n = S.dsv[ent_n & 0x1FFFu];
+          // cell identity = the 3 nibbles this vertex reads, left in place (dead lanes: a value no cell can have)
+          const unsigned key = live ? (rec.w & vmask) : 0xFFFFFFFFu;
+          // fraction u / 65536 without I2F: bytes (u.lo, u.hi, 0x00, 0x4B) = 2^23 + u ;  (2^23 + u) * 2^-16 - 128
+          const float fx = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, selx)), 0x1p-16f, -128.f);
+          const float fy = fmaf(__uint_as_float(__byte_perm(rec.y, 0x4B000000u, sely)), 0x1p-16f, -128.f);
+          const float fz = fmaf(__uint_as_float(__byte_perm(rec.z, 0x4B000000u, selz)), 0x1p-16f, -128.f);
           float w[8];
           {
-            const float wz0 = 1.f - fz, wy0 = 1.f - fy, wx0 = 1.f - fx;
-            const float a00 = wz0 * wy0, a01 = wz0 * fy, a10 = fz * wy0, a11 = fz * fy;
-            w[0] = a00 * wx0; w[1] = a00 * fx; w[2] = a01 * wx0; w[3] = a01 * fx;
-            w[4] = a10 * wx0; w[5] = a10 * fx; w[6] = a11 * wx0; w[7] = a11 * fx;
+            const float2 wy = make_float2(1.f - fy, fy), wx = make_float2(1.f - fx, fx);
+            const float2 a0 = fmul2(1.f - fz, wy), a1 = fmul2(fz, wy);          // (z0y0, z0y1) (z1y0, z1y1)
+            const float2 w01 = fmul2(a0.x, wx), w23 = fmul2(a0.y, wx), w45 = fmul2(a1.x, wx), w67 = fmul2(a1.y, wx);
+            w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y; w[4] = w45.x; w[5] = w45.y; w[6] = w67.x; w[7] = w67.y;
           }
           const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&dv.x));
           const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&dv.y));
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
           unsigned todo = __ballot_sync(FULL, live);
           while (todo) {
             const int leader = __ffs(todo) - 1;
-            const int ksel = __shfl_sync(FULL, key, leader);
+            const unsigned ksel = __shfl_sync(FULL, key, leader);
             const bool tiny = (__shfl_sync(FULL, ent, leader) & 0x8000u) != 0u;
             const unsigned grp = __ballot_sync(FULL, key == ksel);
             todo &= ~grp;
@@ -485,7 +495,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
               continue;
             }
             if (ksel != cur_key) {
-              if (cur_key >= 0) flush(cur_key);
+              if (cur_key != 0xFFFFFFFEu) flush(cur_key);
               cur_key = ksel;
             }
             if ((grp >> lane) & 1u) {
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
             }
           }
         }
-        if (cur_key >= 0) flush(cur_key);
+        if (cur_key != 0xFFFFFFFEu) flush(cur_key);
         if (P.phase_clocks && lane == 0) s_warpclk[warp] = (int)(clock64() - t_b4);
       }
       __syncthreads();                    // hist / offs / sorted are rewritten by the next vertex
