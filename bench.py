@@ -236,8 +236,9 @@ def main():
                        enc_box_predictions={"center_normalized": inp["center_normalized"],
                                             "size_normalized": inp["size_normalized"]}, enc_box_features=inp["feat"])
         loss = synthetic_loss(out, weights)
-        gsync.zero_()
+        gsync.zero_()          # .grad = None: backward hands each parameter its gradient without an add_ kernel
         loss.backward()
+        gsync.gather_()        # one multi-tensor copy into the flat buffer that is all-reduced / stepped
         return loss
 
     def step(inp, fetch_loss):

@@ -50,15 +50,43 @@ class FlatGradAllReduce:
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
-        o = 0
+        self.views, o = [], 0
         for p in self.params:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        self._attached = True          # .grad tensors are the views of the flat buffer
 
     def zero_(self):
-        self.flat.zero_()
+        """Before backward.  The gradients are detached from the flat buffer: with ``.grad is None`` autograd hands
+        every parameter its freshly computed gradient (no kernel) instead of issuing one ``add_`` per parameter into
+        a zeroed view -- ~1000 tiny launches per step for this decoder."""
+        for p in self.params:
+            p.grad = None
+        self._attached = False
+
+    def gather_(self):
+        """After backward: copy the gradients into the flat buffer (a few multi-tensor launches) and make ``.grad``
+        the views again, so that the all-reduce and the optimizer see static addresses."""
+        if self._attached:
+            return self.flat
+        have_v, have_g = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None:
+                have_v.append(v)
+                have_g.append(p.grad)
+        if len(have_v) < len(self.params):
+            self.flat.zero_()
+        if have_v:
+            torch._foreach_copy_(have_v, have_g)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        self._attached = True
+        return self.flat
 
     def sync_(self):
+        self.gather_()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(dist.get_world_size())
