@@ -204,3 +204,48 @@ def test_saved_bias_backward_equals_recompute(seed, B, nQ, nK, rot, monkeypatch)
     for name in ("o", "dq", "dk", "dv"):
         assert np.array_equal(a[name], b[name]), name
     _cmp(a["dT"], b["dT"], 1e-5, 1e-7, "dtables (fp32 atomics: order may differ)")
+
+
+@pytest.mark.parametrize("n,B,nQ,nK,rot,far", [(7, 2, 19, 70, False, 0.3), (9, 1, 9, 260, True, 0.1), (10, 1, 4100, 6, False, 0.0),
+                                               (10, 1, 3, 1030, False, 0.5), (4, 1, 17, 33, False, 0.0)])
+def test_dtables_op_shapes(n, B, nQ, nK, rot, far):
+    """dTables kernel at the edges of its unit shape: table sizes other than 10, partial query blocks / key chunks,
+    more queries than the Morton sort handles (identity order), mixed rotated boxes, many out-of-range pairs."""
+    from vdetr_b200 import ops
+    c = recipe.xattn_case(100 + n, B, nQ, nK, rot, far)
+    ref = ora.box_vertices(c["center"], c["size"]).astype(np.float32)
+    rs = np.random.RandomState(n)
+    ds = rs.standard_normal((B, 4, nQ, nK)).astype(np.float32)
+    shape = (8, n, n, n, 4)
+    want = ora.rpe_bias_backward_tables(ref, c["xyz"], shape, ds.astype(np.float64), c["angle"])
+    got = ops.rpe_bias_grad_tables(torch.from_numpy(c["xyz"]).cuda(), torch.from_numpy(ref).cuda(),
+                                   None if c["angle"] is None else torch.from_numpy(c["angle"]).cuda(),
+                                   torch.zeros(shape, device="cuda"), torch.from_numpy(ds).cuda()).cpu().numpy()
+    assert np.isfinite(got).all()
+    _cmp(got, want, 5e-4, 1e-6, f"dtables n={n}")
+
+
+def test_dtables_full_size_linearity_and_subset_parity():
+    """Properties at the benchmark's full per-scene size (1024 queries x 4096 keys): dTables is linear in dS
+    (up to the fp16 rounding of dS), and with dS non-zero on 24 scattered queries only it equals the oracle evaluated
+    on those queries (the oracle cannot run the full size in seconds)."""
+    from vdetr_b200 import ops
+    B, nQ, nK = 1, 1024, 4096
+    c = recipe.xattn_case(77, B, nQ, nK, False, 0.0)
+    ref_np = ora.box_vertices(c["center"], c["size"]).astype(np.float32)
+    ref = torch.from_numpy(ref_np).cuda()
+    xyz = torch.from_numpy(c["xyz"]).cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    d1 = torch.randn(B, 4, nQ, nK, device="cuda", generator=g)
+    d2 = torch.randn(B, 4, nQ, nK, device="cuda", generator=g)
+    t0 = torch.zeros(8, 10, 10, 10, 4, device="cuda")
+    f = lambda d: ops.rpe_bias_grad_tables(xyz, ref, None, t0, d)           # noqa: E731
+    a, b_, ab = f(d1), f(d2), f(2.0 * d1 + d2)
+    scale = ab.abs().max().item()
+    assert (ab - (2.0 * a + b_)).abs().max().item() <= 2e-3 * scale
+    sel = np.arange(7, nQ, 43)[:24]
+    ds = torch.zeros(B, 4, nQ, nK, device="cuda")
+    ds[:, :, sel] = d1[:, :, sel]
+    got = f(ds).cpu().numpy()
+    want = ora.rpe_bias_backward_tables(ref_np[:, sel], c["xyz"], (8, 10, 10, 10, 4), d1[:, :, sel].cpu().numpy().astype(np.float64))
+    _cmp(got, want, 5e-4, 1e-6, "dtables full-size subset")

@@ -39,7 +39,7 @@ static_assert(NP % THREADS == 0 && (NP / 4) % THREADS == 0 && KC % 128 == 0 && N
 #define VDETR_DT_TINY 8
 #endif
 constexpr int TINY = VDETR_DT_TINY;                              // segments shorter than this use the broadcast mode
-constexpr int MAX_N = 12;                            // cell index + 1 must fit 4 bits with 15 = invalid
+constexpr int MAX_N = 10;                            // shared-memory budget (and the fused forward kernel) stop at 10 points per axis
 constexpr unsigned FULL = 0xffffffffu;
 
 struct Params {
