@@ -138,6 +138,18 @@ size_t vdetr_rpe_dtables_workspace_bytes(const VdetrXattnShape* s);
 int vdetr_rpe_dtables(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
                       const float* dbias, float* dtables, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension of a dense [rows, cols] f32 matrix (the decoder's nn.LayerNorm(256) calls:
+ * models/vdetr_transformer.py:463-466 norm1-3, :586-606 FFNLayer.norm, :129 TransformerDecoder.norm).
+ * cols must satisfy vdetr_layernorm_supported (128, 256, 384 or 512).
+ *   fwd: y [rows,cols], mean [rows], rstd [rows] (saved for backward)       bwd: dx [rows,cols], dgamma / dbeta [cols]
+ *   (dgamma / dbeta are fully overwritten). */
+int vdetr_layernorm_supported(int cols);
+int vdetr_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
+                        float* mean, float* rstd, void* stream);
+int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
+                        int cols, float* dx, float* dgamma, float* dbeta, void* stream);
+
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call
  * copies the 8 counters to the host and clears them (synchronises the device). */

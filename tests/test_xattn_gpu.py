@@ -249,3 +249,24 @@ def test_dtables_full_size_linearity_and_subset_parity():
     got = f(ds).cpu().numpy()
     want = ora.rpe_bias_backward_tables(ref_np[:, sel], c["xyz"], (8, 10, 10, 10, 4), d1[:, :, sel].cpu().numpy().astype(np.float64))
     _cmp(got, want, 5e-4, 1e-6, "dtables full-size subset")
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 256), (37, 256), (8192, 256), (515, 128), (64, 512), (0, 256)])
+def test_layernorm_kernels_match_torch(rows, cols):
+    """csrc/layernorm.cu vs torch.nn.functional.layer_norm (fp32): forward 1e-5, input / parameter gradients 1e-4."""
+    from vdetr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 3 + 1.5).requires_grad_(True)
+    w = (torch.rand(cols, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    b = torch.randn(cols, device="cuda", generator=g).requires_grad_(True)
+    dy = torch.randn(rows, cols, device="cuda", generator=g)
+    want = torch.nn.functional.layer_norm(x.double(), (cols,), w.double(), b.double(), 1e-5)
+    gw = torch.autograd.grad(want, (x, w, b), dy.double())
+    got = ops.layer_norm(x, w, b, 1e-5)
+    gg = torch.autograd.grad(got, (x, w, b), dy)
+    if rows == 0:
+        assert got.shape == (0, cols) and float(gg[1].abs().sum()) == 0.0
+        return
+    assert (got.double() - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    for a, r, name in zip(gg, gw, ("dx", "dgamma", "dbeta")):
+        assert (a.double() - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-6, name

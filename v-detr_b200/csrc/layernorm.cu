@@ -1,0 +1,170 @@
+// LayerNorm over the last dimension, forward and backward, for the decoder's [tokens, 256] activations
+// (nn.LayerNorm in GlobalDecoderLayer / FFNLayer / TransformerDecoder.norm: models/vdetr_transformer.py:463-466,
+// 586-606, 129).  One warp per row, the whole row in registers (cols = 128 * VEC, VEC float4 per lane).
+//   forward : y = (x - mean) * rstd * gamma + beta, mean / rstd saved
+//   backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; dgamma / dbeta are accumulated per
+//             lane over the rows a warp walks, reduced across the CTA in shared memory and added to the output with one
+//             atomic per column per CTA (the 34 LayerNorm backward calls of a decoder step took 3.9 ms with the stock
+//             kernels, whose column reduction is a separate pass).
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamma,
+                                                               const float4* __restrict__ beta, int rows, float eps,
+                                                               float4* __restrict__ y, float* __restrict__ mean,
+                                                               float* __restrict__ rstd) {
+  constexpr int C4 = VEC * 32;                      // float4 per row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_n = 1.0f / (float)(C4 * 4);
+  for (int r = blockIdx.x * LN_WARPS + warp; r < rows; r += gridDim.x * LN_WARPS) {
+    float4 v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i] = x[(size_t)r * C4 + i * 32 + lane];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i].x -= mu; v[i].y -= mu; v[i].z -= mu; v[i].w -= mu;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_n + eps);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 g = __ldg(gamma + i * 32 + lane), b = __ldg(beta + i * 32 + lane);
+      y[(size_t)r * C4 + i * 32 + lane] =
+          make_float4(v[i].x * rs * g.x + b.x, v[i].y * rs * g.y + b.y, v[i].z * rs * g.z + b.z, v[i].w * rs * g.w + b.w);
+    }
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float4* __restrict__ gamma, int rows,
+                                                               float4* __restrict__ dx, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta) {
+  constexpr int C4 = VEC * 32;
+  __shared__ float4 red[LN_WARPS][C4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_n = 1.0f / (float)(C4 * 4);
+  float4 gm[VEC], ag[VEC], ab[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    gm[i] = __ldg(gamma + i * 32 + lane);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = ag[i];
+  }
+  for (int r = blockIdx.x * LN_WARPS + warp; r < rows; r += gridDim.x * LN_WARPS) {
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    float4 xh[VEC], g[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 xv = x[(size_t)r * C4 + i * 32 + lane], d = dy[(size_t)r * C4 + i * 32 + lane];
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+    }
+    const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      dx[(size_t)r * C4 + i * 32 + lane] =
+          make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2), rs * (g[i].z - m1 - xh[i].z * m2),
+                      rs * (g[i].w - m1 - xh[i].w * m2));
+  }
+  // column sums of this CTA: warps -> shared memory -> one atomic per column
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) red[warp][i * 32 + lane] = pass == 0 ? ag[i] : ab[i];
+    __syncthreads();
+    float* out = pass == 0 ? dgamma : dbeta;
+    for (int c = threadIdx.x; c < C4 * 4; c += LN_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) s += reinterpret_cast<const float*>(&red[w][0])[c];
+      atomicAdd(out + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+template <int VEC>
+int launch_fwd(const float* x, const float* gamma, const float* beta, int rows, float eps, float* y, float* mean, float* rstd,
+               cudaStream_t st) {
+  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, vdetr_num_sms() * 8);
+  ln_fwd_kernel<VEC><<<grid, LN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gamma),
+                                                    reinterpret_cast<const float4*>(beta), rows, eps,
+                                                    reinterpret_cast<float4*>(y), mean, rstd);
+  VDETR_LAUNCH_CHECK();
+  return 0;
+}
+template <int VEC>
+int launch_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows, float* dx,
+               float* dgamma, float* dbeta, cudaStream_t st) {
+  // enough rows per warp to amortise the column reduction, enough CTAs to fill the machine
+  int grid = (rows + LN_WARPS * 8 - 1) / (LN_WARPS * 8);
+  grid = max(1, min(grid, vdetr_num_sms() * 4));
+  ln_bwd_kernel<VEC><<<grid, LN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), mean,
+                                                    rstd, reinterpret_cast<const float4*>(gamma), rows,
+                                                    reinterpret_cast<float4*>(dx), dgamma, dbeta);
+  VDETR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vdetr_layernorm_supported(int cols) { return cols == 128 || cols == 256 || cols == 384 || cols == 512; }
+
+int vdetr_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
+                        float* mean, float* rstd, void* stream) {
+  if (rows < 0 || !vdetr_layernorm_supported(cols)) return VDETR_ERR_UNSUPPORTED;
+  if (rows == 0) return 0;
+  if (!x || !gamma || !beta || !y || !mean || !rstd) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (cols / 128) {
+    case 1: return launch_fwd<1>(x, gamma, beta, rows, eps, y, mean, rstd, st);
+    case 2: return launch_fwd<2>(x, gamma, beta, rows, eps, y, mean, rstd, st);
+    case 3: return launch_fwd<3>(x, gamma, beta, rows, eps, y, mean, rstd, st);
+    default: return launch_fwd<4>(x, gamma, beta, rows, eps, y, mean, rstd, st);
+  }
+}
+
+int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
+                        int cols, float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (rows < 0 || !vdetr_layernorm_supported(cols)) return VDETR_ERR_UNSUPPORTED;
+  if (!dgamma || !dbeta) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  VDETR_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)cols * sizeof(float), st));
+  VDETR_CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)cols * sizeof(float), st));
+  if (rows == 0) return 0;
+  if (!dy || !x || !mean || !rstd || !gamma || !dx) return VDETR_ERR_BAD_ARG;
+  switch (cols / 128) {
+    case 1: return launch_bwd<1>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    case 2: return launch_bwd<2>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    case 3: return launch_bwd<3>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    default: return launch_bwd<4>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+  }
+}
+
+}  // extern "C"

@@ -58,7 +58,18 @@ class BatchNormDim1Swap(nn.BatchNorm1d):
         return super().forward(x.permute(1, 2, 0)).permute(2, 0, 1)
 
 
-NORM_DICT = {"bn": BatchNormDim1Swap, "bn1d": nn.BatchNorm1d, "id": nn.Identity, "ln": nn.LayerNorm}
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict) whose fp32 CUDA path runs the library's warp-per-row kernels
+    (csrc/layernorm.cu); anything else (CPU, other dtypes, widths the kernels do not cover) is stock PyTorch."""
+
+    def forward(self, x):
+        from . import ops
+        if len(self.normalized_shape) == 1 and ops.layer_norm_supported(x, self.weight, self.bias):
+            return ops.layer_norm(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
+NORM_DICT = {"bn": BatchNormDim1Swap, "bn1d": nn.BatchNorm1d, "id": nn.Identity, "ln": LayerNorm}
 ACTIVATION_DICT = {"relu": nn.ReLU, "gelu": nn.GELU, "leakyrelu": partial(nn.LeakyReLU, negative_slope=0.1)}
 WEIGHT_INIT_DICT = {"xavier_uniform": nn.init.xavier_uniform_}
 

@@ -128,3 +128,43 @@ def rpe_bias_grad_tables(xyz, ref_pts, ref_angle, tables, dbias, log_scale=512.0
                                      _C.ptr(None if ref_angle is None else ref_angle.contiguous()), _C.ptr(ds4), _C.ptr(out),
                                      _C.ptr(ws), nbytes, _C.stream_ptr()))
     return out
+
+
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        cols = x.shape[-1]
+        x2 = x.reshape(-1, cols)
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _C.check(_C.lib().vdetr_layernorm_fwd(_C.ptr(x2), _C.ptr(weight), _C.ptr(bias), rows, cols, float(eps), _C.ptr(y),
+                                                  _C.ptr(mean), _C.ptr(rstd), _C.stream_ptr()))
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        rows, cols = x2.shape
+        dy2 = dy.contiguous().view(rows, cols)
+        dx = torch.empty_like(x2)
+        dw = torch.empty_like(weight)
+        db = torch.empty_like(weight)
+        with torch.cuda.device(x2.device):
+            _C.check(_C.lib().vdetr_layernorm_bwd(_C.ptr(dy2), _C.ptr(x2), _C.ptr(mean), _C.ptr(rstd), _C.ptr(weight), rows, cols,
+                                                  _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.stream_ptr()))
+        return dx.view(ctx.shape), dw, db, None
+
+
+def layer_norm_supported(x, weight, bias) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None and weight.dim() == 1
+            and weight.dtype == torch.float32 and x.shape[-1] == weight.shape[0] and x.shape[-1] in (128, 256, 384, 512))
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    """nn.LayerNorm over the last dimension (fp32, CUDA) through the library's warp-per-row kernels."""
+    return _LayerNorm.apply(x.contiguous(), weight.contiguous(), bias.contiguous(), eps)
