@@ -150,6 +150,18 @@ int vdetr_layernorm_fwd(const float* x, const float* gamma, const float* beta, i
 int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
                         int cols, float* dx, float* dgamma, float* dbeta, void* stream);
 
+/* Training-mode BatchNorm1d + ReLU on token-major activations x [rows, cols] f32 (the Conv1d(k=1)-BatchNorm1d-ReLU
+ * stacks of models/helpers.py:17-33 and :74-141 evaluated per token).  Batch statistics over the rows; running_mean /
+ * running_var (may be NULL) are updated in place with `momentum` and the unbiased variance, like nn.BatchNorm1d.
+ *   fwd: y, mean [cols], rstd [cols]; workspace: 2 * cols floats.       bwd: dx, dgamma, dbeta (fully overwritten);
+ *   y is the forward output (its sign is the ReLU mask).  cols: vdetr_bn_relu_supported (128, 256, 384, 512). */
+int vdetr_bn_relu_supported(int cols);
+int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float momentum,
+                            float* y, float* mean, float* rstd, float* running_mean, float* running_var, float* workspace,
+                            void* stream);
+int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, void* stream);
+
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call
  * copies the 8 counters to the host and clears them (synchronises the device). */

@@ -270,3 +270,32 @@ def test_layernorm_kernels_match_torch(rows, cols):
     assert (got.double() - want).abs().max().item() <= 1e-5 * want.abs().max().item()
     for a, r, name in zip(gg, gw, ("dx", "dgamma", "dbeta")):
         assert (a.double() - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-6, name
+
+
+@pytest.mark.parametrize("rows,cols", [(16, 256), (77, 128), (8192, 256), (1000, 512)])
+def test_bn_relu_kernels_match_torch(rows, cols):
+    """csrc/batchnorm.cu vs nn.BatchNorm1d(train) + ReLU in fp64: output, running statistics, all three gradients."""
+    from vdetr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 5.0).requires_grad_(True)      # |mean| >> std on purpose
+    bn = torch.nn.BatchNorm1d(cols).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(cols, device="cuda", generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(cols, device="cuda", generator=g) * 0.3)
+        bn.running_mean.normal_(generator=g)
+        bn.running_var.uniform_(0.5, 2.0, generator=g)
+    ref = torch.nn.BatchNorm1d(cols).cuda().double().train()
+    ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    dy = torch.randn(rows, cols, device="cuda", generator=g)
+    xd = x.detach().double().requires_grad_(True)
+    want = torch.relu(ref(xd))
+    gw = torch.autograd.grad(want, (xd, ref.weight, ref.bias), dy.double())
+    assert ops.bn_relu_train_supported(x, bn)
+    got = ops.bn_relu_train(x, bn)
+    gg = torch.autograd.grad(got, (x, bn.weight, bn.bias), dy)
+    assert (got.double() - want).abs().max().item() <= 2e-5 * want.abs().max().item() + 1e-6
+    assert int(bn.num_batches_tracked) == 1
+    assert (bn.running_mean.double() - ref.running_mean).abs().max().item() <= 1e-5
+    assert (bn.running_var.double() - ref.running_var).abs().max().item() <= 1e-4
+    for a, r, name in zip(gg, gw, ("dx", "dgamma", "dbeta")):
+        assert (a.double() - r).abs().max().item() <= 2e-4 * r.abs().max().item() + 1e-6, name

@@ -1,0 +1,240 @@
+// Training-mode BatchNorm1d + ReLU on token-major activations [tokens, C] (the Conv1d(k=1)-BN-ReLU stacks of the box
+// heads and of the query-position MLP: models/helpers.py:17-33, 74-141, evaluated token-major -- helpers.pointwise_tokens).
+//   stats   : per-channel sum and sum of squares of (x - pivot), pivot = row 0 (shifted sums: no cancellation when
+//             |mean| >> std); warps accumulate per-lane column sums over their rows, CTAs reduce in shared memory and
+//             add to global with one atomic per column
+//   apply   : y = relu((x - mean) * rstd * gamma + beta); block 0 also updates running_mean / running_var (unbiased)
+//   bwd sums: dbeta = sum g, dgamma = sum g * xhat with g = dy * [y > 0]  (the two column sums the input gradient needs)
+//   bwd dx  : dx = gamma * rstd * (g - dbeta / T - xhat * dgamma / T)
+// Stock PyTorch runs 3 kernels forward (statistics, transform, ReLU) and 3 backward; here the ReLU rides along.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BN_WARPS = 8;
+
+// column accumulation helper: every lane owns VEC float4 (columns i*128 + lane*4 .. +3)
+template <int VEC, typename F>
+__device__ __forceinline__ void reduce_columns_to_global(float4 (&a)[VEC], float4 (&b)[VEC], float* out_a, float* out_b, F) {
+  __shared__ float4 red[BN_WARPS][VEC * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) red[warp][i * 32 + lane] = pass == 0 ? a[i] : b[i];
+    __syncthreads();
+    float* out = pass == 0 ? out_a : out_b;
+    for (int c = threadIdx.x; c < VEC * 128; c += BN_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < BN_WARPS; ++w) s += reinterpret_cast<const float*>(&red[w][0])[c];
+      atomicAdd(out + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(BN_WARPS * 32) bn_stats_kernel(const float4* __restrict__ x, int rows, float* __restrict__ sum,
+                                                                 float* __restrict__ sumsq) {
+  constexpr int C4 = VEC * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 s[VEC], q[VEC], pv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q[i] = s[i];
+    pv[i] = __ldg(x + i * 32 + lane);                   // pivot = row 0
+  }
+  for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float4 v = x[(size_t)r * C4 + i * 32 + lane];
+      v.x -= pv[i].x; v.y -= pv[i].y; v.z -= pv[i].z; v.w -= pv[i].w;
+      s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+      q[i].x += v.x * v.x; q[i].y += v.y * v.y; q[i].z += v.z * v.z; q[i].w += v.w * v.w;
+    }
+  }
+  reduce_columns_to_global<VEC>(s, q, sum, sumsq, 0);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const float4* __restrict__ x, int rows,
+                                                                      const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                                                      float eps, float momentum, float4* __restrict__ y,
+                                                                      float* __restrict__ mean, float* __restrict__ rstd,
+                                                                      float* running_mean, float* running_var) {
+  constexpr int C4 = VEC * 32, C = C4 * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_n = 1.0f / (float)rows;
+  float4 sc[VEC], sh[VEC];            // y = relu(x * sc + sh)
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    const float4 pv = __ldg(x + i * 32 + lane), g = __ldg(gamma + i * 32 + lane), b = __ldg(beta + i * 32 + lane);
+    float m[4], rs[4];
+    const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ms = __ldg(sum + c0 + e) * inv_n;                       // mean of (x - pivot)
+      const float var = fmaxf(__ldg(sumsq + c0 + e) * inv_n - ms * ms, 0.f);
+      m[e] = ms + pvv[e];
+      rs[e] = rsqrtf(var + eps);
+      if (blockIdx.x == 0 && warp == 0) {
+        mean[c0 + e] = m[e];
+        rstd[c0 + e] = rs[e];
+        if (running_mean) {
+          const float unbiased = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+          running_mean[c0 + e] = (1.f - momentum) * running_mean[c0 + e] + momentum * m[e];
+          running_var[c0 + e] = (1.f - momentum) * running_var[c0 + e] + momentum * unbiased;
+        }
+      }
+    }
+    sc[i] = make_float4(rs[0] * g.x, rs[1] * g.y, rs[2] * g.z, rs[3] * g.w);
+    sh[i] = make_float4(b.x - m[0] * sc[i].x, b.y - m[1] * sc[i].y, b.z - m[2] * sc[i].z, b.w - m[3] * sc[i].w);
+  }
+  (void)C;
+  for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 v = x[(size_t)r * C4 + i * 32 + lane];
+      y[(size_t)r * C4 + i * 32 + lane] =
+          make_float4(fmaxf(fmaf(v.x, sc[i].x, sh[i].x), 0.f), fmaxf(fmaf(v.y, sc[i].y, sh[i].y), 0.f),
+                      fmaxf(fmaf(v.z, sc[i].z, sh[i].z), 0.f), fmaxf(fmaf(v.w, sc[i].w, sh[i].w), 0.f));
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
+                                                                    const float4* __restrict__ x, int rows,
+                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int C4 = VEC * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ag[VEC], ab[VEC], mu[VEC], rs[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = ag[i];
+    mu[i] = __ldg(reinterpret_cast<const float4*>(mean) + i * 32 + lane);
+    rs[i] = __ldg(reinterpret_cast<const float4*>(rstd) + i * 32 + lane);
+  }
+  for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const size_t o = (size_t)r * C4 + i * 32 + lane;
+      const float4 d = dy[o], yy = y[o], xv = x[o];
+      const float gx = yy.x > 0.f ? d.x : 0.f, gy = yy.y > 0.f ? d.y : 0.f, gz = yy.z > 0.f ? d.z : 0.f, gw = yy.w > 0.f ? d.w : 0.f;
+      ab[i].x += gx; ab[i].y += gy; ab[i].z += gz; ab[i].w += gw;
+      ag[i].x += gx * (xv.x - mu[i].x) * rs[i].x; ag[i].y += gy * (xv.y - mu[i].y) * rs[i].y;
+      ag[i].z += gz * (xv.z - mu[i].z) * rs[i].z; ag[i].w += gw * (xv.w - mu[i].w) * rs[i].w;
+    }
+  }
+  reduce_columns_to_global<VEC>(ag, ab, dgamma, dbeta, 0);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
+                                                                  const float4* __restrict__ x, int rows,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float4* __restrict__ gamma, const float* __restrict__ dgamma,
+                                                                  const float* __restrict__ dbeta, float4* __restrict__ dx) {
+  constexpr int C4 = VEC * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_n = 1.0f / (float)rows;
+  float4 mu[VEC], rs[VEC], k1[VEC], k2[VEC], k3[VEC];      // dx = k1 * g - k2 - xhat * k3
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    mu[i] = __ldg(reinterpret_cast<const float4*>(mean) + i * 32 + lane);
+    rs[i] = __ldg(reinterpret_cast<const float4*>(rstd) + i * 32 + lane);
+    const float4 g = __ldg(gamma + i * 32 + lane);
+    const float4 dg = __ldg(reinterpret_cast<const float4*>(dgamma) + i * 32 + lane);
+    const float4 db = __ldg(reinterpret_cast<const float4*>(dbeta) + i * 32 + lane);
+    k1[i] = make_float4(g.x * rs[i].x, g.y * rs[i].y, g.z * rs[i].z, g.w * rs[i].w);
+    k2[i] = make_float4(k1[i].x * db.x * inv_n, k1[i].y * db.y * inv_n, k1[i].z * db.z * inv_n, k1[i].w * db.w * inv_n);
+    k3[i] = make_float4(k1[i].x * dg.x * inv_n, k1[i].y * dg.y * inv_n, k1[i].z * dg.z * inv_n, k1[i].w * dg.w * inv_n);
+  }
+  for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const size_t o = (size_t)r * C4 + i * 32 + lane;
+      const float4 d = dy[o], yy = y[o], xv = x[o];
+      const float gx = yy.x > 0.f ? d.x : 0.f, gy = yy.y > 0.f ? d.y : 0.f, gz = yy.z > 0.f ? d.z : 0.f, gw = yy.w > 0.f ? d.w : 0.f;
+      dx[o] = make_float4(k1[i].x * gx - k2[i].x - (xv.x - mu[i].x) * rs[i].x * k3[i].x,
+                          k1[i].y * gy - k2[i].y - (xv.y - mu[i].y) * rs[i].y * k3[i].y,
+                          k1[i].z * gz - k2[i].z - (xv.z - mu[i].z) * rs[i].z * k3[i].z,
+                          k1[i].w * gw - k2[i].w - (xv.w - mu[i].w) * rs[i].w * k3[i].w);
+    }
+  }
+}
+
+inline int bn_grid(int rows, int rows_per_warp) {
+  int g = (rows + BN_WARPS * rows_per_warp - 1) / (BN_WARPS * rows_per_warp);
+  return g < 1 ? 1 : (g > vdetr_num_sms() * 4 ? vdetr_num_sms() * 4 : g);
+}
+
+template <int VEC>
+int fwd_t(const float* x, const float* gamma, const float* beta, int rows, float eps, float momentum, float* y, float* mean,
+          float* rstd, float* running_mean, float* running_var, float* ws, cudaStream_t st) {
+  const int C = VEC * 128;
+  VDETR_CUDA_TRY(cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(float), st));
+  bn_stats_kernel<VEC><<<bn_grid(rows, 8), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws, ws + C);
+  VDETR_LAUNCH_CHECK();
+  bn_apply_relu_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(
+      reinterpret_cast<const float4*>(x), rows, ws, ws + C, reinterpret_cast<const float4*>(gamma),
+      reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var);
+  VDETR_LAUNCH_CHECK();
+  return 0;
+}
+template <int VEC>
+int bwd_t(const float* dy, const float* y, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
+          float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+  bn_bwd_sums_kernel<VEC><<<bn_grid(rows, 8), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy),
+                                                                     reinterpret_cast<const float4*>(y),
+                                                                     reinterpret_cast<const float4*>(x), rows, mean, rstd, dgamma, dbeta);
+  VDETR_LAUNCH_CHECK();
+  bn_bwd_dx_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(
+      reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
+      reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx));
+  VDETR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vdetr_bn_relu_supported(int cols) { return cols == 128 || cols == 256 || cols == 384 || cols == 512; }
+
+int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float momentum,
+                            float* y, float* mean, float* rstd, float* running_mean, float* running_var, float* workspace,
+                            void* stream) {
+  if (rows < 1 || !vdetr_bn_relu_supported(cols)) return VDETR_ERR_UNSUPPORTED;
+  if (!x || !gamma || !beta || !y || !mean || !rstd || !workspace) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (cols / 128) {
+    case 1: return fwd_t<1>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    case 2: return fwd_t<2>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    case 3: return fwd_t<3>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    default: return fwd_t<4>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+  }
+}
+
+int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (rows < 1 || !vdetr_bn_relu_supported(cols)) return VDETR_ERR_UNSUPPORTED;
+  if (!dy || !y || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  VDETR_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)cols * sizeof(float), st));
+  VDETR_CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)cols * sizeof(float), st));
+  switch (cols / 128) {
+    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+  }
+}
+
+}  // extern "C"

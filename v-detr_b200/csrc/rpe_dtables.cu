@@ -522,23 +522,44 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
   }
 }
 
-// sum of the per-CTA private tables, without the padding cells, times 1 / scale
-__global__ void rpe_dtables_reduce_kernel(const float* __restrict__ priv, int copies, int n, int P3, float* __restrict__ out,
-                                          const unsigned* absmax_bits, int dense) {
+// sum of the per-CTA private tables, without the padding cells, times 1 / scale.  A CTA owns 32 consecutive output
+// elements; its 8 warps split the copies (the loads of a warp are 128 contiguous bytes of one copy).
+__global__ void __launch_bounds__(256) rpe_dtables_reduce_kernel(const float* __restrict__ priv, int copies, int n, int P3,
+                                                                 float* __restrict__ out, const unsigned* absmax_bits, int dense) {
+  __shared__ float part[8][32];
   const float inv = 1.0f / scale_of(*absmax_bits, dense);
   const int total = 8 * n * n * n * 4;
   const size_t copy_stride = (size_t)8 * P3 * P3 * P3 * 4;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int h = i & 3;
-    int r = i >> 2;
-    const int x = r % n; r /= n;
-    const int y = r % n; r /= n;
-    const int z = r % n;
-    const int v = r / n;
-    const size_t src = ((((size_t)v * P3 + z + 1) * P3 + y + 1) * P3 + x + 1) * 4 + h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = blockIdx.x * 32; i0 < total; i0 += gridDim.x * 32) {
+    const int i = i0 + lane;
     float s = 0.f;
-    for (int c = 0; c < copies; ++c) s += priv[c * copy_stride + src];
-    out[i] = s * inv;
+    if (i < total) {
+      const int h = i & 3;
+      int r = i >> 2;
+      const int x = r % n; r /= n;
+      const int y = r % n; r /= n;
+      const int z = r % n;
+      const int v = r / n;
+      const size_t src = ((((size_t)v * P3 + z + 1) * P3 + y + 1) * P3 + x + 1) * 4 + h;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int c = warp;
+      for (; c + 24 < copies; c += 32) {
+        s0 += priv[c * copy_stride + src]; s1 += priv[(c + 8) * copy_stride + src];
+        s2 += priv[(c + 16) * copy_stride + src]; s3 += priv[(c + 24) * copy_stride + src];
+      }
+      for (; c < copies; c += 8) s0 += priv[c * copy_stride + src];
+      s = (s0 + s1) + (s2 + s3);
+    }
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][lane];
+      out[i] = t * inv;
+    }
+    __syncthreads();
   }
 }
 
@@ -707,7 +728,7 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   dt3::rpe_dtables_kernel<<<grid, dt3::THREADS, smem, st>>>(P);
   VDETR_LAUNCH_CHECK();
   const int total = 8 * n * n * n * 4;
-  dt3::rpe_dtables_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(priv, grid, n, P.P3, dtables, absmax_bits, dense_scale);
+  dt3::rpe_dtables_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(priv, grid, n, P.P3, dtables, absmax_bits, dense_scale);
   VDETR_LAUNCH_CHECK();
   return 0;
 }

@@ -21,12 +21,20 @@ def pointwise_tokens(seq, x):
     result (up to summation order) -- but as plain GEMMs on contiguous rows instead of cuDNN convolutions on a
     permuted copy (the cuDNN weight-gradient kernels for the 1/3/18-channel output convolutions alone cost ~80 us
     per call on a B200).  Used for the box heads (models/helpers.py:74-141) and the query-position MLP (:17-33)."""
-    for m in seq:
+    from . import ops
+    mods, i = list(seq), 0
+    while i < len(mods):
+        m = mods[i]
         if isinstance(m, nn.Conv1d):
             assert m.kernel_size == (1,) and m.stride == (1,) and m.groups == 1
             x = F.linear(x, m.weight.squeeze(-1), m.bias)
+        elif (type(m) is nn.BatchNorm1d and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+              and ops.bn_relu_train_supported(x, m)):
+            x = ops.bn_relu_train(x, m)           # batch statistics + running-stat update + ReLU fused (csrc/batchnorm.cu)
+            i += 1
         else:
             x = m(x)
+        i += 1
     return x
 
 

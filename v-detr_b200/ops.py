@@ -168,3 +168,46 @@ def layer_norm_supported(x, weight, bias) -> bool:
 def layer_norm(x, weight, bias, eps=1e-5):
     """nn.LayerNorm over the last dimension (fp32, CUDA) through the library's warp-per-row kernels."""
     return _LayerNorm.apply(x.contiguous(), weight.contiguous(), bias.contiguous(), eps)
+
+
+class _BnReluTrain(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum):
+        rows, cols = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(cols, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(cols, dtype=torch.float32, device=x.device)
+        ws = torch.empty(2 * cols, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _C.check(_C.lib().vdetr_bn_relu_train_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(bias), rows, cols, float(eps), float(momentum),
+                                                      _C.ptr(y), _C.ptr(mean), _C.ptr(rstd), _C.ptr(running_mean),
+                                                      _C.ptr(running_var), _C.ptr(ws), _C.stream_ptr()))
+        ctx.save_for_backward(x, y, weight, mean, rstd)
+        ctx.mark_non_differentiable(*[t for t in (running_mean, running_var) if t is not None])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, mean, rstd = ctx.saved_tensors
+        rows, cols = x.shape
+        dy = dy.contiguous()
+        dx, dw, db = torch.empty_like(x), torch.empty_like(weight), torch.empty_like(weight)
+        with torch.cuda.device(x.device):
+            _C.check(_C.lib().vdetr_bn_relu_train_bwd(_C.ptr(dy), _C.ptr(y), _C.ptr(x), _C.ptr(mean), _C.ptr(rstd), _C.ptr(weight),
+                                                      rows, cols, _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.stream_ptr()))
+        return dx, dw, db, None, None, None, None
+
+
+def bn_relu_train_supported(x, bn) -> bool:
+    return (bn.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 1 and bn.affine
+            and bn.momentum is not None and x.shape[1] in (128, 256, 384, 512) and bn.weight.dtype == torch.float32)
+
+
+def bn_relu_train(x, bn):
+    """relu(BatchNorm1d(x)) for a training-mode nn.BatchNorm1d `bn` on token-major x [T, C] (fp32, CUDA): batch statistics,
+    running-statistics update and ReLU in two kernels forward / two backward (csrc/batchnorm.cu)."""
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BnReluTrain.apply(x.contiguous(), bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum)
