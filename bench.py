@@ -180,7 +180,8 @@ def main():
     config = {"workload": f"C3/C4: {a.batch} scenes per GPU x {NK} keys x {NQ} queries x {NLAYERS} decoder layers, "
                           "fwd+bwd+AdamW, train mode (BN batch stats per GPU, dropout 0), TF32 Linear/Conv layers",
               "global_batch": a.batch * world, "parallelism": f"dp{world}",
-              "l2": "per-step working set (> 2 GB of attention scratch + activations) >> 126 MB L2; no explicit flush"}
+              "l2": "per-step working set (> 6 GB of attention scratch, saved bias and activations) >> 126 MB L2; no explicit flush",
+              "notes": "training keeps the fused forward's per-pair bias (537 MB per layer at batch 8) for the backward"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -271,8 +272,10 @@ def main():
     torch.cuda.synchronize()
     # ---- eager pass with per-kernel CUDA events (roofline numbers); the headline loop below replays a CUDA graph
     C.lib().vdetr_timing_enable(1)
+    C.lib().vdetr_launch_count(1)
     for _ in range(2):
         step(resident, False)
+    own_launches_per_step = int(C.lib().vdetr_launch_count(1)) // 2       # kernels of libvdetr_b200 per step
     import ctypes
     tot = (ctypes.c_float * 3)()
     cnt = (ctypes.c_int * 3)()
@@ -358,14 +361,19 @@ def main():
             "dtype": "fp16/bf16 tensor-core operands (fp16: S=QK^T, O=PV; bf16: gradient GEMMs), fp32 bias/softmax/accumulate",
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": int((cnt[0] + cnt[1] + cnt[2]) // timed_eager_steps) * a.steps,
+            "gpu_launches": own_launches_per_step * a.steps,
             "clocks": sampler.summary(),
             "roofline": {"kernel": "rpe_xattn_fwd_kernel<bias,MQA> (fused Vertex-RPE cross attention, forward)",
                          "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved / peak_tf if peak_tf else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this batch, one ncu --set full
+                         # capture (profiles/r1_ncu_kernels.csv): 18.3 MB read + 516.5 MB written, the write being the
+                         # per-pair bias kept for the backward (16 B x 33.5 M pairs); algorithmic minimum 19 MB
+                         "traffic": 534751488 if a.batch == PER_GPU_BATCH else None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                          "launch_ms": fwd_ms,
-                         "secondary_bound": {"what": "vertex evaluations (3 lg2 + 8-corner x 4-head gather) on FP32/MUFU/LDS pipes",
+                         "secondary_bound": {"what": "instruction issue of the bias gather: 1036 thread-instructions per (query,key) "
+                                                     "pair, issue slots 78 % / FMA pipe 58 % busy (ncu, DESIGN.md 4.1)",
                                              "gevals_per_s": evals / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None}},
             "kernel_ms_per_step": {"xattn_fwd": tot[0] / timed_eager_steps, "xattn_bwd_pass1": tot[1] / timed_eager_steps,
                                    "dtables": tot[2] / timed_eager_steps,

@@ -128,6 +128,8 @@ int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_
  * around [0] the fused forward kernel, [1] the backward pass-1 kernel, [2] the dTables kernel (at most 512
  * launches each between reads).  vdetr_timing_read synchronises on the recorded events, returns the summed
  * device time in ms and the launch counts, and resets the counters. */
+/* Number of kernels this library has launched (host-side count of its own launches; cuBLAS GEMMs are not included). */
+unsigned long long vdetr_launch_count(int reset);
 int vdetr_timing_enable(int enable);
 int vdetr_timing_read(float* total_ms /*[3]*/, int* launches /*[3]*/);
 

@@ -40,6 +40,7 @@ _SIGS = {
     "vdetr_xattn_bwd_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
     "vdetr_xattn_bwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 15 + [c_void_p, c_size_t, c_int, c_void_p]),
     "vdetr_rpe_bias": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p]),
+    "vdetr_launch_count": (ctypes.c_ulonglong, [c_int]),
     "vdetr_timing_enable": (c_int, [c_int]),
     "vdetr_timing_read": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int)]),
     "vdetr_layernorm_supported": (c_int, [c_int]),

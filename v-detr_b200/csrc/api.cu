@@ -24,7 +24,15 @@ VdetrTimingScope::~VdetrTimingScope() {
   if (on) cudaEventRecord(stop, st);
 }
 
+unsigned long long g_vdetr_launches = 0;
+
 extern "C" {
+
+unsigned long long vdetr_launch_count(int reset) {
+  const unsigned long long n = g_vdetr_launches;
+  if (reset) g_vdetr_launches = 0;
+  return n;
+}
 
 int vdetr_timing_enable(int enable) {
   if (enable && !g_timing.created) {

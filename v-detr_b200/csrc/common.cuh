@@ -11,8 +11,11 @@
     if (_e != cudaSuccess) return (int)_e;            \
   } while (0)
 
+// every kernel launch of the library is followed by this check; it also counts the launches (vdetr_launch_count)
+extern unsigned long long g_vdetr_launches;
 #define VDETR_LAUNCH_CHECK()                          \
   do {                                                \
+    ++g_vdetr_launches;                               \
     cudaError_t _e = cudaGetLastError();              \
     if (_e != cudaSuccess) return (int)_e;            \
   } while (0)
