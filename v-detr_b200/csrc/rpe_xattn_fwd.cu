@@ -185,7 +185,7 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             umma_commit(bar_s + ((gj + 1) & 1));
             umma_commit(bar_kfree);
           }
-          mbar_wait(bar_p, gj & 1);
+          mbar_wait_relaxed(bar_p, gj & 1);                  // a whole tile of bias + softmax work away
           mbar_wait(bar_v, gj & 1);
           tc_fence_after();
           {
