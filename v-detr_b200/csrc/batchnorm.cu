@@ -180,9 +180,9 @@ int fwd_t(const float* x, const float* gamma, const float* beta, int rows, float
           float* rstd, float* running_mean, float* running_var, float* ws, cudaStream_t st) {
   const int C = VEC * 128;
   VDETR_CUDA_TRY(cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(float), st));
-  bn_stats_kernel<VEC><<<bn_grid(rows, 8), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws, ws + C);
+  bn_stats_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws, ws + C);
   VDETR_LAUNCH_CHECK();
-  bn_apply_relu_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(
+  bn_apply_relu_kernel<VEC><<<bn_grid(rows, 2), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(x), rows, ws, ws + C, reinterpret_cast<const float4*>(gamma),
       reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var);
   VDETR_LAUNCH_CHECK();
@@ -191,11 +191,11 @@ int fwd_t(const float* x, const float* gamma, const float* beta, int rows, float
 template <int VEC>
 int bwd_t(const float* dy, const float* y, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
           float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
-  bn_bwd_sums_kernel<VEC><<<bn_grid(rows, 8), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy),
+  bn_bwd_sums_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy),
                                                                      reinterpret_cast<const float4*>(y),
                                                                      reinterpret_cast<const float4*>(x), rows, mean, rstd, dgamma, dbeta);
   VDETR_LAUNCH_CHECK();
-  bn_bwd_dx_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(
+  bn_bwd_dx_kernel<VEC><<<bn_grid(rows, 2), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
       reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx));
   VDETR_LAUNCH_CHECK();

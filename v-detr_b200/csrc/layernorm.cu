@@ -121,7 +121,7 @@ template <int VEC>
 int launch_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows, float* dx,
                float* dgamma, float* dbeta, cudaStream_t st) {
   // enough rows per warp to amortise the column reduction, enough CTAs to fill the machine
-  int grid = (rows + LN_WARPS * 8 - 1) / (LN_WARPS * 8);
+  int grid = (rows + LN_WARPS * 4 - 1) / (LN_WARPS * 4);
   grid = max(1, min(grid, vdetr_num_sms() * 4));
   ln_bwd_kernel<VEC><<<grid, LN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), mean,
                                                     rstd, reinterpret_cast<const float4*>(gamma), rows,

@@ -237,7 +237,6 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[c >> 1] = pack_f16x2(pv[0], pv[1]);
           dk_[c >> 1] = pack_f16x2(dv[0], dv[1]);
         }
-        if (SAVED) mbar_arrive(bar_p + (gj & 1));          // ... and (SAVED) this tile's bias buffer as well
         {
           uint4* dstp = reinterpret_cast<uint4*>(P.pb + grow + key0 + slice * 16);
           uint4* dstd = reinterpret_cast<uint4*>(P.dsb + grow + key0 + slice * 16);
@@ -245,6 +244,15 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
         }
         if (HAS_BIAS && !SAVED) named_bar_sync(2, NCOMPUTE);   // (b) every thread has read its bias: the tile may be rewritten
+        if (SAVED) {
+          // Release this tile's TMEM and bias buffers only after the tile is completely done, and keep the compute warps
+          // in lockstep like the recompute variant does.  With the arrive placed before the stores and no CTA-wide barrier
+          // per tile the kernel produced run-to-run different gradients in ~8 % of the launches of a 6-tile item
+          // (tests/dev_determinism.py); either measure alone removes it (0 of 300 runs each), neither costs measurable
+          // time in this bandwidth-bound variant.  The hazard has not been root-caused: both are kept.
+          mbar_arrive(bar_p + (gj & 1));
+          named_bar_sync(2, NCOMPUTE);
+        }
       }
       named_bar_sync(2, NCOMPUTE);                         // sRow / sGeo reusable by the next item
     }
