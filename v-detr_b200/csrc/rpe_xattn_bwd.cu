@@ -243,16 +243,17 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           dstp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dstp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
         }
-        if (HAS_BIAS && !SAVED) named_bar_sync(2, NCOMPUTE);   // (b) every thread has read its bias: the tile may be rewritten
-        if (SAVED) {
-          // Release this tile's TMEM and bias buffers only after the tile is completely done, and keep the compute warps
-          // in lockstep like the recompute variant does.  With the arrive placed before the stores and no CTA-wide barrier
-          // per tile the kernel produced run-to-run different gradients in ~8 % of the launches of a 6-tile item
-          // (tests/dev_determinism.py); either measure alone removes it (0 of 300 runs each), neither costs measurable
-          // time in this bandwidth-bound variant.  The hazard has not been root-caused: both are kept.
-          mbar_arrive(bar_p + (gj & 1));
-          named_bar_sync(2, NCOMPUTE);
-        }
+        // Release this tile's TMEM (and, SAVED, bias) buffers only after the tile is completely done, and end every tile
+        // with a CTA-wide barrier.  The first saved-bias version arrived on bar_p before its global stores and let the
+        // compute warps drift; dq / dk / dv then differed run to run in ~8 % of the launches of a 6-tile item
+        // (tests/dev_determinism.py).  Either measure alone removes it (0 of 300 runs each).  The mbarrier protocol admits
+        // no shared-memory / TMEM hazard, and the wrong values are garbage (up to 8x the tensor's max), not stale tiles:
+        // the suspected cause is a register WAR between the STG.128 above, whose source registers are read late when the
+        // store queue backs up in this bandwidth-bound variant, and the next tile's asynchronous LDTM into the same
+        // registers -- releasing bar_p early lets the next MMA, hence the next LDTM, come sooner (a block-level fence
+        // after the stores did not help: 187 of 300).  All variants therefore end the tile with the barrier.
+        if (SAVED) mbar_arrive(bar_p + (gj & 1));
+        named_bar_sync(2, NCOMPUTE);                       // (b) also: every thread has read its bias tile
       }
       named_bar_sync(2, NCOMPUTE);                         // sRow / sGeo reusable by the next item
     }
