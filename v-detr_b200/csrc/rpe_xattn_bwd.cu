@@ -247,11 +247,10 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // with a CTA-wide barrier.  The first saved-bias version arrived on bar_p before its global stores and let the
         // compute warps drift; dq / dk / dv then differed run to run in ~8 % of the launches of a 6-tile item
         // (tests/dev_determinism.py).  Either measure alone removes it (0 of 300 runs each).  The mbarrier protocol admits
-        // no shared-memory / TMEM hazard, and the wrong values are garbage (up to 8x the tensor's max), not stale tiles:
-        // the suspected cause is a register WAR between the STG.128 above, whose source registers are read late when the
-        // store queue backs up in this bandwidth-bound variant, and the next tile's asynchronous LDTM into the same
-        // registers -- releasing bar_p early lets the next MMA, hence the next LDTM, come sooner (a block-level fence
-        // after the stores did not help: 187 of 300).  All variants therefore end the tile with the barrier.
+        // no shared-memory / TMEM hazard, and the wrong values are garbage (up to 8x the tensor's max), not stale tiles.
+        // A register WAR between the STG.128 above and the next tile's asynchronous LDTM was suspected, but the SASS shows
+        // the loop head waiting on the stores' read barrier, and a block-level fence after the stores made it worse (187 of
+        // 300).  Root cause open; all variants end the tile with the barrier and release bar_p last.
         if (SAVED) mbar_arrive(bar_p + (gj & 1));
         named_bar_sync(2, NCOMPUTE);                       // (b) also: every thread has read its bias tile
       }
