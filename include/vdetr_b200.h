@@ -152,6 +152,9 @@ int vdetr_layernorm_fwd(const float* x, const float* gamma, const float* beta, i
 int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
                         int cols, float* dx, float* dgamma, float* dbeta, void* stream);
 
+/* out[c] = sum_r x[r, c] for a dense [rows, cols] f32 matrix (bias gradient of the token-major Linear layers). */
+int vdetr_colsum(const float* x, int rows, int cols, float* out, void* stream);
+
 /* Training-mode BatchNorm1d + ReLU on token-major activations x [rows, cols] f32 (the Conv1d(k=1)-BatchNorm1d-ReLU
  * stacks of models/helpers.py:17-33 and :74-141 evaluated per token).  Batch statistics over the rows; running_mean /
  * running_var (may be NULL) are updated in place with `momentum` and the unbiased variance, like nn.BatchNorm1d.

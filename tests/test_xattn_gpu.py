@@ -312,3 +312,27 @@ def test_backward_is_run_to_run_deterministic(save, monkeypatch):
         r = _run(I, impl=0)
         for name in ("o", "dq", "dk", "dv"):
             assert np.array_equal(r[name], base[name]), name
+
+
+@pytest.mark.parametrize("T,cin,cout,bias", [(8192, 256, 256, True), (1000, 256, 18, True), (77, 6, 256, True), (512, 256, 64, False)])
+def test_token_linear_matches_torch(T, cin, cout, bias):
+    """ops.linear (cuBLAS GEMMs + the library's column-sum kernel for the bias gradient) vs F.linear in fp64."""
+    from vdetr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T + cout)
+    x = torch.randn(T // 7 if T % 7 == 0 else T, cin, device="cuda", generator=g).requires_grad_(True)
+    w = (torch.randn(cout, cin, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    b = torch.randn(cout, device="cuda", generator=g).requires_grad_(True) if bias else None
+    dy = torch.randn(x.shape[0], cout, device="cuda", generator=g)
+    want = torch.nn.functional.linear(x.double(), w.double(), None if b is None else b.double())
+    ins = (x, w) + ((b,) if bias else ())
+    gw = torch.autograd.grad(want, ins, dy.double())
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        got = ops.linear(x, w, b)
+        gg = torch.autograd.grad(got, ins, dy)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert (got.double() - want).abs().max().item() <= 1e-5 * want.abs().max().item() + 1e-6
+    for a, r, name in zip(gg, gw, ("dx", "dw", "db")):
+        assert (a.double() - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-6, name

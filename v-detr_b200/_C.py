@@ -47,6 +47,7 @@ _SIGS = {
     "vdetr_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdetr_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "vdetr_bn_relu_supported": (c_int, [c_int]),
     "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float] + [c_void_p] * 7),
     "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 4),

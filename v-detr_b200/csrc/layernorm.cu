@@ -168,3 +168,36 @@ int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, cons
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Column sums of a dense [rows, cols] f32 matrix: the bias gradient of every token-major Linear / Conv1d(k=1)
+// layer of the decoder (155 per step; the stock reduction kernel is latency bound on these 8 MB inputs).
+namespace {
+constexpr int CS_ROWS = 64;       // rows per CTA
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.x * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += x[(size_t)r * cols + c]; s1 += x[(size_t)(r + 1) * cols + c];
+    s2 += x[(size_t)(r + 2) * cols + c]; s3 += x[(size_t)(r + 3) * cols + c];
+  }
+  for (; r < r1; ++r) s0 += x[(size_t)r * cols + c];
+  atomicAdd(out + c, (s0 + s1) + (s2 + s3));
+}
+}  // namespace
+
+extern "C" int vdetr_colsum(const float* x, int rows, int cols, float* out, void* stream) {
+  if (rows < 0 || cols < 1) return VDETR_ERR_BAD_ARG;
+  if (!out || (rows > 0 && !x)) return VDETR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  VDETR_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
+  if (rows == 0) return 0;
+  const int threads = cols >= 256 ? 256 : ((cols + 31) / 32) * 32;
+  dim3 grid((rows + CS_ROWS - 1) / CS_ROWS, (cols + threads - 1) / threads);
+  colsum_kernel<<<grid, threads, 0, st>>>(x, rows, cols, out);
+  VDETR_LAUNCH_CHECK();
+  return 0;
+}

@@ -27,7 +27,7 @@ def pointwise_tokens(seq, x):
         m = mods[i]
         if isinstance(m, nn.Conv1d):
             assert m.kernel_size == (1,) and m.stride == (1,) and m.groups == 1
-            x = F.linear(x, m.weight.squeeze(-1), m.bias)
+            x = ops.linear(x, m.weight.squeeze(-1), m.bias)
         elif (type(m) is nn.BatchNorm1d and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
               and ops.bn_relu_train_supported(x, m)):
             x = ops.bn_relu_train(x, m)           # batch statistics + running-stat update + ReLU fused (csrc/batchnorm.cu)
@@ -64,6 +64,14 @@ class BatchNormDim1Swap(nn.BatchNorm1d):
 
     def forward(self, x):
         return super().forward(x.permute(1, 2, 0)).permute(2, 0, 1)
+
+
+class Linear(nn.Linear):
+    """nn.Linear (same parameters / state_dict) routed through ops.linear (bias gradient by the library's kernel)."""
+
+    def forward(self, x):
+        from . import ops
+        return ops.linear(x, self.weight, self.bias)
 
 
 class LayerNorm(nn.LayerNorm):

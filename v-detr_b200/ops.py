@@ -211,3 +211,40 @@ def bn_relu_train(x, bn):
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return _BnReluTrain.apply(x.contiguous(), bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum)
+
+
+class _TokenLinear(Function):
+    """F.linear on [..., in] features whose bias gradient is the library's column-sum kernel (the GEMMs stay cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(dy2.shape[1], dtype=dy2.dtype, device=dy2.device)
+            with torch.cuda.device(dy2.device):
+                _C.check(_C.lib().vdetr_colsum(_C.ptr(dy2), dy2.shape[0], dy2.shape[1], _C.ptr(db), _C.stream_ptr()))
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """torch.nn.functional.linear; on fp32 CUDA tensors that require grad the backward uses the library's column-sum
+    kernel for the bias gradient."""
+    if (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and torch.is_grad_enabled()
+            and (x.requires_grad or weight.requires_grad) and x.shape[-1] == weight.shape[1]):
+        return _TokenLinear.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)

@@ -29,7 +29,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import ops
-from .helpers import ACTIVATION_DICT, NORM_DICT, WEIGHT_INIT_DICT, GenericMLP, PositionEmbeddingLearned, get_clones
+from .helpers import ACTIVATION_DICT, NORM_DICT, WEIGHT_INIT_DICT, GenericMLP, Linear, PositionEmbeddingLearned, get_clones
 
 
 # ------------------------------------------------------------------------------------------------- geometry
@@ -211,7 +211,7 @@ class MultiheadSelfAttention(nn.Module):
         self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
         self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
         self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
-        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        self.out_proj = Linear(embed_dim, embed_dim)
         self.dropout = dropout
         self.attn_drop = nn.Dropout(dropout)
         nn.init.xavier_uniform_(self.in_proj_weight)
@@ -223,11 +223,11 @@ class MultiheadSelfAttention(nn.Module):
         wq, wk, wv = self.in_proj_weight.chunk(3)
         bq, bk, bv = self.in_proj_bias.chunk(3)
         if key is query:
-            qk = F.linear(query, self.in_proj_weight[: 2 * D], self.in_proj_bias[: 2 * D])
+            qk = ops.linear(query, self.in_proj_weight[: 2 * D], self.in_proj_bias[: 2 * D])
             q, k = qk[..., :D], qk[..., D:]
         else:
-            q, k = F.linear(query, wq, bq), F.linear(key, wk, bk)
-        v = F.linear(value, wv, bv)
+            q, k = ops.linear(query, wq, bq), ops.linear(key, wk, bk)
+        v = ops.linear(value, wv, bv)
         q = (q * (hd ** -0.5)).reshape(L, B, H, hd).transpose(0, 1)
         k = k.reshape(-1, B, H, hd).transpose(0, 1)
         v = v.reshape(-1, B, H, hd).transpose(0, 1)
@@ -259,11 +259,11 @@ class ShareSelfAttention(nn.Module):
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
         self.num_heads = num_heads
         self.scale = (dim // num_heads) ** -0.5
-        self.q = nn.Linear(dim, dim, bias=qkv_bias)
-        self.k = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
-        self.v = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.q = Linear(dim, dim, bias=qkv_bias)
+        self.k = Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.v = Linear(dim, dim // num_heads, bias=qkv_bias)
         self.attn_drop = nn.Dropout(dropout)
-        self.proj = nn.Linear(dim, dim)
+        self.proj = Linear(dim, dim)
         self.proj_drop = nn.Dropout(dropout)
         self.softmax = nn.Softmax(dim=-1)
 
@@ -300,11 +300,11 @@ class GlobalShareCrossAttention(nn.Module):
                              torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), dim=-1).unsqueeze(0))
         self.max_value = max_value
         self.cpb_mlps = get_clones(self.build_cpb_mlp(3, args.rpe_dim, num_heads), 8)
-        self.q = nn.Linear(dim, dim, bias=qkv_bias)
-        self.k = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
-        self.v = nn.Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.q = Linear(dim, dim, bias=qkv_bias)
+        self.k = Linear(dim, dim // num_heads, bias=qkv_bias)
+        self.v = Linear(dim, dim // num_heads, bias=qkv_bias)
         self.attn_drop = nn.Dropout(attn_drop)
-        self.proj = nn.Linear(dim, dim)
+        self.proj = Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
         self.softmax = nn.Softmax(dim=-1)
         self.need_weights = False       # set True to get the [B,H,nQ,nK] probabilities back (debug path)
@@ -370,9 +370,9 @@ class FFNLayer(nn.Module):
     def __init__(self, d_model, dim_feedforward=256, dropout=0.1, norm_fn_name="ln", activation="relu",
                  normalize_before=True):
         super().__init__()
-        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear1 = Linear(d_model, dim_feedforward)
         self.dropout = nn.Dropout(dropout, inplace=False)
-        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.linear2 = Linear(dim_feedforward, d_model)
         self.norm = NORM_DICT[norm_fn_name](d_model)
         self.activation = ACTIVATION_DICT[activation]()
         self.normalize_before = normalize_before
@@ -405,9 +405,9 @@ class GlobalDecoderLayer(nn.Module):
         self.dropout1 = nn.Dropout(dropout, inplace=False)
         self.dropout2 = nn.Dropout(dropout, inplace=False)
         self.dropout3 = nn.Dropout(dropout, inplace=False)
-        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear1 = Linear(d_model, dim_feedforward)
         self.dropout = nn.Dropout(dropout, inplace=False)
-        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.linear2 = Linear(dim_feedforward, d_model)
         self.activation = ACTIVATION_DICT[activation]()
         self.normalize_before = normalize_before
 
