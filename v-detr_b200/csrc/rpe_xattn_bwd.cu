@@ -216,7 +216,10 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld16(tdP0 + (gj & 1) * BN + lane_addr + slice * 16, dr);
         tmem_ld_wait();
         tc_fence_before();
-        if (!SAVED) mbar_arrive(bar_p + (gj & 1));         // TMEM buffers of this tile may be overwritten
+        if (!SAVED) {
+          if (HAS_BIAS) fence_proxy_async_smem();          // key xyz was read (generic proxy), bulk copies rewrite it (async proxy)
+          mbar_arrive(bar_p + (gj & 1));                   // TMEM buffers of this tile may be overwritten
+        }
         const float* brow = nullptr;
         if (HAS_BIAS)
           brow = reinterpret_cast<const float*>(sBias + (SAVED ? (gj & 1) * (QT * BIAS_STRIDE_F4) : 0) + (row >> 2) * BIAS_STRIDE_F4 +
@@ -237,22 +240,21 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[c >> 1] = pack_f16x2(pv[0], pv[1]);
           dk_[c >> 1] = pack_f16x2(dv[0], dv[1]);
         }
+        if (SAVED) {
+          // The bias tile was read through the generic proxy and will be overwritten through the async proxy (bulk
+          // copies of tile gj + 2): the mbarrier arrive / wait chain alone does not order the two proxies.  Without this
+          // fence dq / dk / dv differed run to run in 8-17 % of the launches of a 6-tile item (tests/dev_determinism.py;
+          // 0 of 400 with it).
+          fence_proxy_async_smem();
+          mbar_arrive(bar_p + (gj & 1));                   // TMEM buffers and the bias buffer of this tile are free
+        }
         {
           uint4* dstp = reinterpret_cast<uint4*>(P.pb + grow + key0 + slice * 16);
           uint4* dstd = reinterpret_cast<uint4*>(P.dsb + grow + key0 + slice * 16);
           dstp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dstp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
         }
-        // Release this tile's TMEM (and, SAVED, bias) buffers only after the tile is completely done, and end every tile
-        // with a CTA-wide barrier.  The first saved-bias version arrived on bar_p before its global stores and let the
-        // compute warps drift; dq / dk / dv then differed run to run in ~8 % of the launches of a 6-tile item
-        // (tests/dev_determinism.py).  Either measure alone removes it (0 of 300 runs each).  The mbarrier protocol admits
-        // no shared-memory / TMEM hazard, and the wrong values are garbage (up to 8x the tensor's max), not stale tiles.
-        // A register WAR between the STG.128 above and the next tile's asynchronous LDTM was suspected, but the SASS shows
-        // the loop head waiting on the stores' read barrier, and a block-level fence after the stores made it worse (187 of
-        // 300).  Root cause open; all variants end the tile with the barrier and release bar_p last.
-        if (SAVED) mbar_arrive(bar_p + (gj & 1));
-        named_bar_sync(2, NCOMPUTE);                       // (b) also: every thread has read its bias tile
+        if (HAS_BIAS && !SAVED) named_bar_sync(2, NCOMPUTE);   // (b) every thread has read its bias: the tile may be rewritten
       }
       named_bar_sync(2, NCOMPUTE);                         // sRow / sGeo reusable by the next item
     }
