@@ -75,3 +75,57 @@ def test_morton_order_is_a_permutation():
     perm = morton_order(xyz)
     assert perm.shape == (3, 257)
     assert all(sorted(p.tolist()) == list(range(257)) for p in perm)
+
+
+def test_token_major_stacks_equal_conv_stacks():
+    """helpers.pointwise_tokens (GEMMs on [tokens, C] rows) against the reference formulation it replaces (Conv1d(k=1) /
+    BatchNorm1d on [B, C, N], models/helpers.py:17-33, 74-141): same outputs, gradients and running statistics, in
+    train and eval mode."""
+    import copy
+    import torch
+    from vdetr_b200 import helpers
+    torch.manual_seed(0)
+    B, N, C = 3, 50, 256
+    mlp = helpers.GenericMLP(input_dim=C, hidden_dims=[C, C], output_dim=18, norm_fn_name="bn1d", activation="relu",
+                             use_conv=True, dropout=0.0)
+    assert mlp.supports_tokens
+    pe = helpers.PositionEmbeddingLearned(6, C)
+    for train in (True, False):
+        for mod, xin in ((mlp, torch.randn(N, B, C)), (pe, torch.randn(B, N, 6))):
+            a, b = copy.deepcopy(mod).train(train), copy.deepcopy(mod).train(train)
+            xa, xb = xin.clone().requires_grad_(True), xin.clone().requires_grad_(True)
+            if mod is mlp:
+                ya = a(xa.permute(1, 2, 0)).transpose(1, 2)                                  # [B, N, out] as the decoder builds it
+                yb = b.forward_tokens(xb.reshape(N * B, C)).view(N, B, -1).transpose(0, 1)
+            else:
+                ya = a(xa).permute(2, 0, 1)                                                   # [N, B, C]
+                yb = b.forward_tokens(xb)
+            assert torch.allclose(ya, yb, atol=2e-5, rtol=1e-4)
+            g = torch.randn_like(ya)
+            ya.backward(g)
+            yb.backward(g)
+            assert torch.allclose(xa.grad, xb.grad, atol=2e-5, rtol=1e-3)
+            for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
+                assert torch.allclose(p1.grad, p2.grad, atol=1e-4, rtol=1e-3), n1
+            for (n1, b1), (_, b2) in zip(a.named_buffers(), b.named_buffers()):
+                assert torch.allclose(b1.float(), b2.float(), atol=1e-5, rtol=1e-4), n1
+
+
+def test_flat_grad_gather_matches_accumulation():
+    """parallel.FlatGradAllReduce: detached gradients + one multi-tensor copy give the flat buffer the same content as
+    accumulating into its views, parameters without gradient read as zero, and gather_ is idempotent."""
+    import torch
+    from vdetr_b200 import parallel
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    unused = torch.nn.Parameter(torch.ones(5))
+    params = list(net.parameters()) + [unused]
+    fg = parallel.FlatGradAllReduce(params)
+    x = torch.randn(10, 8)
+    fg.zero_()
+    net(x).square().sum().backward()
+    want = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params]
+    flat = fg.gather_()
+    assert torch.equal(flat, torch.cat([w.reshape(-1) for w in want]))
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(fg.params, fg.views))
+    assert torch.equal(fg.gather_(), flat) and torch.equal(fg.sync_(), flat)
