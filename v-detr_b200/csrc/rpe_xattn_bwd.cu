@@ -224,6 +224,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (HAS_BIAS)
           brow = reinterpret_cast<const float*>(sBias + (SAVED ? (gj & 1) * (QT * BIAS_STRIDE_F4) : 0) + (row >> 2) * BIAS_STRIDE_F4 +
                                                 slice * 16) + (row & 3);
+        const bool tail_tile = key0 + BN > P.nK;
         uint32_t pk[8], dk_[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
@@ -233,7 +234,7 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float s = __uint_as_float(sr[c + e]);
             if (HAS_BIAS) s += brow[(c + e) * 4];
             float p = ex2_approx(s * LOG2E - lse2);
-            if (key0 + slice * 16 + c + e >= P.nK) p = 0.f;
+            if (tail_tile && key0 + slice * 16 + c + e >= P.nK) p = 0.f;       // only the last key tile is ragged
             const float ds = p * (__uint_as_float(dr[c + e]) - Drow);        // = g * dS
             pv[e] = p; dv[e] = ds;
           }

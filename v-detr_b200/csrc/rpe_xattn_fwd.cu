@@ -239,6 +239,7 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float x[16];
         float pmax = -INFINITY;
         {
+          const bool tail_tile = key0 + BN > P.nK;
           const float* brow = nullptr;
           if (HAS_BIAS) brow = reinterpret_cast<const float*>(sBias + (row >> 2) * BIAS_STRIDE_F4 + slice * 16) + (row & 3);
 #pragma unroll
@@ -246,7 +247,7 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float s = __uint_as_float(sr[c]);
             if (HAS_BIAS) s += brow[c * 4];
             s *= LOG2E;
-            if (key0 + slice * 16 + c >= P.nK) s = -INFINITY;
+            if (tail_tile && key0 + slice * 16 + c >= P.nK) s = -INFINITY;       // only the last key tile is ragged
             x[c] = s;
             pmax = fmaxf(pmax, s);
           }
