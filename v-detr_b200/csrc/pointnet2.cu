@@ -309,7 +309,12 @@ __global__ void group_grad_kernel(const float* __restrict__ grad_out, const int3
 }
 
 // ------------------------------------------------------------------------------------------ ball query
-constexpr int BQ_THREADS = 128;
+// A warp owns a centre and tests 32 consecutive points per step; hits are appended in point order with a ballot /
+// prefix-popcount, which reproduces the reference's sequential scan (first `nsample` hits in index order, all slots
+// pre-filled with the first hit: ball_query_gpu.cu:25-41) exactly.  The CTA's 8 centres share 1024-point tiles of xyz
+// in shared memory; the scan stops as soon as every centre of the CTA is full.
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_THREADS = BQ_WARPS * 32;
 constexpr int BQ_TILE = 1024;
 __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int N, int M, float radius, int nsample,
@@ -317,19 +322,20 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
   __shared__ float4 tile[BQ_TILE];
   const int b = blockIdx.y;
   const float* pts = xyz + (size_t)b * N * 3;
-  const int j = blockIdx.x * BQ_THREADS + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * BQ_WARPS + warp;
   const bool active = j < M;
   float cx = 0.f, cy = 0.f, cz = 0.f;
   if (active) {
     const float* c = new_xyz + ((size_t)b * M + j) * 3;
-    cx = c[0]; cy = c[1]; cz = c[2];
+    cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
   }
   int32_t* row = idx + ((size_t)b * M + (active ? j : 0)) * nsample;
   const float radius2 = __fmul_rn(radius, radius);                 // ball_query_gpu.cu:25
-  int cnt = active ? 0 : nsample;
-  if (active && nsample > 0) { /* rows without a hit stay zero: ball_query.cpp:22-24 */
-    for (int l = 0; l < nsample; ++l) row[l] = 0;
-  }
+  int cnt = active ? 0 : nsample;                                  // warp-uniform
+  if (active)                                                      // rows without a hit stay zero: ball_query.cpp:22-24
+    for (int l = lane; l < nsample; l += 32) row[l] = 0;
+  __syncwarp();
   for (int base = 0; base < N; base += BQ_TILE) {
     const int len = min(BQ_TILE, N - base);
     __syncthreads();
@@ -338,17 +344,25 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
       tile[t] = make_float4(p[0], p[1], p[2], 0.f);
     }
     __syncthreads();
-    if (cnt < nsample) {
-      for (int t = 0; t < len && cnt < nsample; ++t) {
+    for (int t0 = 0; t0 < len && cnt < nsample; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      if (t < len) {
         const float4 p = tile[t];
         const float dx = __fsub_rn(cx, p.x), dy = __fsub_rn(cy, p.y), dz = __fsub_rn(cz, p.z);
         const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));     // :33-35, FMA-contracted
-        if (d2 < radius2) {                                                        // strict, :36
-          const int k = base + t;
-          if (cnt == 0) for (int l = 0; l < nsample; ++l) row[l] = k;              // :37-41
-          row[cnt] = k;
-          ++cnt;
+        hit = d2 < radius2;                                                        // strict, :36
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (mask) {
+        if (cnt == 0) {                                                            // :37-41: first hit fills every slot
+          const int first = base + t0 + __ffs(mask) - 1;
+          for (int l = lane; l < nsample; l += 32) row[l] = first;
+          __syncwarp();
         }
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (hit && pos < nsample) row[pos] = base + t;
+        cnt = min(nsample, cnt + __popc(mask));
       }
     }
     if (__syncthreads_and(cnt >= nsample)) break;
@@ -448,7 +462,7 @@ int vdetr_pn2_ball_query(const float* new_xyz, const float* xyz, int B, int N, i
   if (B < 0 || N < 0 || M < 0 || nsample < 0) return VDETR_ERR_BAD_ARG;
   if (B == 0 || M == 0 || nsample == 0) return 0;
   if (B > 65535) return VDETR_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)((M + BQ_THREADS - 1) / BQ_THREADS), (unsigned)B);
+  dim3 grid((unsigned)((M + BQ_WARPS - 1) / BQ_WARPS), (unsigned)B);
   ball_query_kernel<<<grid, BQ_THREADS, 0, (cudaStream_t)stream>>>(new_xyz, xyz, N, M, radius, nsample, idx);
   VDETR_LAUNCH_CHECK();
   return 0;
