@@ -107,14 +107,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def build_ours(torch, num_layers=NLAYERS, nq=NQ):
+def build_ours(torch, num_layers=NLAYERS, nq=NQ, dropout=0.1, mlp_dropout=0.3):
+    """The reference's training defaults: --dec_dropout 0.1 (main.py:75; attention, residual and FFN dropouts),
+    --mlp_dropout 0.3 (main.py:92; box heads)."""
     from vdetr_b200 import vdetr_transformer as vt
     args = types.SimpleNamespace(log_scale=512.0, rpe_quant="bilinear_4_10", angle_type="", rpe_dim=128, share_selfattn=False)
-    # dropout 0: the fused attention kernels implement no dropout; the reference trains with 0.1 / 0.3
-    first = vt.FFNLayer(d_model=256, dim_feedforward=256, dropout=0.0)
-    layer = vt.GlobalDecoderLayer(d_model=256, nhead=4, dim_feedforward=256, dropout=0.0, pos_for_key=False, args=args)
+    first = vt.FFNLayer(d_model=256, dim_feedforward=256, dropout=dropout)
+    layer = vt.GlobalDecoderLayer(d_model=256, nhead=4, dim_feedforward=256, dropout=dropout, pos_for_key=False, args=args)
     torch.manual_seed(0)
-    return vt.TransformerDecoder(first, layer, vt.ScanNetBoxConfig(), num_layers=num_layers, decoder_dim=256, mlp_dropout=0.0,
+    return vt.TransformerDecoder(first, layer, vt.ScanNetBoxConfig(), num_layers=num_layers, decoder_dim=256, mlp_dropout=mlp_dropout,
                                  mlp_norm="bn1d", mlp_act="relu", mlp_sep=True, pos_for_key=False, num_queries=nq,
                                  cls_loss="focalloss_0.25", is_bilable=True, q_content="random", return_intermediate=True,
                                  args=args)
@@ -161,6 +162,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="scenes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="--dec_dropout of the reference (main.py:75)")
+    ap.add_argument("--mlp-dropout", type=float, default=0.3, help="--mlp_dropout of the reference (main.py:92)")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of one step to this file and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying a captured CUDA graph")
     ap.add_argument("--max-seconds", type=int, default=480, help="hard watchdog: abort instead of hanging")
@@ -178,7 +181,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     config = {"workload": f"C3/C4: {a.batch} scenes per GPU x {NK} keys x {NQ} queries x {NLAYERS} decoder layers, "
-                          "fwd+bwd+AdamW, train mode (BN batch stats per GPU, dropout 0), TF32 Linear/Conv layers",
+                          f"fwd+bwd+AdamW, train mode (BN batch stats per GPU, dec_dropout {a.dropout} incl. attention dropout "
+                          f"inside the fused kernels, mlp_dropout {a.mlp_dropout}), TF32 Linear/Conv layers",
               "global_batch": a.batch * world, "parallelism": f"dp{world}",
               "l2": "per-step working set (> 6 GB of attention scratch, saved bias and activations) >> 126 MB L2; no explicit flush",
               "notes": "training keeps the fused forward's per-pair bias (537 MB per layer at batch 8) for the backward"}
@@ -215,7 +219,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import vdetr_b200._C as C
 
-    dec = build_ours(torch).to(dev).train()
+    dec = build_ours(torch, dropout=a.dropout, mlp_dropout=a.mlp_dropout).to(dev).train()
     for p in dec.pointcls_heads.parameters():        # used by ModelVDETR.forward, not by the decoder itself
         p.requires_grad_(False)
     from vdetr_b200 import parallel
@@ -277,8 +281,8 @@ def main():
         step(resident, False)
     own_launches_per_step = int(C.lib().vdetr_launch_count(1)) // 2       # kernels of libvdetr_b200 per step
     import ctypes
-    tot = (ctypes.c_float * 3)()
-    cnt = (ctypes.c_int * 3)()
+    tot = (ctypes.c_float * 4)()
+    cnt = (ctypes.c_int * 4)()
     C.lib().vdetr_timing_read(tot, cnt)
     C.lib().vdetr_timing_enable(0)
     timed_eager_steps = 2
@@ -376,7 +380,7 @@ def main():
                                                      "pair, issue slots 78 % / FMA pipe 58 % busy (ncu, DESIGN.md 4.1)",
                                              "gevals_per_s": evals / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None}},
             "kernel_ms_per_step": {"xattn_fwd": tot[0] / timed_eager_steps, "xattn_bwd_pass1": tot[1] / timed_eager_steps,
-                                   "dtables": tot[2] / timed_eager_steps,
+                                   "dtables": tot[2] / timed_eager_steps, "xattn_bwd_pass2_dkdv": tot[3] / timed_eager_steps,
                                    "launches_per_step": [int(c) // timed_eager_steps for c in cnt],
                                    "how": "CUDA events around each launch (vdetr_timing_*), eager pass of 2 steps"}}
     if rank == 0:

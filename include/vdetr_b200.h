@@ -99,39 +99,47 @@ typedef struct VdetrXattnShape {
  *           leaves the fp32 bias of every (query,key) pair for the backward, which then streams it back instead
  *           of recomputing it (training: 16 B per pair of activation memory buys ~5x on the backward pass-1
  *           kernel; the reference keeps ~2.4 GB of autograd intermediates per layer-scene for the same purpose).
+ *   dropout_p, dropout_seed: nn.Dropout on the attention probabilities (attn_drop, vdetr_transformer.py:751-752;
+ *           main.py:75 trains with 0.1).  dropout_p in [0,1); when > 0, dropout_seed is a DEVICE pointer to one 64-bit
+ *           seed (device memory so that the call can be captured in a CUDA graph and re-seeded between replays).
+ *           The keep mask of element (row, key) is a pure function of (seed, row, key) -- Philox4x32-10,
+ *           csrc/philox.cuh -- so the backward regenerates it from the same seed; kept probabilities are scaled by
+ *           1/(1-p).  dropout_p = 0 (eval) ignores the seed.  impl 1 does not implement dropout.
  * impl: 0 = tcgen05/TMA fused kernel (product path), 1 = SIMT validation kernel.
  * workspace: vdetr_xattn_fwd_workspace_bytes(&shape, impl). */
 size_t vdetr_xattn_fwd_workspace_bytes(const VdetrXattnShape* s, int impl);
 size_t vdetr_xattn_bias_save_bytes(const VdetrXattnShape* s, int impl);   /* 0 when the option does not apply */
 int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v,
                     const float* xyz, const float* ref_pts, const float* ref_angle, const float* tables,
-                    float* out, float* lse, float* bias_save, void* workspace, size_t workspace_bytes, int impl,
-                    void* stream);
+                    float* out, float* lse, float* bias_save, float dropout_p, const uint64_t* dropout_seed,
+                    void* workspace, size_t workspace_bytes, int impl, void* stream);
 
-/* Backward of the same op (dropout disabled):
+/* Backward of the same op:
  *   in : q,k,v,xyz,ref_pts,ref_angle,tables as forward; out, lse from forward; dout [B,nQ,H,hd];
- *        bias_saved = the forward's bias_save buffer or NULL (NULL: the bias is recomputed)
+ *        bias_saved = the forward's bias_save buffer or NULL (NULL: the forward kernel is run once more into a
+ *        transient buffer inside the workspace -- pass bias_is_saved = 0 to the workspace query);
+ *        dropout_p / dropout_seed: the values the forward was called with
  *   out: dq [B,nQ,H,hd], dk, dv [B,nK,kv_heads,hd], dtables [8,n,n,n,H]  -- all fully overwritten.
  *   No gradient is produced for xyz / ref_pts (detached in the reference, vdetr_transformer.py:369-412). */
-size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl);
+size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl, int bias_is_saved);
 int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v,
                     const float* xyz, const float* ref_pts, const float* ref_angle, const float* tables,
-                    const float* out, const float* lse, const float* dout, const float* bias_saved, float* dq,
-                    float* dk, float* dv, float* dtables, void* workspace, size_t workspace_bytes, int impl,
-                    void* stream);
+                    const float* out, const float* lse, const float* dout, const float* bias_saved, float dropout_p,
+                    const uint64_t* dropout_seed, float* dq, float* dk, float* dv, float* dtables, void* workspace,
+                    size_t workspace_bytes, int impl, void* stream);
 
 /* Bias only (debug / return_attn_weights path): rpe [B,H,nQ,nK] f32  (vdetr_transformer.py:708-731). */
 int vdetr_rpe_bias(const VdetrXattnShape* s, const float* xyz, const float* ref_pts, const float* ref_angle,
                    const float* tables, float* rpe, void* stream);
 
 /* Optional per-kernel timing for benchmarks: when enabled, CUDA events are recorded on the launch stream
- * around [0] the fused forward kernel, [1] the backward pass-1 kernel, [2] the dTables kernel (at most 512
- * launches each between reads).  vdetr_timing_read synchronises on the recorded events, returns the summed
+ * around [0] the fused forward kernel, [1] the backward pass-1 kernel, [2] the dTables kernel, [3] the backward
+ * pass-2 (dK / dV) kernel (cross-attention launches only; at most 512 launches each between reads).  vdetr_timing_read synchronises on the recorded events, returns the summed
  * device time in ms and the launch counts, and resets the counters. */
 /* Number of kernels this library has launched (host-side count of its own launches; cuBLAS GEMMs are not included). */
 unsigned long long vdetr_launch_count(int reset);
 int vdetr_timing_enable(int enable);
-int vdetr_timing_read(float* total_ms /*[3]*/, int* launches /*[3]*/);
+int vdetr_timing_read(float* total_ms /*[4]*/, int* launches /*[4]*/);
 
 /* Adjoint of vdetr_rpe_bias w.r.t. the tables: dtables[8,n,n,n,H] = sum_{b,q,k} dbias[b,q,k,h] * w_corner
  * (what autograd of F.grid_sample returns for its input at vdetr_transformer.py:727-731).
@@ -145,27 +153,36 @@ int vdetr_rpe_dtables(const VdetrXattnShape* s, const float* xyz, const float* r
  * models/vdetr_transformer.py:463-466 norm1-3, :586-606 FFNLayer.norm, :129 TransformerDecoder.norm).
  * cols must satisfy vdetr_layernorm_supported (128, 256, 384 or 512).
  *   fwd: y [rows,cols], mean [rows], rstd [rows] (saved for backward)       bwd: dx [rows,cols], dgamma / dbeta [cols]
- *   (dgamma / dbeta are fully overwritten). */
+ *   (dgamma / dbeta are fully overwritten).
+ * Column sums that cross CTAs (dgamma / dbeta here, the BatchNorm statistics and gradients, vdetr_colsum) are reduced
+ * without float atomics: per-CTA partial sums in `workspace` (vdetr_reduce_workspace_floats(cols) floats, not
+ * initialised by the caller) are added in a fixed order, so results are bit-reproducible run to run -- like the stock
+ * nn.LayerNorm / nn.BatchNorm1d kernels the reference relies on. */
+size_t vdetr_reduce_workspace_floats(int cols);
 int vdetr_layernorm_supported(int cols);
 int vdetr_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float* y,
                         float* mean, float* rstd, void* stream);
 int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
-                        int cols, float* dx, float* dgamma, float* dbeta, void* stream);
+                        int cols, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
 
-/* out[c] = sum_r x[r, c] for a dense [rows, cols] f32 matrix (bias gradient of the token-major Linear layers). */
-int vdetr_colsum(const float* x, int rows, int cols, float* out, void* stream);
+/* out[c] = sum_r x[r, c] for a dense [rows, cols] f32 matrix (bias gradient of the token-major Linear layers).
+ * workspace: vdetr_colsum_workspace_floats(cols) floats; deterministic (fixed summation order). */
+size_t vdetr_colsum_workspace_floats(int cols);
+int vdetr_colsum(const float* x, int rows, int cols, float* out, float* workspace, void* stream);
 
 /* Training-mode BatchNorm1d + ReLU on token-major activations x [rows, cols] f32 (the Conv1d(k=1)-BatchNorm1d-ReLU
  * stacks of models/helpers.py:17-33 and :74-141 evaluated per token).  Batch statistics over the rows; running_mean /
  * running_var (may be NULL) are updated in place with `momentum` and the unbiased variance, like nn.BatchNorm1d.
- *   fwd: y, mean [cols], rstd [cols]; workspace: 2 * cols floats.       bwd: dx, dgamma, dbeta (fully overwritten);
- *   y is the forward output (its sign is the ReLU mask).  cols: vdetr_bn_relu_supported (128, 256, 384, 512). */
+ *   fwd: y, mean [cols], rstd [cols].       bwd: dx, dgamma, dbeta (fully overwritten);
+ *   y is the forward output (its sign is the ReLU mask).  cols: vdetr_bn_relu_supported (128, 256, 384, 512).
+ *   workspace (both directions): vdetr_reduce_workspace_floats(cols) floats. */
 int vdetr_bn_relu_supported(int cols);
 int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float momentum,
                             float* y, float* mean, float* rstd, float* running_mean, float* running_var, float* workspace,
                             void* stream);
 int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
-                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, void* stream);
+                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, float* workspace,
+                            void* stream);
 
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call

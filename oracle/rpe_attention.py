@@ -125,26 +125,33 @@ def rpe_bias(ref_pts, xyz, tables, ref_angle=None, log_scale=512.0, max_value=4.
     return out
 
 
-def xattn_core_forward(q, k, v, bias):
-    """P = softmax_k(q k^T + bias); O = P v.   MQA: k, v are shared by all heads.
+def xattn_core_forward(q, k, v, bias, keep=None, p_drop=0.0):
+    """P = softmax_k(q k^T + bias); O = dropout(P) v.   MQA: k, v are shared by all heads.
 
-    Reference: models/vdetr_transformer.py:739-753 (attn_mask=None, dropout off).
+    Reference: models/vdetr_transformer.py:739-753 (attn_mask=None).  Dropout (:751-752, nn.Dropout on the
+    probabilities) is expressed through an explicit keep mask [B,H,nQ,nK] so that it can be compared with a kernel that
+    draws the same mask: dropout(P) = P * keep / (1 - p_drop).
     q [B,H,nQ,hd] (already multiplied by hd^-0.5), k,v [B,nK,hd], bias [B,H,nQ,nK]
-    ->  O [B,H,nQ,hd], P [B,H,nQ,nK], LSE [B,H,nQ] (natural log).
+    ->  O [B,H,nQ,hd], P [B,H,nQ,nK] (before dropout), LSE [B,H,nQ] (natural log).
     """
     s = np.einsum("bhqd,bkd->bhqk", q, k) + bias
     m = s.max(-1, keepdims=True)
     e = np.exp(s - m)
     l = e.sum(-1, keepdims=True)
     p = e / l
-    o = np.einsum("bhqk,bkd->bhqd", p, v)
+    pd = p if keep is None else p * keep / (1.0 - p_drop)
+    o = np.einsum("bhqk,bkd->bhqd", pd, v)
     return o, p, (m + np.log(l))[..., 0]
 
 
-def xattn_core_backward(q, k, v, p, o, do):
+def xattn_core_backward(q, k, v, p, o, do, keep=None, p_drop=0.0):
     """Analytic backward of xattn_core_forward.  Returns dq, dk, dv, dbias (= dS)."""
-    dv = np.einsum("bhqk,bhqd->bkd", p, do)
+    scale = None if keep is None else keep / (1.0 - p_drop)
+    pd = p if keep is None else p * scale
+    dv = np.einsum("bhqk,bhqd->bkd", pd, do)
     dp = np.einsum("bhqd,bkd->bhqk", do, v)
+    if keep is not None:
+        dp = dp * scale
     delta = (do * o).sum(-1, keepdims=True)
     ds = p * (dp - delta)
     dq = np.einsum("bhqk,bkd->bhqd", ds, k)

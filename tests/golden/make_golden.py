@@ -68,6 +68,28 @@ def gen_xattn(vt, cfg, name, seed, B, nQ, nK, rotated, far):
     print(name, {k: v.shape for k, v in out.items() if not k.startswith("grad.")})
 
 
+def gen_xattn_mask(vt, cfg, name, seed, B, nQ, nK):
+    """attn_mask semantics of the reference (models/vdetr_transformer.py:743-749): a bool mask sets the LOGIT to -100,
+    a float mask is added.  Same module / inputs as xattn_small; the masks come from recipe.xattn_masks."""
+    args = types.SimpleNamespace(log_scale=512.0, rpe_quant="bilinear_4_10", angle_type="", rpe_dim=128)
+    mod = vt.GlobalShareCrossAttention(256, 4, args=args).eval()
+    sd = mod.state_dict()
+    for k, v in recipe.xattn_params(seed).items():
+        sd[k] = torch.from_numpy(v)
+    mod.load_state_dict(sd)
+    case = recipe.xattn_case(seed + 1, B, nQ, nK, False, 0.3)
+    ref = ref_vertices(cfg, torch.from_numpy(case["center"]), torch.from_numpy(case["size"]), torch.zeros(B, nQ), vt)
+    mb, mf = recipe.xattn_masks(seed + 2, B, nQ, nK)
+    out = {}
+    with torch.no_grad():
+        for tag, m in (("bool", torch.from_numpy(mb)), ("float", torch.from_numpy(mf))):
+            x, attn = mod(torch.from_numpy(case["query"]), torch.from_numpy(case["key"]), ref, None,
+                          torch.from_numpy(case["xyz"]), attn_mask=m)
+            out["x_" + tag], out["attn_" + tag] = x.numpy(), attn.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def build_ref_decoder(vt, cfg, L, nq, dropout, mlp_dropout, share=False):
     args = types.SimpleNamespace(log_scale=512.0, rpe_quant="bilinear_4_10", angle_type="", rpe_dim=128,
                                  share_selfattn=share)
@@ -129,7 +151,11 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     Cfg, vt = import_reference()
     cfg = Cfg()
+    if "--only-mask" in sys.argv:
+        gen_xattn_mask(vt, cfg, "xattn_mask", 11, B=2, nQ=24, nK=80)
+        sys.exit(0)
     gen_xattn(vt, cfg, "xattn_small", 11, B=2, nQ=24, nK=80, rotated=False, far=0.3)
+    gen_xattn_mask(vt, cfg, "xattn_mask", 11, B=2, nQ=24, nK=80)
     gen_xattn(vt, cfg, "xattn_rot", 21, B=1, nQ=16, nK=48, rotated=True, far=0.2)
     gen_decoder(vt, cfg, "decoder_eval", 31, B=2, nK=96, nq=32, L=2, train=False)
     gen_decoder(vt, cfg, "decoder_train", 41, B=2, nK=96, nq=32, L=2, train=True)

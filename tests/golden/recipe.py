@@ -55,6 +55,15 @@ def xattn_case(seed: int, B: int, nQ: int, nK: int, rotated: bool = False, far: 
     return dict(xyz=xyz, center=center, size=size, angle=angle, query=query, key=key, dout=dout)
 
 
+def xattn_masks(seed: int, B: int, nQ: int, nK: int):
+    """attn_mask test inputs [B,nQ,nK]: a bool mask (about 30 % masked, never a whole row) and a float mask."""
+    rs = np.random.RandomState(seed)
+    mb = rs.rand(B, nQ, nK) < 0.3
+    mb[:, :, 0] = False
+    mf = (rs.standard_normal((B, nQ, nK)) * 2.0).astype(np.float32)
+    return mb, mf
+
+
 def fill_state_dict(shapes: dict, seed: int, scale: float = 0.08) -> dict:
     """Deterministic values for an arbitrary {name: shape} (sorted-key order), used for whole-decoder
     golden vectors.  BatchNorm running_var gets positive values, num_batches_tracked zeros."""

@@ -17,7 +17,8 @@ KEYS = ("sem_cls_logits", "center_normalized", "size_normalized", "angle_logits"
 
 
 def _dense_rpe_attention(q, k, v, xyz=None, ref_pts=None, ref_angle=None, tables=None, log_scale=512.0, max_value=4.0,
-                         impl=None, impl_bwd=None):
+                         impl=None, impl_bwd=None, dropout_p=0.0, dropout_seed=None):
+    assert dropout_p == 0.0          # eval-mode wiring test
     qh = q.permute(0, 2, 1, 3)
     kh, vh = k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)
     s = qh @ kh.transpose(-1, -2)

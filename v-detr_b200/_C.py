@@ -36,9 +36,11 @@ _SIGS = {
     "vdetr_pn2_group_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vdetr_xattn_fwd_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
     "vdetr_xattn_bias_save_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
-    "vdetr_xattn_fwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 10 + [c_void_p, c_size_t, c_int, c_void_p]),
-    "vdetr_xattn_bwd_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int]),
-    "vdetr_xattn_bwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 15 + [c_void_p, c_size_t, c_int, c_void_p]),
+    "vdetr_xattn_fwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 10 + [c_float, c_void_p] +
+                        [c_void_p, c_size_t, c_int, c_void_p]),
+    "vdetr_xattn_bwd_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape), c_int, c_int]),
+    "vdetr_xattn_bwd": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 11 + [c_float, c_void_p] + [c_void_p] * 4 +
+                        [c_void_p, c_size_t, c_int, c_void_p]),
     "vdetr_rpe_bias": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p]),
     "vdetr_launch_count": (ctypes.c_ulonglong, [c_int]),
     "vdetr_timing_enable": (c_int, [c_int]),
@@ -46,11 +48,13 @@ _SIGS = {
     "vdetr_layernorm_supported": (c_int, [c_int]),
     "vdetr_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdetr_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                    c_void_p]),
-    "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p]),
+    "vdetr_reduce_workspace_floats": (c_size_t, [c_int]),
+    "vdetr_colsum_workspace_floats": (c_size_t, [c_int]),
+    "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vdetr_bn_relu_supported": (c_int, [c_int]),
     "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float] + [c_void_p] * 7),
-    "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 4),
+    "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 5),
     "vdetr_debug_dt_clocks": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "vdetr_rpe_dtables_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape)]),
     "vdetr_rpe_dtables": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),

@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
         raise RuntimeError(f"nvcc failed on {failed}")
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcublas"])
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs)
     open(stamp, "w").write(dig)
     return LIB
 

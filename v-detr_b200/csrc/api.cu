@@ -8,7 +8,7 @@ struct TimingState {
   bool enabled = false;
   cudaEvent_t start[VDETR_T_COUNT][TIMING_RING];
   cudaEvent_t stop[VDETR_T_COUNT][TIMING_RING];
-  int n[VDETR_T_COUNT] = {0, 0, 0};
+  int n[VDETR_T_COUNT] = {0, 0, 0, 0};
   bool created = false;
 } g_timing;
 }  // namespace
@@ -48,7 +48,7 @@ int vdetr_timing_enable(int enable) {
   return 0;
 }
 
-int vdetr_timing_read(float* total_ms /*[3]*/, int* launches /*[3]*/) {
+int vdetr_timing_read(float* total_ms /*[4]*/, int* launches /*[4]*/) {
   for (int k = 0; k < VDETR_T_COUNT; ++k) {
     float sum = 0.f;
     for (int i = 0; i < g_timing.n[k]; ++i) {
@@ -89,7 +89,8 @@ size_t vdetr_xattn_bias_save_bytes(const VdetrXattnShape* s, int impl) {
 
 int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                     const float* ref_pts, const float* ref_angle, const float* tables, float* out, float* lse,
-                    float* bias_save, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+                    float* bias_save, float dropout_p, const uint64_t* dropout_seed, void* workspace, size_t workspace_bytes,
+                    int impl, void* stream) {
   int rc = vdetr_check_shape(s);
   if (rc) return rc;
   if (s->B == 0 || s->nQ == 0) return 0;
@@ -97,31 +98,40 @@ int vdetr_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, co
   if (!q || !k || !v || !out || !lse) return VDETR_ERR_BAD_ARG;
   if (s->has_bias && (!xyz || !ref_pts || !tables)) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1) return simt_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, st);
+  if (impl == 1) {
+    if (dropout_p > 0.f) return VDETR_ERR_UNSUPPORTED;      // the validation kernels implement no dropout
+    return simt_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, st);
+  }
   if (impl == 0)
-    return tc_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save, workspace, workspace_bytes, st);
+    return tc_xattn_fwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save, dropout_p,
+                        reinterpret_cast<const unsigned long long*>(dropout_seed), workspace, workspace_bytes, st);
   return VDETR_ERR_BAD_ARG;
 }
 
-size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl) {
+size_t vdetr_xattn_bwd_workspace_bytes(const VdetrXattnShape* s, int impl, int bias_is_saved) {
   if (vdetr_check_shape(s) != 0) return 0;
-  return impl == 0 ? tc_xattn_bwd_workspace(s) : 0;
+  return impl == 0 ? tc_xattn_bwd_workspace(s, bias_is_saved) : 0;
 }
 
 int vdetr_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                     const float* ref_pts, const float* ref_angle, const float* tables, const float* out,
-                    const float* lse, const float* dout, const float* bias_saved, float* dq, float* dk, float* dv,
-                    float* dtables, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+                    const float* lse, const float* dout, const float* bias_saved, float dropout_p,
+                    const uint64_t* dropout_seed, float* dq, float* dk, float* dv, float* dtables, void* workspace,
+                    size_t workspace_bytes, int impl, void* stream) {
   int rc = vdetr_check_shape(s);
   if (rc) return rc;
   if (s->B == 0 || s->nQ == 0 || s->nK == 0) return (s->nK == 0 && s->B && s->nQ) ? VDETR_ERR_BAD_ARG : 0;
   if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return VDETR_ERR_BAD_ARG;
   if (s->has_bias && (!xyz || !ref_pts || !tables || !dtables)) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1) return simt_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, dq, dk, dv, dtables, st);
+  if (impl == 1) {
+    if (dropout_p > 0.f) return VDETR_ERR_UNSUPPORTED;
+    return simt_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, dq, dk, dv, dtables, st);
+  }
   if (impl == 0)
-    return tc_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, bias_saved, dq, dk, dv, dtables,
-                        workspace, workspace_bytes, st);
+    return tc_xattn_bwd(s, q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, dout, bias_saved, dropout_p,
+                        reinterpret_cast<const unsigned long long*>(dropout_seed), dq, dk, dv, dtables, workspace,
+                        workspace_bytes, st);
   return VDETR_ERR_BAD_ARG;
 }
 

@@ -1,42 +1,48 @@
 // Training-mode BatchNorm1d + ReLU on token-major activations [tokens, C] (the Conv1d(k=1)-BN-ReLU stacks of the box
 // heads and of the query-position MLP: models/helpers.py:17-33, 74-141, evaluated token-major -- helpers.pointwise_tokens).
 //   stats   : per-channel sum and sum of squares of (x - pivot), pivot = row 0 (shifted sums: no cancellation when
-//             |mean| >> std); warps accumulate per-lane column sums over their rows, CTAs reduce in shared memory and
-//             add to global with one atomic per column
+//             |mean| >> std); warps accumulate per-lane column sums over their rows, CTAs reduce in shared memory, store
+//             their partial sums, and the last CTA to finish adds the partials in block order (det_reduce.cuh: no float
+//             atomics, so two identical calls give identical bits)
 //   apply   : y = relu((x - mean) * rstd * gamma + beta); block 0 also updates running_mean / running_var (unbiased)
 //   bwd sums: dbeta = sum g, dgamma = sum g * xhat with g = dy * [y > 0]  (the two column sums the input gradient needs)
 //   bwd dx  : dx = gamma * rstd * (g - dbeta / T - xhat * dgamma / T)
 // Stock PyTorch runs 3 kernels forward (statistics, transform, ReLU) and 3 backward; here the ReLU rides along.
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace {
 
 constexpr int BN_WARPS = 8;
 
-// column accumulation helper: every lane owns VEC float4 (columns i*128 + lane*4 .. +3)
-template <int VEC, typename F>
-__device__ __forceinline__ void reduce_columns_to_global(float4 (&a)[VEC], float4 (&b)[VEC], float* out_a, float* out_b, F) {
+// column accumulation helper: every lane owns VEC float4 (columns i*128 + lane*4 .. +3).  The CTA's sums of the two
+// quantities go to part[blockIdx.x][2 * C]; the last CTA writes the totals to out_a[C] / out_b[C].
+template <int VEC>
+__device__ __forceinline__ void reduce_columns_to_global(float4 (&a)[VEC], float4 (&b)[VEC], float* out_a, float* out_b, float* part,
+                                                         unsigned* ticket) {
   __shared__ float4 red[BN_WARPS][VEC * 32];
+  constexpr int C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) red[warp][i * 32 + lane] = pass == 0 ? a[i] : b[i];
     __syncthreads();
-    float* out = pass == 0 ? out_a : out_b;
-    for (int c = threadIdx.x; c < VEC * 128; c += BN_WARPS * 32) {
+    for (int c = threadIdx.x; c < C; c += BN_WARPS * 32) {
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < BN_WARPS; ++w) s += reinterpret_cast<const float*>(&red[w][0])[c];
-      atomicAdd(out + c, s);
+      part[(size_t)blockIdx.x * 2 * C + pass * C + c] = s;
     }
     __syncthreads();
   }
+  det_finish_columns<BN_WARPS * 32>(part, gridDim.x, 2 * C, ticket, out_a, out_b, C);
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(BN_WARPS * 32) bn_stats_kernel(const float4* __restrict__ x, int rows, float* __restrict__ sum,
-                                                                 float* __restrict__ sumsq) {
+                                                                 float* __restrict__ sumsq, float* __restrict__ part,
+                                                                 unsigned* __restrict__ ticket) {
   constexpr int C4 = VEC * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 s[VEC], q[VEC], pv[VEC];
@@ -55,7 +61,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_stats_kernel(const float4* _
       q[i].x += v.x * v.x; q[i].y += v.y * v.y; q[i].z += v.z * v.z; q[i].w += v.w * v.w;
     }
   }
-  reduce_columns_to_global<VEC>(s, q, sum, sumsq, 0);
+  reduce_columns_to_global<VEC>(s, q, sum, sumsq, part, ticket);
 }
 
 template <int VEC>
@@ -110,7 +116,8 @@ template <int VEC>
 __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
                                                                     const float4* __restrict__ x, int rows,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                    float* __restrict__ part, unsigned* __restrict__ ticket) {
   constexpr int C4 = VEC * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 ag[VEC], ab[VEC], mu[VEC], rs[VEC];
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4
       ag[i].z += gz * (xv.z - mu[i].z) * rs[i].z; ag[i].w += gw * (xv.w - mu[i].w) * rs[i].w;
     }
   }
-  reduce_columns_to_global<VEC>(ag, ab, dgamma, dbeta, 0);
+  reduce_columns_to_global<VEC>(ag, ab, dgamma, dbeta, part, ticket);
 }
 
 template <int VEC>
@@ -174,13 +181,19 @@ inline int bn_grid(int rows, int rows_per_warp) {
   int g = (rows + BN_WARPS * rows_per_warp - 1) / (BN_WARPS * rows_per_warp);
   return g < 1 ? 1 : (g > vdetr_num_sms() * 4 ? vdetr_num_sms() * 4 : g);
 }
+inline int bn_red_grid(int rows) {                 // kernels that end in a cross-CTA reduction: at most 64 partial sums
+  const int g = bn_grid(rows, 4);
+  return g > VDETR_RED_MAX_BLOCKS ? VDETR_RED_MAX_BLOCKS : g;
+}
 
 template <int VEC>
 int fwd_t(const float* x, const float* gamma, const float* beta, int rows, float eps, float momentum, float* y, float* mean,
           float* rstd, float* running_mean, float* running_var, float* ws, cudaStream_t st) {
   const int C = VEC * 128;
-  VDETR_CUDA_TRY(cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(float), st));
-  bn_stats_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws, ws + C);
+  float* part = ws + 2 * C;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * C);
+  VDETR_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+  bn_stats_kernel<VEC><<<bn_red_grid(rows), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws, ws + C, part, ticket);
   VDETR_LAUNCH_CHECK();
   bn_apply_relu_kernel<VEC><<<bn_grid(rows, 2), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(x), rows, ws, ws + C, reinterpret_cast<const float4*>(gamma),
@@ -190,10 +203,15 @@ int fwd_t(const float* x, const float* gamma, const float* beta, int rows, float
 }
 template <int VEC>
 int bwd_t(const float* dy, const float* y, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
-          float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
-  bn_bwd_sums_kernel<VEC><<<bn_grid(rows, 4), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy),
-                                                                     reinterpret_cast<const float4*>(y),
-                                                                     reinterpret_cast<const float4*>(x), rows, mean, rstd, dgamma, dbeta);
+          float* dx, float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
+  const int C = VEC * 128;
+  float* part = ws + 2 * C;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * C);
+  VDETR_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+  bn_bwd_sums_kernel<VEC><<<bn_red_grid(rows), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy),
+                                                                      reinterpret_cast<const float4*>(y),
+                                                                      reinterpret_cast<const float4*>(x), rows, mean, rstd, dgamma, dbeta,
+                                                                      part, ticket);
   VDETR_LAUNCH_CHECK();
   bn_bwd_dx_kernel<VEC><<<bn_grid(rows, 2), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
@@ -207,6 +225,8 @@ int bwd_t(const float* dy, const float* y, const float* x, const float* mean, co
 extern "C" {
 
 int vdetr_bn_relu_supported(int cols) { return cols == 128 || cols == 256 || cols == 384 || cols == 512; }
+
+size_t vdetr_reduce_workspace_floats(int cols) { return cols > 0 ? vdetr_reduce_ws_floats(cols) : 0; }
 
 int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float momentum,
                             float* y, float* mean, float* rstd, float* running_mean, float* running_var, float* workspace,
@@ -223,17 +243,16 @@ int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* bet
 }
 
 int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
-                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, void* stream) {
+                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, float* workspace,
+                            void* stream) {
   if (rows < 1 || !vdetr_bn_relu_supported(cols)) return VDETR_ERR_UNSUPPORTED;
-  if (!dy || !y || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta) return VDETR_ERR_BAD_ARG;
+  if (!dy || !y || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || !workspace) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  VDETR_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)cols * sizeof(float), st));
-  VDETR_CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)cols * sizeof(float), st));
   switch (cols / 128) {
-    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
-    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
-    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
-    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
   }
 }
 

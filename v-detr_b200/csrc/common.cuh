@@ -33,9 +33,9 @@ static inline int vdetr_num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Optional kernel timing (bench.py): CUDA events recorded on the launch stream around the three dominant
+// Optional kernel timing (bench.py): CUDA events recorded on the launch stream around the dominant
 // kernels.  Disabled by default; enabling costs two cudaEventRecord per launch.
-enum VdetrTimedKernel { VDETR_T_FWD = 0, VDETR_T_BWD = 1, VDETR_T_DTABLES = 2, VDETR_T_COUNT = 3 };
+enum VdetrTimedKernel { VDETR_T_FWD = 0, VDETR_T_BWD = 1, VDETR_T_DTABLES = 2, VDETR_T_BWD2 = 3, VDETR_T_COUNT = 4 };
 struct VdetrTimingScope {
   int kind;
   cudaStream_t st;

@@ -3,10 +3,11 @@
 // 586-606, 129).  One warp per row, the whole row in registers (cols = 128 * VEC, VEC float4 per lane).
 //   forward : y = (x - mean) * rstd * gamma + beta, mean / rstd saved
 //   backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; dgamma / dbeta are accumulated per
-//             lane over the rows a warp walks, reduced across the CTA in shared memory and added to the output with one
-//             atomic per column per CTA (the 34 LayerNorm backward calls of a decoder step took 3.9 ms with the stock
-//             kernels, whose column reduction is a separate pass).
+//             lane over the rows a warp walks, reduced across the CTA in shared memory, stored as per-CTA partial sums
+//             and added up in block order by the last CTA (det_reduce.cuh; the 34 LayerNorm backward calls of a decoder
+//             step took 3.9 ms with the stock kernels, whose column reduction is a separate pass).
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace {
 
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float4* __r
                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                const float4* __restrict__ gamma, int rows,
                                                                float4* __restrict__ dx, float* __restrict__ dgamma,
-                                                               float* __restrict__ dbeta) {
+                                                               float* __restrict__ dbeta, float* __restrict__ part,
+                                                               unsigned* __restrict__ ticket) {
   constexpr int C4 = VEC * 32;
   __shared__ float4 red[LN_WARPS][C4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -90,21 +92,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float4* __r
           make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2), rs * (g[i].z - m1 - xh[i].z * m2),
                       rs * (g[i].w - m1 - xh[i].w * m2));
   }
-  // column sums of this CTA: warps -> shared memory -> one atomic per column
+  // column sums of this CTA: warps -> shared memory -> per-CTA partial sums -> last CTA adds them in block order
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) red[warp][i * 32 + lane] = pass == 0 ? ag[i] : ab[i];
     __syncthreads();
-    float* out = pass == 0 ? dgamma : dbeta;
     for (int c = threadIdx.x; c < C4 * 4; c += LN_WARPS * 32) {
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < LN_WARPS; ++w) s += reinterpret_cast<const float*>(&red[w][0])[c];
-      atomicAdd(out + c, s);
+      part[(size_t)blockIdx.x * 2 * (C4 * 4) + pass * (C4 * 4) + c] = s;
     }
     __syncthreads();
   }
+  det_finish_columns<LN_WARPS * 32>(part, gridDim.x, 2 * C4 * 4, ticket, dgamma, dbeta, C4 * 4);
 }
 
 template <int VEC>
@@ -119,13 +121,17 @@ int launch_fwd(const float* x, const float* gamma, const float* beta, int rows, 
 }
 template <int VEC>
 int launch_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows, float* dx,
-               float* dgamma, float* dbeta, cudaStream_t st) {
-  // enough rows per warp to amortise the column reduction, enough CTAs to fill the machine
+               float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
+  // enough rows per warp to amortise the column reduction; at most 64 CTAs (= partial sums of the final reduction)
+  constexpr int C = VEC * 128;
   int grid = (rows + LN_WARPS * 4 - 1) / (LN_WARPS * 4);
-  grid = max(1, min(grid, vdetr_num_sms() * 4));
+  grid = max(1, min(grid, VDETR_RED_MAX_BLOCKS));
+  float* part = ws + 2 * C;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * C);
+  VDETR_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   ln_bwd_kernel<VEC><<<grid, LN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), mean,
                                                     rstd, reinterpret_cast<const float4*>(gamma), rows,
-                                                    reinterpret_cast<float4*>(dx), dgamma, dbeta);
+                                                    reinterpret_cast<float4*>(dx), dgamma, dbeta, part, ticket);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
@@ -151,19 +157,21 @@ int vdetr_layernorm_fwd(const float* x, const float* gamma, const float* beta, i
 }
 
 int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
-                        int cols, float* dx, float* dgamma, float* dbeta, void* stream) {
+                        int cols, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream) {
   if (rows < 0 || !vdetr_layernorm_supported(cols)) return VDETR_ERR_UNSUPPORTED;
   if (!dgamma || !dbeta) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  VDETR_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)cols * sizeof(float), st));
-  VDETR_CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)cols * sizeof(float), st));
-  if (rows == 0) return 0;
-  if (!dy || !x || !mean || !rstd || !gamma || !dx) return VDETR_ERR_BAD_ARG;
+  if (rows == 0) {
+    VDETR_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)cols * sizeof(float), st));
+    VDETR_CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)cols * sizeof(float), st));
+    return 0;
+  }
+  if (!dy || !x || !mean || !rstd || !gamma || !dx || !workspace) return VDETR_ERR_BAD_ARG;
   switch (cols / 128) {
-    case 1: return launch_bwd<1>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
-    case 2: return launch_bwd<2>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
-    case 3: return launch_bwd<3>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
-    default: return launch_bwd<4>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, st);
+    case 1: return launch_bwd<1>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    case 2: return launch_bwd<2>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    case 3: return launch_bwd<3>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    default: return launch_bwd<4>(dy, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
   }
 }
 
@@ -173,31 +181,56 @@ int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, cons
 // Column sums of a dense [rows, cols] f32 matrix: the bias gradient of every token-major Linear / Conv1d(k=1)
 // layer of the decoder (155 per step; the stock reduction kernel is latency bound on these 8 MB inputs).
 namespace {
-constexpr int CS_ROWS = 64;       // rows per CTA
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
+// grid = (row slices <= 64, column tiles of blockDim.x); a CTA sums its row slice for its columns, stores the partial sums,
+// and the last CTA of the column tile (one ticket per tile) adds the slices in order: deterministic, no float atomics.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ out,
+                                                     float* __restrict__ part, unsigned* __restrict__ tickets) {
+  __shared__ bool s_last;
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int r0 = blockIdx.x * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = r0;
-  for (; r + 3 < r1; r += 4) {
-    s0 += x[(size_t)r * cols + c]; s1 += x[(size_t)(r + 1) * cols + c];
-    s2 += x[(size_t)(r + 2) * cols + c]; s3 += x[(size_t)(r + 3) * cols + c];
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  if (c < cols) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+      s0 += x[(size_t)r * cols + c]; s1 += x[(size_t)(r + 1) * cols + c];
+      s2 += x[(size_t)(r + 2) * cols + c]; s3 += x[(size_t)(r + 3) * cols + c];
+    }
+    for (; r < r1; ++r) s0 += x[(size_t)r * cols + c];
+    part[(size_t)blockIdx.x * cols + c] = (s0 + s1) + (s2 + s3);
   }
-  for (; r < r1; ++r) s0 += x[(size_t)r * cols + c];
-  atomicAdd(out + c, (s0 + s1) + (s2 + s3));
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(tickets + blockIdx.y, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || c >= cols) return;
+  __threadfence();
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = 0; b < (int)gridDim.x; ++b) s[b & 3] += __ldcg(part + (size_t)b * cols + c);
+  out[c] = (s[0] + s[1]) + (s[2] + s[3]);
 }
 }  // namespace
 
-extern "C" int vdetr_colsum(const float* x, int rows, int cols, float* out, void* stream) {
+// workspace: vdetr_colsum_workspace_floats(cols) floats
+extern "C" size_t vdetr_colsum_workspace_floats(int cols) { return cols > 0 ? (size_t)VDETR_RED_MAX_BLOCKS * cols + 64 : 0; }
+
+extern "C" int vdetr_colsum(const float* x, int rows, int cols, float* out, float* workspace, void* stream) {
   if (rows < 0 || cols < 1) return VDETR_ERR_BAD_ARG;
-  if (!out || (rows > 0 && !x)) return VDETR_ERR_BAD_ARG;
+  if (!out || (rows > 0 && (!x || !workspace))) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  VDETR_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
-  if (rows == 0) return 0;
+  if (rows == 0) {
+    VDETR_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
+    return 0;
+  }
   const int threads = cols >= 256 ? 256 : ((cols + 31) / 32) * 32;
-  dim3 grid((rows + CS_ROWS - 1) / CS_ROWS, (cols + threads - 1) / threads);
-  colsum_kernel<<<grid, threads, 0, st>>>(x, rows, cols, out);
+  const int tiles = (cols + threads - 1) / threads;
+  if (tiles > 64) return VDETR_ERR_UNSUPPORTED;
+  int slices = (rows + 63) / 64;
+  slices = slices > VDETR_RED_MAX_BLOCKS ? VDETR_RED_MAX_BLOCKS : slices;
+  unsigned* tickets = reinterpret_cast<unsigned*>(workspace + (size_t)VDETR_RED_MAX_BLOCKS * cols);
+  VDETR_CUDA_TRY(cudaMemsetAsync(tickets, 0, 64 * sizeof(unsigned), st));
+  dim3 grid(slices, tiles);
+  colsum_kernel<<<grid, threads, 0, st>>>(x, rows, cols, out, workspace, tickets);
   VDETR_LAUNCH_CHECK();
   return 0;
 }

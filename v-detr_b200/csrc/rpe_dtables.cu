@@ -53,6 +53,8 @@ struct Params {
   const unsigned* absmax_bits;            // -> scale
   float* priv;                            // [gridDim.x][8][P3^3][4]
   int4 cost;                              // per-segment cost model of the accumulation phase (see seg_cost)
+  int only_slow;                          // dt3 as the companion of dt4: only queries whose box is not axis aligned
+  const int* slow_count;                  // [1] number of such queries in the whole call (only_slow: 0 -> nothing to do)
   unsigned long long* phase_clocks;       // [8] optional (developer): cycles per phase summed over CTAs, else null
 };
 
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
   int* costp = S.offs + nbins + 1;  // [nbins+1] exclusive scan of the per-cell cost estimate
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (P.only_slow && *P.slow_count == 0) return;
   long long t_prev = clock64();
   auto tick = [&](int phase) {      // call right after a __syncthreads(): time since the previous tick -> phase
     if (P.phase_clocks && tid == 0) {
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
         const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
         hi = __ldg(g); lo = __ldg(g + 1);
         slow = __float_as_int(hi.w) == 0;
+        if (P.only_slow && !slow) q = -1;                    // axis-aligned boxes are the dt4 kernel's
       }
       S.sgeo[tid * 2] = hi; S.sgeo[tid * 2 + 1] = lo;
       S.sq[tid] = q; s_slow[tid] = slow;
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
     bool any_slow = false;
 #pragma unroll
     for (int ql = 0; ql < QB; ++ql) any_slow = any_slow || (s_slow[ql] != 0 && S.sq[ql] >= 0);
+    if (P.only_slow && !any_slow) continue;                  // (block-uniform: read from shared memory after the barrier)
 
     // ---- phase A: records.  A thread takes 4 consecutive keys of one query at a time so that the scaled-fp16 dS of
     // the 4 heads arrives as four 8-byte loads (64 loads of 2 bytes per thread left the phase latency bound).
@@ -522,6 +527,375 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
   }
 }
 
+
+}  // namespace dt3
+
+// =====================================================================================================================
+// dt4: the same adjoint for AXIS-ALIGNED boxes (every query of the ScanNet configuration: num_angle_bin = 1) with the
+// accumulation done by warp-level tensor-core MMAs instead of per-lane register accumulators + shuffle transposes.
+//
+//   unit      = (scene, 12 Morton-adjacent queries, 512 Morton-adjacent keys) = 6144 pairs; phase A as in dt3.
+//   round     = a PAIR of vertices that differ only in the x sign (0,3) (1,2) (4,7) (5,6): they share the y and z
+//               transforms, hence the (z, y) part of their table cell and 4 of the 6 weight factors.  ONE counting sort
+//               per round, by (z, y, x+ cell, min(x+ cell - x- cell, 3)): vertex A (x+) is perfectly sorted and vertex B
+//               (x-) is sorted inside A's segments.
+//   accumulate: a warp walks its share of the sorted list 32 pairs per step; lane = pair computes the 8 corner weights of
+//               A and of B (fp32, rounded once to fp16) and leaves them with the 4 heads' dS in a per-warp staging
+//               tile; per 16 pairs ldmatrix builds the fragments of ONE mma.sync.m16n8k16:
+//                   D[16 x 8] += W^T[16 x 16 pairs] * dS[16 pairs x 8]     rows 0-7 = A's corners, 8-15 = B's corners,
+//                                                                          columns 0-3 = heads
+//               D stays in registers while the cell of the vertex does not change; a cell change costs one vector RED
+//               per lane (no transposition), a block that straddles cells is handled by masking the fragment rows.
+// Queries whose box is not axis aligned are skipped here (zero weights) and handled by dt3 with only_slow = 1.
+namespace dt4 {
+
+using dt3::axis_rec;
+using dt3::FULL;
+using dt3::Params;
+
+constexpr int QB = 12, KC = 512, NP = QB * KC;          // 6144 pairs per unit
+constexpr int THREADS = 512, WARPS = 16, ITEMS = NP / THREADS;
+static_assert(NP % THREADS == 0 && (NP / 4) % THREADS == 0 && KC == THREADS, "unit shape");
+constexpr int XI = 12;                                   // x index values of a sort bin: cells 0..10, 11 = vertex A outside the table
+constexpr int SORT_PAD = 64;                             // dummy entries behind the sorted list (whole steps + the prefetch)
+constexpr int STAGE_BYTES = 3 * 32 * 16;                 // per warp: A weights, B weights, dS (16 B per pair each)
+
+__host__ __device__ inline int nbins_of(int n) { return (n + 1) * (n + 1) * XI * 4; }
+__host__ __device__ inline size_t region_bytes(int n) {
+  const size_t r = ((size_t)nbins_of(n) + 1 + 3) / 4 * 16;
+  return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
+}
+__host__ __device__ inline size_t smem_bytes(int n) {
+  return (size_t)(NP + 2) * 24 + (size_t)(NP + SORT_PAD) * 2 + region_bytes(n) + WARPS * STAGE_BYTES + QB * 2 * 16 + 64 * 4 + 64;
+}
+
+// run structure of a warp's 32 bins (see dt3::run_pack); bins need 13 bits here:
+//   bits [0,13) bin + 1 (0 = pair outside the table)   [13,18) rank inside the run   [18,24) run length
+__device__ __forceinline__ unsigned run_pack13(int bin, int lane) {
+  const int prev = __shfl_up_sync(FULL, bin, 1);
+  const bool head = lane == 0 || bin != prev;
+  const unsigned heads = __ballot_sync(FULL, head);
+  const unsigned below = heads & (FULL >> (31 - lane));
+  const int hl = 31 - __clz(below);
+  const unsigned above = (hl == 31) ? 0u : (heads & ~((2u << hl) - 1u));
+  const int end = above ? (__ffs(above) - 1) : 32;
+  return (unsigned)(bin + 1) | ((unsigned)(lane - hl) << 13) | ((unsigned)(end - hl) << 18);
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(x), "f"(y) : "memory");
+}
+// 16-bit lanes of a fragment register kept where the membership bit of their pair is set (bit 0 -> low half, bit 1 -> high)
+__device__ __forceinline__ uint32_t keep_halves(uint32_t v, unsigned bits) {
+  const uint32_t m = ((0u - (bits & 1u)) & 0x0000FFFFu) | ((0u - ((bits >> 1) & 1u)) & 0xFFFF0000u);
+  return v & m;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) rpe_dtables_mma_kernel(const Params P) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  // [NP + 2] records / dS (entry NP = dummy; NP + 2 keeps every later region 16-byte aligned), [NP + SORT_PAD] sorted ids
+  static_assert(((NP + 2) * 24) % 16 == 0 && ((NP + SORT_PAD) * 2) % 16 == 0, "16-byte alignment of the shared-memory regions");
+  uint4* s_recs = reinterpret_cast<uint4*>(sm);
+  uint2* s_dsv = reinterpret_cast<uint2*>(sm + (size_t)(NP + 2) * 16);
+  uint16_t* s_sorted = reinterpret_cast<uint16_t*>(sm + (size_t)(NP + 2) * 24);
+  uint8_t* region = sm + (size_t)(NP + 2) * 24 + (size_t)(NP + SORT_PAD) * 2;
+  int* s_hist = reinterpret_cast<int*>(region);                                     // [nbins + 1] counts -> cursors
+  float4* s_xyz = reinterpret_cast<float4*>(region);                                // [KC] phase A only (aliases hist)
+  uint8_t* s_stage = region + region_bytes(P.n);                                    // [WARPS][STAGE_BYTES]
+  float4* s_geo = reinterpret_cast<float4*>(s_stage + WARPS * STAGE_BYTES);         // [QB][2]
+  int* s_q = reinterpret_cast<int*>(s_geo + QB * 2);                                // [QB] query index or -1 (also -1: not axis aligned)
+  int* s_misc = s_q + 16;                                                           // [0] sorted count, [2..2+WARPS) scan scratch
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbins = nbins_of(P.n);
+  const int R = P.R;
+  const int cells_pad = P.P3 * P.P3 * P.P3;
+  float* my_priv = P.priv + (size_t)blockIdx.x * 8 * cells_pad * 4;
+  long long t_prev = clock64();
+  auto tick = [&](int phase) {
+    if (P.phase_clocks && tid == 0) {
+      const long long t = clock64();
+      atomicAdd(P.phase_clocks + phase, (unsigned long long)(t - t_prev));
+      t_prev = t;
+    }
+  };
+  // fragment roles of this lane in the accumulate phase
+  const int fg = lane >> 2, ft = lane & 3;                        // D row (corner) / column pair
+  const int fcz = fg >> 2, fcy = (fg >> 1) & 1, fcx = fg & 1;
+  uint8_t* my_stage = s_stage + warp * STAGE_BYTES;
+  const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(my_stage);
+  // ldmatrix row addresses: A fragment tiles (WA k0-7, WB k0-7, WA k8-15, WB k8-15), B fragment tiles (dS k0-7, dS k8-15)
+  const uint32_t a_row = stage_u32 + ((lane >> 3) & 1) * 512 + (((lane >> 4) & 1) * 8 + (lane & 7)) * 16;
+  const uint32_t b_row = stage_u32 + 1024 + (((lane >> 3) & 1) * 8 + (lane & 7)) * 16;
+
+  if (tid == 0) {                                                 // dummy record: contributes nothing, x cells invalid
+    s_recs[NP] = make_uint4(0u, 0u, 0u, 0x000000FFu);
+    s_dsv[NP] = make_uint2(0u, 0u);
+  }
+
+  for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+    int r = u;
+    const int kc = r % P.kchunks; r /= P.kchunks;
+    const int qb = r % P.qblocks;
+    const int b = r / P.qblocks;
+    const int q0 = qb * QB, k0 = kc * KC;
+
+    __syncthreads();                      // previous unit completely done with shared memory
+    if (tid < QB) {
+      const int qi = q0 + tid;
+      int q = -1;
+      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+      if (qi < P.nQ) {
+        q = __ldg(P.qperm + (size_t)b * P.nQ + qi);
+        const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
+        hi = __ldg(g); lo = __ldg(g + 1);
+        if (__float_as_int(hi.w) == 0) q = -1;                    // not axis aligned: handled by the dt3 kernel
+      }
+      s_geo[tid * 2] = hi; s_geo[tid * 2 + 1] = lo;
+      s_q[tid] = q;
+    }
+    for (int i = tid; i < KC; i += THREADS) {
+      float4 kx = make_float4(1e9f, 1e9f, 1e9f, 0.f);
+      if (k0 + i < P.nK) kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + i);
+      s_xyz[i] = kx;
+    }
+    __syncthreads();
+
+    // ---- phase A: records (6 axis transforms per pair) + the 4 heads' scaled fp16 dS; 4 consecutive keys per thread
+    {
+      constexpr int KG = KC / 4, GI = NP / 4 / THREADS;
+#pragma unroll 1
+      for (int gi = 0; gi < GI; ++gi) {
+        const int g = gi * THREADS + tid, ql = g / KG, kl0 = (g % KG) * 4;
+        const int q = s_q[ql];
+        uint2 hd[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) hd[h] = make_uint2(0u, 0u);
+        const bool any = q >= 0 && k0 + kl0 < P.nK;
+        if (any) {
+          const __half* dp = P.dsb + ((size_t)b * P.nQp + q) * 4 * P.nKp + k0 + kl0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) hd[h] = __ldg(reinterpret_cast<const uint2*>(dp + (size_t)h * P.nKp));
+        }
+        const float4 hi = s_geo[ql * 2], lo = s_geo[ql * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kl = kl0 + j, p = ql * KC + kl;
+          uint4 rec = make_uint4(0u, 0u, 0u, 0x00FFFFFFu);
+          uint2 dv = make_uint2(0u, 0u);
+          if (any && k0 + kl < P.nK) {
+            const int sh = 16 * (j & 1);
+            const unsigned w0 = (j < 2) ? hd[0].x : hd[0].y, w1 = (j < 2) ? hd[1].x : hd[1].y;
+            const unsigned w2 = (j < 2) ? hd[2].x : hd[2].y, w3 = (j < 2) ? hd[3].x : hd[3].y;
+            dv = make_uint2(((w0 >> sh) & 0xFFFFu) | (((w1 >> sh) & 0xFFFFu) << 16), ((w2 >> sh) & 0xFFFFu) | (((w3 >> sh) & 0xFFFFu) << 16));
+            const float4 kx = s_xyz[kl];
+            unsigned nxp, nxm, nyp, nym, nzp, nzm, fxp, fxm, fyp, fym, fzp, fzm;
+            axis_rec(hi.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxp, fxp);
+            axis_rec(lo.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxm, fxm);
+            axis_rec(hi.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nyp, fyp);
+            axis_rec(lo.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nym, fym);
+            axis_rec(hi.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzp, fzp);
+            axis_rec(lo.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzm, fzm);
+            rec.x = fxp | (fxm << 16); rec.y = fyp | (fym << 16); rec.z = fzp | (fzm << 16);
+            rec.w = nxp | (nxm << 4) | (nyp << 8) | (nym << 12) | (nzp << 16) | (nzm << 20);
+          }
+          s_recs[p] = rec;
+          s_dsv[p] = dv;
+        }
+      }
+    }
+    __syncthreads();                      // records complete; the xyz staging area becomes the histogram
+    tick(0);
+
+    for (int round = 0; round < 4; ++round) {
+      // round -> (y slot, z slot) and the two vertices: A has x+, B has x-  (sign table in dt3::vertex_slots)
+      const int ys = round & 1, zs = (round < 2) ? 1 : 0;
+      const int vertA = (round < 2 ? 0 : 4) + ys, vertB = (round < 2 ? 3 : 7) - ys;
+      const int shy = 16 * ys, shz = 16 * zs;
+      const int nby = 8 + 4 * ys, nbz = 16 + 4 * zs;
+
+      for (int i = tid; i <= nbins; i += THREADS) s_hist[i] = 0;
+      __syncthreads();
+      tick(1);
+
+      // ---- B1: histogram of the sort bins
+      unsigned myrun[ITEMS];
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const unsigned w = s_recs[it * THREADS + tid].w;
+        const int xa = w & 15, xb = (w >> 4) & 15, ny = (w >> nby) & 15, nz = (w >> nbz) & 15;
+        const bool a_ok = xa != 15, b_ok = xb != 15;
+        int bin = -1;
+        if (max(ny, nz) != 15 && (a_ok || b_ok)) {
+          const int xi = a_ok ? xa : XI - 1;
+          const int d = (a_ok && b_ok) ? min(max(xa - xb, 0), 3) : 0;
+          bin = (((nz * R + ny) * XI + xi) << 2) + d;
+        }
+        const unsigned rp = run_pack13(bin, lane);
+        myrun[it] = rp;
+        if ((rp & 0x3E000u) == 0u && bin >= 0) atomicAdd(s_hist + bin, (int)(rp >> 18));        // run head
+      }
+      __syncthreads();
+      tick(2);
+
+      // ---- B2: exclusive scan of the histogram, in place (counts -> scatter cursors)
+      {
+        const int per = (nbins + THREADS - 1) / THREADS;
+        const int lo = tid * per, hi = min(nbins, lo + per);
+        int mine = 0;
+        for (int i = lo; i < hi; ++i) mine += s_hist[i];
+        int x = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(FULL, x, o);
+          if (lane >= o) x += y;
+        }
+        if (lane == 31) s_misc[2 + warp] = x;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_misc[2 + w];
+        int run = wbase + x - mine;
+        for (int i = lo; i < hi; ++i) {
+          const int c = s_hist[i];
+          s_hist[i] = run;
+          run += c;
+        }
+        if (tid == THREADS - 1) s_misc[0] = run;             // number of sorted pairs
+      }
+      __syncthreads();
+      tick(3);
+
+      // ---- B3: counting-sort scatter; dummy entries behind the list (whole 32-pair steps + the prefetch of the walk)
+      const int nsorted = s_misc[0];
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const unsigned rp = myrun[it];
+        const int bin = (int)(rp & 0x1FFFu) - 1, rank = (int)((rp >> 13) & 31u);
+        int base = 0;
+        if (rank == 0 && bin >= 0) base = atomicAdd(s_hist + bin, (int)(rp >> 18));
+        base = __shfl_sync(FULL, base, lane - rank);
+        if (bin >= 0) s_sorted[base + rank] = (uint16_t)(it * THREADS + tid);
+      }
+      if (tid < SORT_PAD) s_sorted[nsorted + tid] = (uint16_t)NP;
+      __syncthreads();
+      tick(4);
+
+      // ---- B4: accumulate.  Warp w owns the steps [s0, s1) of 32 sorted pairs.
+      {
+        const int steps = (nsorted + 31) >> 5;
+        const int s0 = (steps * warp) / WARPS, s1 = (steps * (warp + 1)) / WARPS;
+        float* tabA = my_priv + (size_t)vertA * cells_pad * 4;
+        float* tabB = my_priv + (size_t)vertB * cells_pad * 4;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};                 // d[0..1]: A's corner fg, heads 2ft, 2ft+1; d[2..3]: B's
+        unsigned curA = 0xFFFFu, curB = 0xFFFFu;           // cell (nz << 8 | ny << 4 | nx) being accumulated; 0xFFFF = none
+
+        auto flush = [&](unsigned key, float* tab, float& v0, float& v1) {
+          const int nx = key & 15, ny = (key >> 4) & 15, nz = (key >> 8) & 15;
+          if (key != 0xFFFFu && nx <= P.n && ft < 2 && (v0 != 0.f || v1 != 0.f))
+            red_add_v2(tab + ((((nz + fcz) * P.P3 + (ny + fcy)) * P.P3 + (nx + fcx)) << 2) + 2 * ft, v0, v1);
+          v0 = 0.f; v1 = 0.f;
+        };
+
+        const unsigned sely = ys ? 0x7432u : 0x7410u, selz = zs ? 0x7432u : 0x7410u;
+        const uint16_t* sp = s_sorted + s0 * 32 + lane;
+        unsigned ent_n = *sp;
+        uint4 rec_n = s_recs[ent_n];
+        uint2 dv_n = s_dsv[ent_n];
+        for (int st = s0; st < s1; ++st) {
+          const uint4 rec = rec_n;
+          const uint2 dv = dv_n;
+          sp += 32;
+          ent_n = *sp;
+          rec_n = s_recs[ent_n];
+          dv_n = s_dsv[ent_n];
+
+          const unsigned xa = rec.w & 15u, xb = (rec.w >> 4) & 15u;
+          const unsigned zy = (((rec.w >> nbz) & 15u) << 8) | (((rec.w >> nby) & 15u) << 4);
+          const unsigned keyA = zy | (xa == 15u ? 11u : xa), keyB = zy | (xb == 15u ? 11u : xb);
+          // fractions u / 65536 without I2F: bytes (u.lo, u.hi, 0x00, 0x4B) = 2^23 + u ;  (2^23 + u) * 2^-16 - 128
+          const float fz = fmaf(__uint_as_float(__byte_perm(rec.z, 0x4B000000u, selz)), 0x1p-16f, -128.f);
+          const float fy = fmaf(__uint_as_float(__byte_perm(rec.y, 0x4B000000u, sely)), 0x1p-16f, -128.f);
+          const float fa = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, 0x7410u)), 0x1p-16f, -128.f);
+          const float fb = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, 0x7432u)), 0x1p-16f, -128.f);
+          {
+            const float2 wy = make_float2(1.f - fy, fy);
+            const float2 z0 = dt3::fmul2(1.f - fz, wy), z1 = dt3::fmul2(fz, wy);       // (z0y0, z0y1) (z1y0, z1y1)
+            const float2 wa = xa == 15u ? make_float2(0.f, 0.f) : make_float2(1.f - fa, fa);
+            const float2 wb = xb == 15u ? make_float2(0.f, 0.f) : make_float2(1.f - fb, fb);
+            // corner index = cz * 4 + cy * 2 + cx  -> halves 0..7 of the pair's row
+            const float2 a01 = dt3::fmul2(z0.x, wa), a23 = dt3::fmul2(z0.y, wa), a45 = dt3::fmul2(z1.x, wa), a67 = dt3::fmul2(z1.y, wa);
+            const float2 b01 = dt3::fmul2(z0.x, wb), b23 = dt3::fmul2(z0.y, wb), b45 = dt3::fmul2(z1.x, wb), b67 = dt3::fmul2(z1.y, wb);
+            __syncwarp();                                 // the previous step's ldmatrix reads are complete
+            uint4* stg = reinterpret_cast<uint4*>(my_stage);
+            stg[lane] = make_uint4(tc::pack_f16x2(a01.x, a01.y), tc::pack_f16x2(a23.x, a23.y), tc::pack_f16x2(a45.x, a45.y),
+                                   tc::pack_f16x2(a67.x, a67.y));
+            stg[32 + lane] = make_uint4(tc::pack_f16x2(b01.x, b01.y), tc::pack_f16x2(b23.x, b23.y), tc::pack_f16x2(b45.x, b45.y),
+                                        tc::pack_f16x2(b67.x, b67.y));
+            stg[64 + lane] = make_uint4(dv.x, dv.y, 0u, 0u);
+            __syncwarp();
+          }
+          // uniformity of the two 16-pair blocks of this step, per vertex
+          const unsigned refA = __shfl_sync(FULL, keyA, lane & 16), refB = __shfl_sync(FULL, keyB, lane & 16);
+          const unsigned eqA = __ballot_sync(FULL, keyA == refA), eqB = __ballot_sync(FULL, keyB == refB);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t a0, a1, a2, a3, b0, b1;
+            ldmatrix_x4_trans(a_row + h * 256, a0, a1, a2, a3);
+            ldmatrix_x2_trans(b_row + h * 256, b0, b1);
+            const bool uniA = ((eqA >> (16 * h)) & 0xFFFFu) == 0xFFFFu, uniB = ((eqB >> (16 * h)) & 0xFFFFu) == 0xFFFFu;
+            if (uniA && uniB) {
+              const unsigned kA = __shfl_sync(FULL, keyA, 16 * h), kB = __shfl_sync(FULL, keyB, 16 * h);
+              if (kA != curA) { flush(curA, tabA, d[0], d[1]); curA = kA; }
+              if (kB != curB) { flush(curB, tabB, d[2], d[3]); curB = kB; }
+              mma_16816(d, a0, a1, a2, a3, b0, b1);
+              continue;
+            }
+            // a block that straddles cells: one masked MMA per distinct cell and vertex
+#pragma unroll 1
+            for (int v = 0; v < 2; ++v) {
+              const unsigned key = v ? keyB : keyA;
+              unsigned todo = 0xFFFFu << (16 * h);
+              while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const unsigned ksel = __shfl_sync(FULL, key, leader);
+                const unsigned grp = __ballot_sync(FULL, key == ksel) & (0xFFFFu << (16 * h));
+                todo &= ~grp;
+                const unsigned bits = (grp >> (16 * h)) >> (2 * ft);          // membership of pairs 2ft, 2ft+1 (bits 0,1), 2ft+8, 2ft+9 (bits 8,9)
+                if (v == 0) {
+                  if (ksel != curA) { flush(curA, tabA, d[0], d[1]); curA = ksel; }
+                  mma_16816(d, keep_halves(a0, bits), 0u, keep_halves(a2, bits >> 8), 0u, b0, b1);
+                } else {
+                  if (ksel != curB) { flush(curB, tabB, d[2], d[3]); curB = ksel; }
+                  mma_16816(d, 0u, keep_halves(a1, bits), 0u, keep_halves(a3, bits >> 8), b0, b1);
+                }
+              }
+            }
+          }
+        }
+        flush(curA, tabA, d[0], d[1]);
+        flush(curB, tabB, d[2], d[3]);
+      }
+      __syncthreads();                    // hist / sorted are rewritten by the next round
+      tick(5);
+    }
+  }
+}
+
+}  // namespace dt4
+
+namespace dt3 {
+
 // sum of the per-CTA private tables, without the padding cells, times 1 / scale.  A CTA owns 32 consecutive output
 // elements; its 8 warps split the copies (the loads of a warp are 128 contiguous bytes of one copy).
 __global__ void __launch_bounds__(256) rpe_dtables_reduce_kernel(const float* __restrict__ priv, int copies, int n, int P3,
@@ -566,11 +940,18 @@ __global__ void __launch_bounds__(256) rpe_dtables_reduce_kernel(const float* __
 // Morton order of the queries of every scene (box centre = mean of vertices 2 (-,-,-) and 4 (+,+,+)): neighbouring
 // boxes see the keys in the same table cells, which halves the number of segments per unit.
 constexpr int QSORT_MAX = 4096;
-__global__ void __launch_bounds__(1024, 1) rpe_dtables_qorder_kernel(const float4* __restrict__ geo, int nQ, int nQp, int* __restrict__ qperm) {
+__global__ void __launch_bounds__(1024, 1) rpe_dtables_qorder_kernel(const float4* __restrict__ geo, int nQ, int nQp, int* __restrict__ qperm,
+                                                                     int* __restrict__ slow_count) {
   __shared__ unsigned long long keys[QSORT_MAX];
   __shared__ float red[6][32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* out = qperm + (size_t)b * nQ;
+  {                                       // number of queries whose box is not axis aligned (dt3 handles those)
+    int ns = 0;
+    for (int i = tid; i < nQ; i += blockDim.x) ns += __float_as_int(__ldg(&geo[((size_t)b * nQp + i) * 9].w)) == 0;
+    ns = __reduce_add_sync(FULL, ns);
+    if (lane == 0 && ns) atomicAdd(slow_count, ns);
+  }
   if (nQ > QSORT_MAX) {                   // identity: still correct, only less coherent
     for (int i = tid; i < nQ; i += blockDim.x) out[i] = i;
     return;
@@ -672,7 +1053,7 @@ extern "C" int vdetr_debug_dt_clocks(unsigned long long* out8) {
 // scratch of the dTables pass: query order + one zero-padded private table per CTA
 size_t rpe_dtables_scratch_bytes(const VdetrXattnShape* s) {
   const int P3 = s->grid_n + 2;
-  return vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024) +
+  return vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024) + 1024 +
          vdetr_align_up((size_t)vdetr_num_sms() * 8 * P3 * P3 * P3 * 4 * sizeof(float), 1024);
 }
 
@@ -693,7 +1074,8 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   if (smem > 232448) return VDETR_ERR_UNSUPPORTED;
   uint8_t* w = reinterpret_cast<uint8_t*>(scratch);
   int* qperm = reinterpret_cast<int*>(w);
-  float* priv = reinterpret_cast<float*>(w + vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024));
+  int* slow_count = reinterpret_cast<int*>(w + vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024));
+  float* priv = reinterpret_cast<float*>(w + vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024) + 1024);
 
   dt3::Params P = {};
   P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = nQp; P.nKp = nKp; P.n = n; P.R = n + 1; P.P3 = n + 2;
@@ -717,18 +1099,37 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
     return k;
   }();
   P.cost = cost;
-  const int grid = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
+  P.slow_count = slow_count;
+  // VDETR_DT_IMPL=3: the dt3 kernel for every query (the kernel of round 1); default: dt4 (tensor-core accumulation) for
+  // axis-aligned boxes + dt3 for the others (exits at once when there are none)
+  static const bool use_dt4 = []() { const char* e = getenv("VDETR_DT_IMPL"); return !(e && e[0] == '3'); }();
+  P.only_slow = use_dt4 ? 1 : 0;
+  const int grid3 = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
+  dt3::Params P4 = P;
+  P4.qblocks = (s->nQ + dt4::QB - 1) / dt4::QB;
+  P4.kchunks = (s->nK + dt4::KC - 1) / dt4::KC;
+  P4.units = s->B * P4.qblocks * P4.kchunks;
+  const int grid4 = P4.units < vdetr_num_sms() ? P4.units : vdetr_num_sms();
+  const size_t smem4 = dt4::smem_bytes(n);
+  if (use_dt4 && smem4 > 232448) return VDETR_ERR_UNSUPPORTED;
+  const int copies = (use_dt4 && grid4 > grid3) ? grid4 : grid3;
   const size_t copy_bytes = (size_t)8 * P.P3 * P.P3 * P.P3 * 4 * sizeof(float);
 
   VdetrTimingScope timing(VDETR_T_DTABLES, st);
-  VDETR_CUDA_TRY(cudaMemsetAsync(priv, 0, copy_bytes * grid, st));
-  dt3::rpe_dtables_qorder_kernel<<<s->B, 1024, 0, st>>>(geo, s->nQ, nQp, qperm);
+  VDETR_CUDA_TRY(cudaMemsetAsync(priv, 0, copy_bytes * copies, st));
+  VDETR_CUDA_TRY(cudaMemsetAsync(slow_count, 0, sizeof(int), st));
+  dt3::rpe_dtables_qorder_kernel<<<s->B, 1024, 0, st>>>(geo, s->nQ, nQp, qperm, slow_count);
   VDETR_LAUNCH_CHECK();
+  if (use_dt4) {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(dt4::rpe_dtables_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    dt4::rpe_dtables_mma_kernel<<<grid4, dt4::THREADS, smem4, st>>>(P4);
+    VDETR_LAUNCH_CHECK();
+  }
   VDETR_CUDA_TRY(cudaFuncSetAttribute(dt3::rpe_dtables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dt3::rpe_dtables_kernel<<<grid, dt3::THREADS, smem, st>>>(P);
+  dt3::rpe_dtables_kernel<<<grid3, dt3::THREADS, smem, st>>>(P);
   VDETR_LAUNCH_CHECK();
   const int total = 8 * n * n * n * 4;
-  dt3::rpe_dtables_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(priv, grid, n, P.P3, dtables, absmax_bits, dense_scale);
+  dt3::rpe_dtables_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(priv, copies, n, P.P3, dtables, absmax_bits, dense_scale);
   VDETR_LAUNCH_CHECK();
   return 0;
 }

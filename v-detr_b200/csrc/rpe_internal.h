@@ -18,22 +18,26 @@ int rpe_bias_launch(const VdetrXattnShape* s, const float* xyz, const float* ref
 
 // impl = 0 (product kernels: tcgen05 + TMA, rpe_xattn_fwd.cu / rpe_xattn_bwd.cu)
 size_t tc_xattn_fwd_workspace(const VdetrXattnShape* s);
+// drop_p > 0 with a device seed: dropout on the attention probabilities (philox.cuh), identical masks in fwd / bwd
 int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                  const float* ref, const float* ang, const float* tables, float* out, float* lse, float* bias_save,
-                 void* ws, size_t ws_bytes, cudaStream_t st);
+                 float drop_p, const unsigned long long* drop_seed, void* ws, size_t ws_bytes, cudaStream_t st);
 // bytes of the optional per-pair bias buffer the forward can leave for the backward ([B][nQp][nKp] float4; 0 = n/a)
 size_t tc_xattn_bias_save_bytes(const VdetrXattnShape* s);
-size_t tc_xattn_bwd_workspace(const VdetrXattnShape* s);
+// bias_is_saved = 0: room for re-running the forward kernel into a transient bias buffer is included
+size_t tc_xattn_bwd_workspace(const VdetrXattnShape* s, int bias_is_saved);
 int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                  const float* ref, const float* ang, const float* tables, const float* out, const float* lse,
-                 const float* dout, const float* bias_saved, float* dq, float* dk, float* dv, float* dtables, void* ws,
-                 size_t ws_bytes, cudaStream_t st);
+                 const float* dout, const float* bias_saved, float drop_p, const unsigned long long* drop_seed, float* dq,
+                 float* dk, float* dv, float* dtables, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // Operand packing shared by the product forward / backward kernels (rpe_xattn_fwd.cu):
-//   qp   bf16 [rows][64]   MQA rows = (b*nQp + q)*4 + h        MHA rows = (b*4 + h)*nQp + q     (zero padded)
-//   dop  bf16, same layout as qp (backward only)
-//   kp   bf16 [B][kvh][nKp][64]           vp bf16 same layout (backward only)
-//   vtp  bf16 [B][kvh][64][nKp]   (V transposed: keys contiguous)
+//   qp   fp16 [rows][64]   MQA rows = (b*nQp + q)*4 + h        MHA rows = (b*4 + h)*nQp + q     (zero padded)
+//   qpl  fp16, same layout: the rounding residual q - fp16(q) (hi/lo split: S = Qh Kh^T + Ql Kh^T + Qh Kl^T is
+//        accurate to ~2^-22 relative although every MMA operand is fp16)
+//   dop  fp16, same layout as qp (backward only)
+//   kp / kpl fp16 [B][kvh][nKp][64] (hi / lo)     vp fp16 same layout (backward only)
+//   vtp  fp16 [B][kvh][64][nKp]   (V transposed: keys contiguous)
 //   xyz4 f32  [B][nKp] float4
 //   geo  f32  [B][nQp][9] float4: (x+,y+,z+,fast flag) (x-,y-,z-,0) 24 vertex floats (cos,sin,0,0)
 // Precision plan: every tensor-core operand is FP16 (11-bit significand: 8x tighter than BF16 at the same
@@ -45,6 +49,7 @@ struct VdetrPack {
   const float *q, *k, *v, *xyz, *ref, *ang, *dout;
   const unsigned* dout_absmax_bits;      // device: bits of max|dout| (backward only)
   __half *qp, *kp, *vtp;                 // forward operands (and the S recompute of the backward)
+  __half *qpl, *kpl;                     // rounding residuals of qp / kp (hi/lo split of the S = Q K^T operands)
   __half *vp, *dop;                      // backward: row-major V, scaled dO (null in the forward)
   float4* xyz4;
   float4* geo;

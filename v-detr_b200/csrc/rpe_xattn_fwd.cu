@@ -7,17 +7,22 @@
 //     32 queries x 4 heads and ONE geometry evaluation per (query, key) pair feeds all four heads (float4 cell);
 //   * MHA (decoder self attention): 128 queries of one head, no bias.
 // Per 64-key tile:
-//   TMA      K tile [64 x 64] fp16 (128B swizzle), V^T tile [64 d x 64 keys], key xyz (1-D bulk copy)
-//   tcgen05  S = Q K^T  -> TMEM (double buffered), issued one tile ahead by the control warp
+//   TMA      K tile [64 x 64] fp16 hi + lo (128B swizzle), V^T tile [64 d x 64 keys], key xyz (1-D bulk copy)
+//   tcgen05  S = Qh Kh^T + Ql Kh^T + Qh Kl^T  -> TMEM (double buffered), issued one tile ahead by the control warp;
+//            q = Qh + Ql, k = Kh + Kl are fp16 hi/lo splits of the fp32 operands, so S carries ~2^-22 relative
+//            rounding instead of fp16's 2^-11 (the tensor pipe is idle: three MMAs cost nothing here)
 //   CUDA     all 16 compute warps: Vertex-RPE bias of the 32 x 64 (query,key) pairs (lanes = 32 consecutive
 //            keys, so table reads broadcast), staged through shared memory;
 //            then every thread owns (row, 16 key columns): tcgen05.ld S, + bias, online softmax (row max via a
 //            4-way smem exchange), P -> shared memory in the UMMA K-major swizzled layout
 //   tcgen05  O += P V   (accumulator stays in TMEM for the whole item; rescaled in place when the max moves)
+//   dropout  (training, nn.Dropout on the probabilities, vdetr_transformer.py:751-752) Philox keep-mask per (row, key)
+//            applied to P before the PV product; the softmax denominator uses the undropped P
 // Nothing of size nQ x nK ever reaches global memory.
 #include "rpe_internal.h"
 #include "tc_common.cuh"
 #include "rpe_fast.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -52,19 +57,24 @@ struct FwdParams {
   float* part_o;                // [items][128][64]   (splits > 1)
   float2* part_ml;              // [items][128] (m in log2 units, l)
   float4* bias_out;             // [B][nQp][nKp] bias of the 4 heads per pair, or null (saved for the backward)
+  const unsigned long long* drop_seed;   // device pointer to the 64-bit dropout seed, or null (no dropout)
+  uint32_t drop_thresh;         // philox::thresh_of(p)
+  float drop_inv_keep;          // 1 / (1 - p)
 };
 
 struct SmemLayout {
-  uint32_t tables, q, k, vt, p, bias, xyz, geo, smax, bars, total;
+  uint32_t tables, q, ql, k, kl, vt, p, bias, xyz, geo, smax, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
   SmemLayout L;
   uint32_t o = 0;
   L.q = o;      o += BM * 128;                       // 16 KB  (1024-aligned: o == 0)
+  L.ql = o;     o += BM * 128;                       // 16 KB  rounding residual of Q
   L.k = o;      o += BN * 128;                       //  8 KB
+  L.kl = o;     o += BN * 128;                       //  8 KB  rounding residual of K
   L.vt = o;     o += HD * 128;                       //  8 KB
   L.p = o;      o += BM * 128;                       // 16 KB
-  L.tables = o; o += (uint32_t)((table_bytes + 1023) / 1024 * 1024);
+  L.tables = o; o += (uint32_t)((table_bytes + 15) / 16 * 16);
   L.bias = o;   o += QT * BIAS_STRIDE_F4 * 16;       // 33,280 B
   L.xyz = o;    o += 2 * BN * 16;
   L.geo = o;    o += QT * GEO_F4 * 16;
@@ -77,13 +87,16 @@ __host__ __device__ inline SmemLayout smem_layout(int table_bytes) {
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool HAS_BIAS, bool MQA>
 __global__ void __launch_bounds__(NTHREADS, 1)
-rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQl,
+                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmKl,
                      const __grid_constant__ CUtensorMap tmVt, const FwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
   const SmemLayout L = smem_layout(HAS_BIAS ? rpe::pair_table_bytes(P.grid_n) : 0);
   uint8_t* sQ = smem + L.q;
+  uint8_t* sQl = smem + L.ql;
   uint8_t* sK = smem + L.k;
+  uint8_t* sKl = smem + L.kl;
   uint8_t* sVt = smem + L.vt;
   uint8_t* sP = smem + L.p;
   const char* sTab = reinterpret_cast<const char*>(smem + L.tables);
@@ -110,7 +123,7 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(bar_s + 0, 1); mbar_init(bar_s + 1, 1);
       mbar_init(bar_p, NCOMPUTE); mbar_init(bar_pv, 1);
       fence_barrier_init();
-      prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmVt);
+      prefetch_tmap(&tmQ); prefetch_tmap(&tmQl); prefetch_tmap(&tmK); prefetch_tmap(&tmKl); prefetch_tmap(&tmVt);
     }
     __syncwarp();
     tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -126,6 +139,24 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const uint32_t idesc_s = umma_idesc_f16(BM, BN);
   const uint32_t idesc_o = umma_idesc_f16(BM, HD);
+  philox::Dropout drop;
+  drop.thresh = P.drop_seed ? P.drop_thresh : 0u;
+  drop.inv_keep = P.drop_inv_keep;
+  {
+    const unsigned long long seed = P.drop_seed ? __ldg(P.drop_seed) : 0ull;
+    drop.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  }
+  // S(tile) = Qh Kh^T + Ql Kh^T + Qh Kl^T into TMEM columns [tcol, tcol + BN)
+  auto issue_s = [&](uint32_t tcol) {
+    const uint64_t dqh = umma_desc_sw128(smem_u32(sQ)), dql = umma_desc_sw128(smem_u32(sQl));
+    const uint64_t dkh = umma_desc_sw128(smem_u32(sK)), dkl = umma_desc_sw128(smem_u32(sKl));
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) umma_bf16(tcol, dqh + (uint64_t)(kk * 2), dkh + (uint64_t)(kk * 2), idesc_s, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) umma_bf16(tcol, dql + (uint64_t)(kk * 2), dkh + (uint64_t)(kk * 2), idesc_s, true);
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) umma_bf16(tcol, dqh + (uint64_t)(kk * 2), dkl + (uint64_t)(kk * 2), idesc_s, true);
+  };
 
   uint32_t g = 0;          // tiles processed by this CTA so far (phase bookkeeping)
   uint32_t it = 0;         // items processed by this CTA so far
@@ -148,10 +179,12 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ======================================================================== control warp (one lane)
       if (lane == 0) {
         if (it > 0) mbar_wait(bar_pv, (g - 1) & 1);       // last PV of the previous item: sVt / sQ are free
-        mbar_arrive_expect_tx(bar_q, BM * 128);
+        mbar_arrive_expect_tx(bar_q, 2 * BM * 128);
         tma_load_2d(sQ, &tmQ, 0, qrow0, bar_q);
-        mbar_arrive_expect_tx(bar_k + (g & 1), BN * 128 + (HAS_BIAS ? BN * 16 : 0));
+        tma_load_2d(sQl, &tmQl, 0, qrow0, bar_q);
+        mbar_arrive_expect_tx(bar_k + (g & 1), 2 * BN * 128 + (HAS_BIAS ? BN * 16 : 0));
         tma_load_2d(sK, &tmK, 0, krow0 + tile_begin * BN, bar_k + (g & 1));
+        tma_load_2d(sKl, &tmKl, 0, krow0 + tile_begin * BN, bar_k + (g & 1));
         if (HAS_BIAS)
           bulk_load_1d(sXyz + (g & 1) * BN, P.xyz4 + (size_t)b * P.nKp + tile_begin * BN, BN * 16, bar_k + (g & 1));
         mbar_arrive_expect_tx(bar_v, HD * 128);
@@ -159,29 +192,22 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(bar_q, it & 1);
         mbar_wait(bar_k + (g & 1), (g >> 1) & 1);
         tc_fence_after();
-        {
-          const uint64_t da = umma_desc_sw128(smem_u32(sQ)), db = umma_desc_sw128(smem_u32(sK));
-#pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk)
-            umma_bf16(tS0 + (g & 1) * BN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc_s, kk > 0);
-          umma_commit(bar_s + (g & 1));
-          umma_commit(bar_kfree);
-        }
+        issue_s(tS0 + (g & 1) * BN);
+        umma_commit(bar_s + (g & 1));
+        umma_commit(bar_kfree);
         for (int j = 0; j < T; ++j) {
           const uint32_t gj = g + j;
           if (j + 1 < T) {
             mbar_wait(bar_kfree, gj & 1);
             uint64_t* bk = bar_k + ((gj + 1) & 1);
-            mbar_arrive_expect_tx(bk, BN * 128 + (HAS_BIAS ? BN * 16 : 0));
+            mbar_arrive_expect_tx(bk, 2 * BN * 128 + (HAS_BIAS ? BN * 16 : 0));
             tma_load_2d(sK, &tmK, 0, krow0 + (tile_begin + j + 1) * BN, bk);
+            tma_load_2d(sKl, &tmKl, 0, krow0 + (tile_begin + j + 1) * BN, bk);
             if (HAS_BIAS)
               bulk_load_1d(sXyz + ((gj + 1) & 1) * BN, P.xyz4 + (size_t)b * P.nKp + (tile_begin + j + 1) * BN, BN * 16, bk);
             mbar_wait(bk, ((gj + 1) >> 1) & 1);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(sQ)), db = umma_desc_sw128(smem_u32(sK));
-#pragma unroll
-            for (int kk = 0; kk < HD / 16; ++kk)
-              umma_bf16(tS0 + ((gj + 1) & 1) * BN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc_s, kk > 0);
+            issue_s(tS0 + ((gj + 1) & 1) * BN);
             umma_commit(bar_s + ((gj + 1) & 1));
             umma_commit(bar_kfree);
           }
@@ -267,6 +293,17 @@ rpe_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           // accumulate the row sum from the fp16-rounded values that the PV MMA will actually use
           const float2 rb = __half22float2(*reinterpret_cast<const __half2*>(&pk[c >> 1]));
           psum += rb.x + rb.y;
+        }
+        if (drop.thresh) {
+          // dropout on the probabilities: the PV operand becomes P * keep / (1 - p); the denominator above does not change
+          const uint32_t keep = philox::keep_mask16(drop, (uint32_t)(qrow0 + row), (uint32_t)((key0 >> 4) + slice));
+          const __half hk = __float2half_rn(drop.inv_keep), hz = __float2half_rn(0.f);
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const __half2 sc = __halves2half2(((keep >> c) & 1u) ? hk : hz, ((keep >> (c + 1)) & 1u) ? hk : hz);
+            const __half2 v = __hmul2(*reinterpret_cast<const __half2*>(&pk[c >> 1]), sc);
+            pk[c >> 1] = *reinterpret_cast<const uint32_t*>(&v);
+          }
         }
         l_run = l_run * alpha + psum;
         m_run = m_new;
@@ -385,6 +422,14 @@ __global__ void vdetr_absmax_kernel(const float* x, size_t n, unsigned* out_bits
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));      // non-negative floats order like uints
 }
 
+// fp16 hi/lo split of an fp32 value: x ~= hi + lo to ~2^-22 relative.  Saturated at the fp16 range (the reference is
+// fp32 and would stay finite; a saturated operand is wrong but finite, an infinite one poisons the whole softmax row).
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  const float xs = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
+}
+
 __global__ void vdetr_pack_kernel(VdetrPack K) {
   const float gscale = K.dout ? vdetr_grad_scale(*K.dout_absmax_bits) : 1.f;
   const size_t nq = K.qp ? (size_t)K.B * K.nQp * 4 * 64 : 0;           // destination elements of Qp
@@ -402,7 +447,10 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       else { q = (int)(r % K.nQp); h = (int)((r / K.nQp) & 3); b = (int)(r / ((size_t)K.nQp * 4)); }
       float val = 0.f;
       if (q < K.nQ) val = K.q[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
-      K.qp[i] = __float2half_rn(val);
+      __half vh, vl;
+      split_f16(val, vh, vl);
+      K.qp[i] = vh;
+      if (K.qpl) K.qpl[i] = vl;
       if (K.dout) {
         float dv = 0.f;
         if (q < K.nQ) dv = K.dout[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
@@ -416,11 +464,14 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       const int hk = (int)((r / K.nKp) % K.kvh), b = (int)(r / ((size_t)K.nKp * K.kvh));
       float val = 0.f;
       if (key < K.nK) val = K.k[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-      K.kp[e] = __float2half_rn(val);
+      __half vh, vl;
+      split_f16(val, vh, vl);
+      K.kp[e] = vh;
+      if (K.kpl) K.kpl[e] = vl;
       if (K.vp) {                                            // row-major V as well (backward: dP = dO V^T)
         float vv = 0.f;
         if (key < K.nK) vv = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-        K.vp[e] = __float2half_rn(vv);
+        K.vp[e] = __float2half_rn(fminf(fmaxf(vv, -65504.f), 65504.f));
       }
     } else if (i < nq + 2 * nk) {
       if (!K.vtp) continue;
@@ -431,7 +482,7 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       const int hk = (int)((r >> 6) % K.kvh), b = (int)((r >> 6) / K.kvh);
       float val = 0.f;
       if (key < K.nK) val = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-      K.vtp[e] = __float2half_rn(val);
+      K.vtp[e] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
     } else if (i < nq + 2 * nk + nx) {
       const size_t e = i - nq - 2 * nk;
       const int key = (int)(e % K.nKp), b = (int)(e / K.nKp);
@@ -478,7 +529,7 @@ namespace {
 
 struct FwdPlan {
   int nQp, nKp, mtiles, splits, tiles_per_split, items;
-  size_t off_qp, off_kp, off_vtp, off_xyz, off_geo, off_po, off_pml, total;
+  size_t off_qp, off_qpl, off_kp, off_kpl, off_vtp, off_xyz, off_geo, off_po, off_pml, total;
 };
 
 FwdPlan make_plan(const VdetrXattnShape* s) {
@@ -508,7 +559,9 @@ FwdPlan make_plan(const VdetrXattnShape* s) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += vdetr_align_up(bytes, 1024); return r; };
   p.off_qp = take((size_t)s->B * p.nQp * 4 * 64 * 2);
+  p.off_qpl = take((size_t)s->B * p.nQp * 4 * 64 * 2);
   p.off_kp = take((size_t)s->B * s->kv_heads * p.nKp * 64 * 2);
+  p.off_kpl = take((size_t)s->B * s->kv_heads * p.nKp * 64 * 2);
   p.off_vtp = take((size_t)s->B * s->kv_heads * p.nKp * 64 * 2);
   p.off_xyz = take(s->has_bias ? (size_t)s->B * p.nKp * 16 : 0);
   p.off_geo = take(s->has_bias ? (size_t)s->B * p.nQp * GEO_F4 * 16 : 0);
@@ -529,9 +582,10 @@ size_t tc_xattn_fwd_workspace(const VdetrXattnShape* s) { return make_plan(s).to
 
 int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const float* v, const float* xyz,
                  const float* ref, const float* ang, const float* tables, float* out, float* lse, float* bias_save,
-                 void* ws, size_t ws_bytes, cudaStream_t st) {
+                 float drop_p, const unsigned long long* drop_seed, void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool mqa = s->kv_heads == 1;
   if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
+  if (!(drop_p >= 0.f) || drop_p >= 1.f || (drop_p > 0.f && !drop_seed)) return VDETR_ERR_BAD_ARG;
   const FwdPlan pl = make_plan(s);
   if (!ws || ws_bytes < pl.total) return VDETR_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return VDETR_ERR_WORKSPACE;      // cudaMalloc / torch give >= 256 B
@@ -541,17 +595,21 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   pk.B = s->B; pk.nQ = s->nQ; pk.nK = s->nK; pk.nQp = pl.nQp; pk.nKp = pl.nKp; pk.kvh = s->kv_heads; pk.has_bias = s->has_bias;
   pk.q = q; pk.k = k; pk.v = v; pk.xyz = xyz; pk.ref = ref; pk.ang = (s->has_bias && s->rotate) ? ang : nullptr;
   pk.qp = reinterpret_cast<__half*>(w + pl.off_qp);
+  pk.qpl = reinterpret_cast<__half*>(w + pl.off_qpl);
   pk.kp = reinterpret_cast<__half*>(w + pl.off_kp);
+  pk.kpl = reinterpret_cast<__half*>(w + pl.off_kpl);
   pk.vtp = reinterpret_cast<__half*>(w + pl.off_vtp);
   pk.xyz4 = reinterpret_cast<float4*>(w + pl.off_xyz);
   pk.geo = reinterpret_cast<float4*>(w + pl.off_geo);
   vdetr_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(pk);
   VDETR_LAUNCH_CHECK();
 
-  CUtensorMap tmQ, tmK, tmVt;
+  CUtensorMap tmQ, tmQl, tmK, tmKl, tmVt;
   int rc;
   if ((rc = vdetr_make_tmap_bf16_rows64(&tmQ, pk.qp, (uint64_t)s->B * pl.nQp * 4, BM, true))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmQl, pk.qpl, (uint64_t)s->B * pl.nQp * 4, BM, true))) return rc;
   if ((rc = vdetr_make_tmap_bf16_rows64(&tmK, pk.kp, (uint64_t)s->B * s->kv_heads * pl.nKp, BN, true))) return rc;
+  if ((rc = vdetr_make_tmap_bf16_rows64(&tmKl, pk.kpl, (uint64_t)s->B * s->kv_heads * pl.nKp, BN, true))) return rc;
   if ((rc = vdetr_make_tmap_bf16_2d(&tmVt, pk.vtp, (uint64_t)s->B * s->kv_heads * HD, (uint64_t)pl.nKp, HD, true))) return rc;
 
   FwdParams P = {};
@@ -564,6 +622,9 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   P.xyz4 = pk.xyz4; P.geo = pk.geo; P.tables = reinterpret_cast<const float4*>(tables);
   P.out = out; P.lse = lse;
   P.bias_out = s->has_bias ? reinterpret_cast<float4*>(bias_save) : nullptr;
+  P.drop_seed = drop_p > 0.f ? drop_seed : nullptr;
+  P.drop_thresh = philox::thresh_of(drop_p);
+  P.drop_inv_keep = 1.0f / (1.0f - drop_p);
   P.part_o = reinterpret_cast<float*>(w + pl.off_po);
   P.part_ml = reinterpret_cast<float2*>(w + pl.off_pml);
 
@@ -575,13 +636,13 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   VdetrTimingScope timing(s->has_bias ? VDETR_T_FWD : VDETR_T_COUNT, st);
   if (s->has_bias) {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rpe_xattn_fwd_kernel<true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);
+    rpe_xattn_fwd_kernel<true, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmQl, tmK, tmKl, tmVt, P);
   } else if (mqa) {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rpe_xattn_fwd_kernel<false, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);
+    rpe_xattn_fwd_kernel<false, true><<<grid, NTHREADS, smem, st>>>(tmQ, tmQl, tmK, tmKl, tmVt, P);
   } else {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(rpe_xattn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rpe_xattn_fwd_kernel<false, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmK, tmVt, P);
+    rpe_xattn_fwd_kernel<false, false><<<grid, NTHREADS, smem, st>>>(tmQ, tmQl, tmK, tmKl, tmVt, P);
   }
   VDETR_LAUNCH_CHECK();
   if (pl.splits > 1) {

@@ -117,6 +117,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
   return d;
 }
+// Same for an MN-major operand (the "M" / "N" index is the contiguous one): tiles as TMA writes them for a box of
+// [k rows][64 elements] with the 128-byte swizzle.  Canonical layout (cute/atom/mma_traits_sm100.hpp, in 16-byte units):
+// Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) -- 64 contiguous MN elements per 128-B row, 8 k-rows per 1024-B
+// group, k-groups SBO apart, 64-element MN blocks LBO apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4)                       // c_format = F32
@@ -128,6 +141,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // Same for FP16 x FP16 -> F32 (format code 0).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// FP16 x FP16 -> F32 with per-operand majorness (bit 15: A is MN-major, bit 16: B is MN-major)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_major(int M, int N, bool a_mn, bool b_mn) {
+  return umma_idesc_f16(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {

@@ -33,10 +33,39 @@ def _shape(q, k, tables, log_scale, max_value, rotate, has_bias):
     return _C.XattnShape(B, nQ, nK, H, hd, n, float(log_scale), float(max_value), int(rotate), kvh, int(has_bias))
 
 
+def _validate(q, k, v, xyz, ref_pts, ref_angle, tables):
+    """Shape contract of the kernels (they index raw pointers: a mismatch must never reach the device)."""
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise RuntimeError("q must be [B,nQ,H,hd], k / v must be [B,nK,kv_heads,hd]")
+    B, nQ, H, hd = q.shape
+    if (H, hd) != (4, 64):
+        raise RuntimeError(f"the attention kernels are built for 4 heads x 64 channels, got {H} x {hd}")
+    if k.shape != v.shape or k.shape[0] != B or k.shape[3] != hd or k.shape[2] not in (1, H):
+        raise RuntimeError(f"k {tuple(k.shape)} / v {tuple(v.shape)} do not match q {tuple(q.shape)}")
+    if tables is None:
+        return
+    nK = k.shape[1]
+    if k.shape[2] != 1:
+        raise RuntimeError("the Vertex-RPE bias requires one shared K/V head (kv_heads = 1)")
+    if tables.dim() != 5 or tables.shape[0] != 8 or tables.shape[4] != H or not (tables.shape[1] == tables.shape[2] == tables.shape[3]):
+        raise RuntimeError(f"tables must be [8,n,n,n,{H}], got {tuple(tables.shape)}")
+    if xyz is None or tuple(xyz.shape) != (B, nK, 3):
+        raise RuntimeError(f"xyz must be [{B},{nK},3]")
+    if ref_pts is None or tuple(ref_pts.shape) != (B, nQ, 8, 3):
+        raise RuntimeError(f"ref_pts must be [{B},{nQ},8,3]")
+    if ref_angle is not None and tuple(ref_angle.shape) != (B, nQ):
+        raise RuntimeError(f"ref_angle must be [{B},{nQ}]")
+
+
 class _RpeAttention(Function):
     @staticmethod
-    def forward(ctx, q, k, v, xyz, ref_pts, ref_angle, tables, log_scale, max_value, impl, impl_bwd):
+    def forward(ctx, q, k, v, xyz, ref_pts, ref_angle, tables, log_scale, max_value, impl, impl_bwd, dropout_p, dropout_seed):
         has_bias = tables is not None
+        _validate(q, k, v, xyz, ref_pts, ref_angle, tables)
+        if dropout_p > 0.0:
+            if impl != IMPL_TCGEN05 or impl_bwd != IMPL_TCGEN05:
+                raise RuntimeError("attention dropout is implemented by the tcgen05 kernels only (impl 0)")
+            _C.require_cuda("dropout_seed", dropout_seed, torch.int64)
         for name, t in (("q", q), ("k", k), ("v", v)):
             _C.require_cuda(name, t, torch.float32)
         if has_bias:
@@ -58,53 +87,83 @@ class _RpeAttention(Function):
                 if nsave:
                     bias_save = torch.empty(nsave, dtype=torch.uint8, device=q.device)
             _C.check(L.vdetr_xattn_fwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
-                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(bias_save), _C.ptr(ws), nbytes, impl,
-                                       _C.stream_ptr()))
-        ctx.save_for_backward(q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save)
-        ctx.meta = (log_scale, max_value, impl_bwd, has_bias)
+                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(bias_save), float(dropout_p),
+                                       _C.ptr(dropout_seed), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
+        ctx.save_for_backward(q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save, dropout_seed)
+        ctx.meta = (log_scale, max_value, impl_bwd, has_bias, float(dropout_p))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save = ctx.saved_tensors
-        log_scale, max_value, impl, has_bias = ctx.meta
+        q, k, v, xyz, ref_pts, ref_angle, tables, out, lse, bias_save, dropout_seed = ctx.saved_tensors
+        log_scale, max_value, impl, has_bias, dropout_p = ctx.meta
         dout = dout.contiguous()
         s = _shape(q, k, tables, log_scale, max_value, ref_angle is not None, has_bias)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         dtab = torch.empty_like(tables) if has_bias else None
         L = _C.lib()
         with torch.cuda.device(q.device):
-            nbytes = L.vdetr_xattn_bwd_workspace_bytes(s, impl)
+            nbytes = L.vdetr_xattn_bwd_workspace_bytes(s, impl, int(bias_save is not None))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device) if nbytes else None
             _C.check(L.vdetr_xattn_bwd(s, _C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(xyz), _C.ptr(ref_pts), _C.ptr(ref_angle),
-                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(dout), _C.ptr(bias_save), _C.ptr(dq),
-                                       _C.ptr(dk), _C.ptr(dv), _C.ptr(dtab), _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
-        return dq, dk, dv, None, None, None, dtab, None, None, None, None
+                                       _C.ptr(tables), _C.ptr(out), _C.ptr(lse), _C.ptr(dout), _C.ptr(bias_save),
+                                       float(dropout_p), _C.ptr(dropout_seed), _C.ptr(dq), _C.ptr(dk), _C.ptr(dv), _C.ptr(dtab),
+                                       _C.ptr(ws), nbytes, impl, _C.stream_ptr()))
+        return dq, dk, dv, None, None, None, dtab, None, None, None, None, None, None
+
+
+def new_dropout_seed(device) -> torch.Tensor:
+    """One 64-bit seed on `device`, drawn from torch's CUDA generator (so torch.manual_seed controls it and the draw is
+    legal inside CUDA-graph capture: every replay advances the generator and re-seeds the attention dropout)."""
+    return torch.randint(-(2 ** 62), 2 ** 62, (1,), dtype=torch.int64, device=device)
 
 
 def rpe_attention(q, k, v, xyz=None, ref_pts=None, ref_angle=None, tables=None, log_scale=512.0, max_value=4.0,
-                  impl=None, impl_bwd=None):
-    """softmax_k(q k^T + rpe(ref_pts, xyz, tables)) v.
+                  impl=None, impl_bwd=None, dropout_p=0.0, dropout_seed=None):
+    """softmax_k(q k^T + rpe(ref_pts, xyz, tables)) v, with optional dropout on the probabilities.
 
     q [B,nQ,H,hd] (pre-scaled by hd^-0.5), k/v [B,nK,kvh,hd] (kvh = 1: shared K/V head, kvh = H: per head),
     xyz [B,nK,3], ref_pts [B,nQ,8,3], ref_angle [B,nQ] or None, tables [8,n,n,n,H] or None (no bias).
+    dropout_p > 0: nn.Dropout(p) on the attention probabilities (vdetr_transformer.py:751-752) inside the kernels;
+    dropout_seed = int64 CUDA tensor [1] (default: a fresh draw from torch's generator).
     Returns [B,nQ,H,hd].  Gradients: q, k, v, tables (xyz / ref_pts are detached in the reference).
     """
+    dropout_p = float(dropout_p)
+    if not 0.0 <= dropout_p < 1.0:
+        raise RuntimeError(f"dropout_p must be in [0, 1), got {dropout_p}")
+    if dropout_p > 0.0 and dropout_seed is None:
+        dropout_seed = new_dropout_seed(q.device)
+    if dropout_p == 0.0:
+        dropout_seed = None
     impl = default_impl() if impl is None else impl
     impl_bwd = int(os.environ.get("VDETR_B200_IMPL_BWD", impl)) if impl_bwd is None else impl_bwd
     return _RpeAttention.apply(q.contiguous(), k.contiguous(), v.contiguous(),
                                None if xyz is None else xyz.contiguous(),
                                None if ref_pts is None else ref_pts.contiguous(),
                                None if ref_angle is None else ref_angle.contiguous(),
-                               None if tables is None else tables.contiguous(), log_scale, max_value, impl, impl_bwd)
+                               None if tables is None else tables.contiguous(), log_scale, max_value, impl, impl_bwd,
+                               dropout_p, dropout_seed)
+
+
+def _validate_bias_args(xyz, ref_pts, ref_angle, tables):
+    if xyz.dim() != 3 or xyz.shape[2] != 3:
+        raise RuntimeError("xyz must be [B,nK,3]")
+    B, nK = xyz.shape[:2]
+    if ref_pts.dim() != 4 or ref_pts.shape[0] != B or tuple(ref_pts.shape[2:]) != (8, 3):
+        raise RuntimeError(f"ref_pts must be [{B},nQ,8,3], got {tuple(ref_pts.shape)}")
+    nQ = ref_pts.shape[1]
+    if tables.dim() != 5 or tables.shape[0] != 8 or tables.shape[4] != 4 or not (tables.shape[1] == tables.shape[2] == tables.shape[3]):
+        raise RuntimeError(f"tables must be [8,n,n,n,4] (4 heads), got {tuple(tables.shape)}")
+    if ref_angle is not None and tuple(ref_angle.shape) != (B, nQ):
+        raise RuntimeError(f"ref_angle must be [{B},{nQ}]")
+    return B, nK, nQ
 
 
 def rpe_bias(xyz, ref_pts, tables, ref_angle=None, log_scale=512.0, max_value=4.0):
     """Materialise rpe [B,H,nQ,nK] (debug / return_attn_weights path; vdetr_transformer.py:708-731)."""
     for name, t in (("xyz", xyz), ("ref_pts", ref_pts), ("tables", tables)):
         _C.require_cuda(name, t, torch.float32)
-    B, nK = xyz.shape[:2]
-    nQ = ref_pts.shape[1]
+    B, nK, nQ = _validate_bias_args(xyz, ref_pts, ref_angle, tables)
     s = _C.XattnShape(B, nQ, nK, 4, 64, tables.shape[1], float(log_scale), float(max_value), int(ref_angle is not None), 1, 1)
     out = torch.empty(B, 4, nQ, nK, dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
@@ -115,8 +174,9 @@ def rpe_bias(xyz, ref_pts, tables, ref_angle=None, log_scale=512.0, max_value=4.
 
 def rpe_bias_grad_tables(xyz, ref_pts, ref_angle, tables, dbias, log_scale=512.0, max_value=4.0):
     """dTables [8,n,n,n,H] from a dense d(bias) [B,H,nQ,nK] (adjoint of ``rpe_bias``)."""
-    B, nK = xyz.shape[:2]
-    nQ = ref_pts.shape[1]
+    B, nK, nQ = _validate_bias_args(xyz, ref_pts, ref_angle, tables)
+    if tuple(dbias.shape) != (B, 4, nQ, nK):
+        raise RuntimeError(f"dbias must be [{B},4,{nQ},{nK}], got {tuple(dbias.shape)}")
     s = _C.XattnShape(B, nQ, nK, 4, 64, tables.shape[1], float(log_scale), float(max_value), int(ref_angle is not None), 1, 1)
     ds4 = dbias.permute(0, 2, 3, 1).contiguous()
     out = torch.empty_like(tables)
@@ -128,6 +188,11 @@ def rpe_bias_grad_tables(xyz, ref_pts, ref_angle, tables, dbias, log_scale=512.0
                                      _C.ptr(None if ref_angle is None else ref_angle.contiguous()), _C.ptr(ds4), _C.ptr(out),
                                      _C.ptr(ws), nbytes, _C.stream_ptr()))
     return out
+
+
+def _reduce_ws(cols, device):
+    """Scratch of the deterministic cross-CTA column reductions (partial sums + ticket); never read by the caller."""
+    return torch.empty(_C.lib().vdetr_reduce_workspace_floats(cols), dtype=torch.float32, device=device)
 
 
 class _LayerNorm(Function):
@@ -155,8 +220,9 @@ class _LayerNorm(Function):
         dw = torch.empty_like(weight)
         db = torch.empty_like(weight)
         with torch.cuda.device(x2.device):
+            ws = _reduce_ws(cols, x2.device)
             _C.check(_C.lib().vdetr_layernorm_bwd(_C.ptr(dy2), _C.ptr(x2), _C.ptr(mean), _C.ptr(rstd), _C.ptr(weight), rows, cols,
-                                                  _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.stream_ptr()))
+                                                  _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.ptr(ws), _C.stream_ptr()))
         return dx.view(ctx.shape), dw, db, None
 
 
@@ -177,8 +243,8 @@ class _BnReluTrain(Function):
         y = torch.empty_like(x)
         mean = torch.empty(cols, dtype=torch.float32, device=x.device)
         rstd = torch.empty(cols, dtype=torch.float32, device=x.device)
-        ws = torch.empty(2 * cols, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
+            ws = _reduce_ws(cols, x.device)
             _C.check(_C.lib().vdetr_bn_relu_train_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(bias), rows, cols, float(eps), float(momentum),
                                                       _C.ptr(y), _C.ptr(mean), _C.ptr(rstd), _C.ptr(running_mean),
                                                       _C.ptr(running_var), _C.ptr(ws), _C.stream_ptr()))
@@ -193,8 +259,9 @@ class _BnReluTrain(Function):
         dy = dy.contiguous()
         dx, dw, db = torch.empty_like(x), torch.empty_like(weight), torch.empty_like(weight)
         with torch.cuda.device(x.device):
+            ws = _reduce_ws(cols, x.device)
             _C.check(_C.lib().vdetr_bn_relu_train_bwd(_C.ptr(dy), _C.ptr(y), _C.ptr(x), _C.ptr(mean), _C.ptr(rstd), _C.ptr(weight),
-                                                      rows, cols, _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.stream_ptr()))
+                                                      rows, cols, _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.ptr(ws), _C.stream_ptr()))
         return dx, dw, db, None, None, None, None
 
 
@@ -237,7 +304,8 @@ class _TokenLinear(Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(dy2.shape[1], dtype=dy2.dtype, device=dy2.device)
             with torch.cuda.device(dy2.device):
-                _C.check(_C.lib().vdetr_colsum(_C.ptr(dy2), dy2.shape[0], dy2.shape[1], _C.ptr(db), _C.stream_ptr()))
+                ws = torch.empty(_C.lib().vdetr_colsum_workspace_floats(dy2.shape[1]), dtype=torch.float32, device=dy2.device)
+                _C.check(_C.lib().vdetr_colsum(_C.ptr(dy2), dy2.shape[0], dy2.shape[1], _C.ptr(db), _C.ptr(ws), _C.stream_ptr()))
         return dx, dw, db
 
 

@@ -140,6 +140,18 @@ def morton_order(xyz: Tensor) -> Tensor:
     return torch.argsort(code, dim=1)
 
 
+_HEAD_STREAMS = {}
+
+
+def _head_streams(device, n):
+    """Side streams for the independent box heads of a level, cached per device at module level (stream objects in
+    module state would break copy.deepcopy / torch.save of the model)."""
+    key = (device.type, device.index)
+    if key not in _HEAD_STREAMS or len(_HEAD_STREAMS[key]) < n:
+        _HEAD_STREAMS[key] = [torch.cuda.Stream(device) for _ in range(n)]
+    return _HEAD_STREAMS[key][:n]
+
+
 class BoxProcessor(object):
     """Turns MLP head outputs into boxes (:20-90)."""
 
@@ -188,15 +200,19 @@ class BoxProcessor(object):
 
 
 # ------------------------------------------------------------------------------------------------- attention
-def _dense_attention(q, k, v, bias, drop):
-    """Materialising attention used only for return_attn_weights / attn_mask / train-time attention dropout
-    (the fused kernels implement none of the three).  q [B,nQ,H,hd], k/v [B,nK,kvh,hd], bias [B,H,nQ,nK] or None."""
+def _dense_attention(q, k, v, bias, drop, mask=None):
+    """Materialising attention used only for return_attn_weights / attn_mask (the fused kernels return no [B,H,nQ,nK]
+    tensor and take no mask).  q [B,nQ,H,hd], k/v [B,nK,kvh,hd], bias [B,H,nQ,nK] or None; mask [B,1|H,nQ,nK]: bool
+    entries set the *logit* to -100, float masks are added (:743-749).  Returns (o, probabilities after dropout), the
+    tensor the reference returns as `attn` (:751-758)."""
     qh, kh, vh = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)
     s = qh @ kh.transpose(-1, -2)
     if bias is not None:
         s = s + bias
-    p = torch.softmax(s, dim=-1)
-    o = (drop(p) @ vh).permute(0, 2, 1, 3)
+    if mask is not None:
+        s = s.masked_fill(mask, -100.0) if mask.dtype == torch.bool else s + mask
+    p = drop(torch.softmax(s, dim=-1))
+    o = (p @ vh).permute(0, 2, 1, 3)
     return o, p
 
 
@@ -231,11 +247,10 @@ class MultiheadSelfAttention(nn.Module):
         q = (q * (hd ** -0.5)).reshape(L, B, H, hd).transpose(0, 1)
         k = k.reshape(-1, B, H, hd).transpose(0, 1)
         v = v.reshape(-1, B, H, hd).transpose(0, 1)
-        plain = attn_mask is None and key_padding_mask is None and not need_weights and \
-            not (self.training and self.dropout > 0)
+        plain = attn_mask is None and key_padding_mask is None and not need_weights
         weights = None
         if plain:
-            o = ops.rpe_attention(q, k, v)
+            o = ops.rpe_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0)
         else:
             bias = None
             if attn_mask is not None:
@@ -274,10 +289,7 @@ class ShareSelfAttention(nn.Module):
         q = (self.q(query) * self.scale).reshape(L, B, H, D // H).transpose(0, 1)
         k = self.k(key).transpose(0, 1).unsqueeze(2)
         v = self.v(value).transpose(0, 1).unsqueeze(2)
-        if self.training and self.attn_drop.p > 0:
-            o, _ = _dense_attention(q, k, v, None, self.attn_drop)
-        else:
-            o = ops.rpe_attention(q, k, v)
+        o = ops.rpe_attention(q, k, v, dropout_p=self.attn_drop.p if self.training else 0.0)
         x = self.proj(o.transpose(0, 1).reshape(L, B, D))
         return self.proj_drop(x), None
 
@@ -307,7 +319,6 @@ class GlobalShareCrossAttention(nn.Module):
         self.proj = Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
         self.softmax = nn.Softmax(dim=-1)
-        self.need_weights = False       # set True to get the [B,H,nQ,nK] probabilities back (debug path)
 
     def build_cpb_mlp(self, in_dim, hidden_dim, out_dim):
         return nn.Sequential(nn.Linear(in_dim, hidden_dim, bias=True), nn.ReLU(inplace=False),
@@ -318,8 +329,11 @@ class GlobalShareCrossAttention(nn.Module):
         gradient (dTables) is the kernel output that autograd carries on into the MLP weights."""
         return torch.stack([mlp(self.relative_coords_table)[0] for mlp in self.cpb_mlps])
 
-    def forward(self, query, key, reference_point, reference_angle, xyz, attn_mask=None, key_padding_mask=None):
+    def forward(self, query, key, reference_point, reference_angle, xyz, attn_mask=None, key_padding_mask=None,
+                need_weights=False):
         # query [nQ,B,D]  key [nK,B,D]  reference_point [B,nQ,8,3]  xyz [B,nK,3]
+        # need_weights=True (GlobalDecoderLayer's return_attn_weights) or an attn_mask select the materialising path,
+        # which returns the [B,H,nQ,nK] probabilities like the reference does; otherwise attn is None.
         nQ, B, D = query.shape
         H = self.num_heads
         if self.interp_method != "bilinear":
@@ -332,17 +346,14 @@ class GlobalShareCrossAttention(nn.Module):
         ref = reference_point.detach().float()
         ang = reference_angle.detach().float() if rotate else None
         pts = xyz.detach().float()
-        fused = attn_mask is None and not self.need_weights and not (self.training and self.attn_drop.p > 0)
+        fused = attn_mask is None and not need_weights
         attn = None
         if fused:
-            o = ops.rpe_attention(q, k, v, pts, ref, ang, tables, self.log_scale, self.max_value)
+            o = ops.rpe_attention(q, k, v, pts, ref, ang, tables, self.log_scale, self.max_value,
+                                  dropout_p=self.attn_drop.p if self.training else 0.0)
         else:
             bias = _RpeBiasFn.apply(pts, ref, ang, tables, self.log_scale, self.max_value)
-            if attn_mask is not None:
-                m = attn_mask.unsqueeze(1)
-                bias = bias.masked_fill(m, -100.0) if m.dtype == torch.bool else bias + m
-                # (the reference fills the *logits* with -100; filling the bias differs by q.k only where masked)
-            o, attn = _dense_attention(q, k, v, bias, self.attn_drop)
+            o, attn = _dense_attention(q, k, v, bias, self.attn_drop, None if attn_mask is None else attn_mask.unsqueeze(1))
         x = self.proj(o.transpose(0, 1).reshape(nQ, B, D))
         return self.proj_drop(x), attn
 
@@ -416,11 +427,11 @@ class GlobalDecoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def _cross(self, tgt, memory, reference_point, reference_angle, enc_xyz, memory_mask, memory_key_padding_mask, pos,
-               query_pos):
+               query_pos, need_weights=False):
         key = self.with_pos_embed(memory, pos) if self.pos_for_key else memory
         return self.multihead_attn(query=self.with_pos_embed(tgt, query_pos), key=key, reference_point=reference_point,
                                    reference_angle=reference_angle, xyz=enc_xyz, attn_mask=memory_mask,
-                                   key_padding_mask=memory_key_padding_mask)
+                                   key_padding_mask=memory_key_padding_mask, need_weights=need_weights)
 
     def forward_post(self, tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask=None,
                      memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None,
@@ -429,7 +440,7 @@ class GlobalDecoderLayer(nn.Module):
         tgt = self.norm1(tgt + self.dropout1(self.self_attn(qk, qk, value=tgt, attn_mask=tgt_mask,
                                                             key_padding_mask=tgt_key_padding_mask)[0]))
         x, attn = self._cross(tgt, memory, reference_point, reference_angle, enc_xyz, memory_mask,
-                              memory_key_padding_mask, pos, query_pos)
+                              memory_key_padding_mask, pos, query_pos, return_attn_weights)
         tgt = self.norm2(tgt + self.dropout2(x))
         tgt = self.norm3(tgt + self.dropout3(self.linear2(self.dropout(self.activation(self.linear1(tgt))))))
         return (tgt, attn) if return_attn_weights else (tgt, None)
@@ -443,7 +454,7 @@ class GlobalDecoderLayer(nn.Module):
                                                  key_padding_mask=tgt_key_padding_mask)[0])
         t2 = self.norm2(tgt)
         x, attn = self._cross(t2, memory, reference_point, reference_angle, enc_xyz, memory_mask,
-                              memory_key_padding_mask, pos, query_pos)
+                              memory_key_padding_mask, pos, query_pos, return_attn_weights)
         tgt = tgt + self.dropout2(x)
         t2 = self.norm3(tgt)
         tgt = tgt + self.dropout3(self.linear2(self.dropout(self.activation(self.linear1(t2)))))
@@ -453,14 +464,8 @@ class GlobalDecoderLayer(nn.Module):
                 memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None,
                 return_attn_weights=False):
         fn = self.forward_pre if self.normalize_before else self.forward_post
-        if return_attn_weights:
-            self.multihead_attn.need_weights = True
-        try:
-            return fn(tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask, memory_mask,
-                      tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos, return_attn_weights)
-        finally:
-            if return_attn_weights:
-                self.multihead_attn.need_weights = False
+        return fn(tgt, memory, reference_point, reference_angle, enc_xyz, point_cloud_dims, tgt_mask, memory_mask,
+                  tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos, return_attn_weights)
 
 
 class TransformerDecoder(nn.Module):
@@ -505,7 +510,6 @@ class TransformerDecoder(nn.Module):
         self.box_processor = BoxProcessor(dataset_config, cls_loss=cls_loss)
         self.sort_keys = True       # Morton-order the key tokens once per forward (see module docstring)
         self.parallel_heads = os.environ.get("VDETR_B200_PARALLEL_HEADS", "1") != "0"
-        self._head_streams = {}
 
     def _head_factory(self, decoder_dim, mlp_dropout):
         return partial(GenericMLP, norm_fn_name=self.mlp_norm, activation=self.mlp_act, use_conv=True,
@@ -556,16 +560,15 @@ class TransformerDecoder(nn.Module):
         if not (feats.is_cuda and self.parallel_heads):
             return {n: run(n) for n in self.HEAD_NAMES}
         cur = torch.cuda.current_stream(feats.device)
-        key = feats.device.index
-        if key not in self._head_streams:
-            self._head_streams[key] = [torch.cuda.Stream(feats.device) for _ in self.HEAD_NAMES]
+        streams = _head_streams(feats.device, len(self.HEAD_NAMES))
         out = {}
-        for n, st in zip(self.HEAD_NAMES, self._head_streams[key]):
+        for n, st in zip(self.HEAD_NAMES, streams):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 out[n] = run(n)
-        for st in self._head_streams[key]:
+        for n, st in zip(self.HEAD_NAMES, streams):
             cur.wait_stream(st)
+            out[n].record_stream(cur)        # allocated on a side stream, consumed (and later freed) on `cur`
         return out
 
     def get_proposal_box_predictions_refine(self, idx, query_xyz, point_cloud_dims, box_features,
