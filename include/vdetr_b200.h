@@ -170,19 +170,22 @@ int vdetr_layernorm_bwd(const float* dy, const float* x, const float* mean, cons
 size_t vdetr_colsum_workspace_floats(int cols);
 int vdetr_colsum(const float* x, int rows, int cols, float* out, float* workspace, void* stream);
 
-/* Training-mode BatchNorm1d + ReLU on token-major activations x [rows, cols] f32 (the Conv1d(k=1)-BatchNorm1d-ReLU
- * stacks of models/helpers.py:17-33 and :74-141 evaluated per token).  Batch statistics over the rows; running_mean /
- * running_var (may be NULL) are updated in place with `momentum` and the unbiased variance, like nn.BatchNorm1d.
- *   fwd: y, mean [cols], rstd [cols].       bwd: dx, dgamma, dbeta (fully overwritten);
- *   y is the forward output (its sign is the ReLU mask).  cols: vdetr_bn_relu_supported (128, 256, 384, 512).
- *   workspace (both directions): vdetr_reduce_workspace_floats(cols) floats. */
+/* Training-mode BatchNorm1d + ReLU on token-major activations (the Conv1d(k=1)-BatchNorm1d-ReLU stacks of
+ * models/helpers.py:17-33 and :74-141 evaluated per token).  `groups` independent BatchNorm layers of `cols` channels each
+ * are normalised by one call (the 5 box heads of a decoder level, models/vdetr_transformer.py:256-300, evaluated
+ * together): element (row r, group g, channel c) is x[g * group_stride + r * row_stride + c] (strides in floats, multiples
+ * of 4) -- groups = 1, row_stride = cols is a plain dense [rows, cols] matrix; y / dy / dx use the same layout.
+ * gamma, beta, mean, rstd, running_mean, running_var, dgamma, dbeta are [groups * cols].  Batch statistics over the rows;
+ * running_mean / running_var (may be NULL) are updated in place with `momentum` and the unbiased variance, like
+ * nn.BatchNorm1d.  y is the forward output (its sign is the ReLU mask).  cols: vdetr_bn_relu_supported (128, 256, 384,
+ * 512).  workspace (both directions): vdetr_reduce_workspace_floats(groups * cols) floats. */
 int vdetr_bn_relu_supported(int cols);
-int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float momentum,
-                            float* y, float* mean, float* rstd, float* running_mean, float* running_var, float* workspace,
-                            void* stream);
+int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, int groups,
+                            long long group_stride, long long row_stride, float eps, float momentum, float* y, float* mean,
+                            float* rstd, float* running_mean, float* running_var, float* workspace, void* stream);
 int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
-                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, float* workspace,
-                            void* stream);
+                            const float* gamma, int rows, int cols, int groups, long long group_stride, long long row_stride,
+                            float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
 
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call

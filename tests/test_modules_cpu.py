@@ -130,3 +130,42 @@ def test_flat_grad_gather_matches_accumulation():
     assert torch.equal(flat, torch.cat([w.reshape(-1) for w in want]))
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(fg.params, fg.views))
     assert torch.equal(fg.gather_(), flat) and torch.equal(fg.sync_(), flat)
+
+
+def test_grouped_heads_equal_head_by_head():
+    """TransformerDecoder._run_heads_grouped (one GEMM / batched GEMMs / grouped BatchNorm for the 5 heads of a level)
+    against the head-by-head token path, eval and train mode, including the running-statistics update."""
+    import copy
+    from vdetr_b200 import vdetr_transformer as vt
+    dec = _build(1, 16, False)
+    heads = dec.mlp_heads[1]
+    g = torch.Generator().manual_seed(3)
+    for n in dec.HEAD_NAMES:
+        for m in heads[n].modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(generator=g); m.running_var.uniform_(0.5, 2.0, generator=g)
+                m.weight.data.normal_(generator=g); m.bias.data.normal_(generator=g)
+        heads[n].layers[-1].weight.data.normal_(generator=g); heads[n].layers[-1].bias.data.normal_(generator=g)
+        for m in heads[n].modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    x = torch.randn(16, 3, 256, generator=g)
+    for train in (False, True):
+        dec.train(train)
+        stacks = dec._grouped_plan(heads)
+        assert stacks is not None
+        twin = copy.deepcopy(heads)
+        a = dec._run_heads_grouped(stacks, x.reshape(48, 256), 16, 3)
+        dec.group_heads = False
+        b = dec._run_heads(twin, x)
+        dec.group_heads = True
+        for n in dec.HEAD_NAMES:
+            assert a[n].shape == b[n].shape
+            assert (a[n] - b[n]).abs().max().item() <= 1e-4 * (b[n].abs().max().item() + 1.0), n
+        for n in dec.HEAD_NAMES:
+            for m1, m2 in zip(heads[n].modules(), twin[n].modules()):
+                if isinstance(m1, torch.nn.BatchNorm1d):
+                    assert torch.allclose(m1.running_mean, m2.running_mean, atol=1e-5)
+                    assert torch.allclose(m1.running_var, m2.running_var, atol=1e-5)
+                    assert int(m1.num_batches_tracked) == int(m2.num_batches_tracked)
+    _ = vt

@@ -53,8 +53,9 @@ _SIGS = {
     "vdetr_colsum_workspace_floats": (c_size_t, [c_int]),
     "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vdetr_bn_relu_supported": (c_int, [c_int]),
-    "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float] + [c_void_p] * 7),
-    "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 5),
+    "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong,
+                                        c_float, c_float] + [c_void_p] * 7),
+    "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong] + [c_void_p] * 5),
     "vdetr_debug_dt_clocks": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "vdetr_rpe_dtables_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape)]),
     "vdetr_rpe_dtables": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),

@@ -8,6 +8,10 @@
 //   bwd sums: dbeta = sum g, dgamma = sum g * xhat with g = dy * [y > 0]  (the two column sums the input gradient needs)
 //   bwd dx  : dx = gamma * rstd * (g - dbeta / T - xhat * dgamma / T)
 // Stock PyTorch runs 3 kernels forward (statistics, transform, ReLU) and 3 backward; here the ReLU rides along.
+// Several independent BatchNorm layers of the same width are normalised by ONE launch (the 5 box heads of a decoder level
+// evaluated together): blockIdx.y = group; element (row r, group g, channel c) is x[g * group_stride + r * row_stride + c],
+// which covers both the channels-last [tokens, G * C] output of a concatenated GEMM and the head-major [G, tokens, C]
+// output of a batched one.  gs4 / ld4 below are group_stride / 4 and row_stride / 4.
 #include "common.cuh"
 #include "det_reduce.cuh"
 
@@ -38,13 +42,18 @@ __device__ __forceinline__ void reduce_columns_to_global(float4 (&a)[VEC], float
   }
   det_finish_columns<BN_WARPS * 32>(part, gridDim.x, 2 * C, ticket, out_a, out_b, C);
 }
+// per-chunk views of the reduction workspace: partial sums [chunk][64][2 * C], one ticket per chunk
+template <int VEC>
+__device__ __forceinline__ float* chunk_part(float* part) { return part + (size_t)blockIdx.y * VDETR_RED_MAX_BLOCKS * 2 * (VEC * 128); }
 
 template <int VEC>
 __global__ void __launch_bounds__(BN_WARPS * 32) bn_stats_kernel(const float4* __restrict__ x, int rows, float* __restrict__ sum,
                                                                  float* __restrict__ sumsq, float* __restrict__ part,
-                                                                 unsigned* __restrict__ ticket) {
-  constexpr int C4 = VEC * 32;
+                                                                 unsigned* __restrict__ ticket, int ld4, size_t gs4) {
+  constexpr int C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  x += blockIdx.y * gs4; sum += blockIdx.y * C; sumsq += blockIdx.y * C;
+  part = chunk_part<VEC>(part); ticket += blockIdx.y;
   float4 s[VEC], q[VEC], pv[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -55,7 +64,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_stats_kernel(const float4* _
   for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      float4 v = x[(size_t)r * C4 + i * 32 + lane];
+      float4 v = x[(size_t)r * ld4 + i * 32 + lane];
       v.x -= pv[i].x; v.y -= pv[i].y; v.z -= pv[i].z; v.w -= pv[i].w;
       s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
       q[i].x += v.x * v.x; q[i].y += v.y * v.y; q[i].z += v.z * v.z; q[i].w += v.w * v.w;
@@ -70,9 +79,12 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const floa
                                                                       const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                       float eps, float momentum, float4* __restrict__ y,
                                                                       float* __restrict__ mean, float* __restrict__ rstd,
-                                                                      float* running_mean, float* running_var) {
+                                                                      float* running_mean, float* running_var, int ld4, size_t gs4) {
   constexpr int C4 = VEC * 32, C = C4 * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  x += blockIdx.y * gs4; y += blockIdx.y * gs4; gamma += blockIdx.y * C4; beta += blockIdx.y * C4;
+  sum += blockIdx.y * C; sumsq += blockIdx.y * C; mean += blockIdx.y * C; rstd += blockIdx.y * C;
+  if (running_mean) { running_mean += blockIdx.y * C; running_var += blockIdx.y * C; }
   const float inv_n = 1.0f / (float)rows;
   float4 sc[VEC], sh[VEC];            // y = relu(x * sc + sh)
 #pragma unroll
@@ -104,8 +116,8 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const floa
   for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 v = x[(size_t)r * C4 + i * 32 + lane];
-      y[(size_t)r * C4 + i * 32 + lane] =
+      const float4 v = x[(size_t)r * ld4 + i * 32 + lane];
+      y[(size_t)r * ld4 + i * 32 + lane] =
           make_float4(fmaxf(fmaf(v.x, sc[i].x, sh[i].x), 0.f), fmaxf(fmaf(v.y, sc[i].y, sh[i].y), 0.f),
                       fmaxf(fmaf(v.z, sc[i].z, sh[i].z), 0.f), fmaxf(fmaf(v.w, sc[i].w, sh[i].w), 0.f));
     }
@@ -117,9 +129,13 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4
                                                                     const float4* __restrict__ x, int rows,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                    float* __restrict__ part, unsigned* __restrict__ ticket) {
-  constexpr int C4 = VEC * 32;
+                                                                    float* __restrict__ part, unsigned* __restrict__ ticket, int ld4,
+                                                                    size_t gs4) {
+  constexpr int C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  dy += blockIdx.y * gs4; y += blockIdx.y * gs4; x += blockIdx.y * gs4;
+  mean += blockIdx.y * C; rstd += blockIdx.y * C; dgamma += blockIdx.y * C; dbeta += blockIdx.y * C;
+  part = chunk_part<VEC>(part); ticket += blockIdx.y;
   float4 ag[VEC], ab[VEC], mu[VEC], rs[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4
   for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const size_t o = (size_t)r * C4 + i * 32 + lane;
+      const size_t o = (size_t)r * ld4 + i * 32 + lane;
       const float4 d = dy[o], yy = y[o], xv = x[o];
       const float gx = yy.x > 0.f ? d.x : 0.f, gy = yy.y > 0.f ? d.y : 0.f, gz = yy.z > 0.f ? d.z : 0.f, gw = yy.w > 0.f ? d.w : 0.f;
       ab[i].x += gx; ab[i].y += gy; ab[i].z += gz; ab[i].w += gw;
@@ -147,9 +163,12 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* 
                                                                   const float4* __restrict__ x, int rows,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float4* __restrict__ gamma, const float* __restrict__ dgamma,
-                                                                  const float* __restrict__ dbeta, float4* __restrict__ dx) {
-  constexpr int C4 = VEC * 32;
+                                                                  const float* __restrict__ dbeta, float4* __restrict__ dx, int ld4,
+                                                                  size_t gs4) {
+  constexpr int C4 = VEC * 32, C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  dy += blockIdx.y * gs4; y += blockIdx.y * gs4; x += blockIdx.y * gs4; dx += blockIdx.y * gs4; gamma += blockIdx.y * C4;
+  mean += blockIdx.y * C; rstd += blockIdx.y * C; dgamma += blockIdx.y * C; dbeta += blockIdx.y * C;
   const float inv_n = 1.0f / (float)rows;
   float4 mu[VEC], rs[VEC], k1[VEC], k2[VEC], k3[VEC];      // dx = k1 * g - k2 - xhat * k3
 #pragma unroll
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* 
   for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const size_t o = (size_t)r * C4 + i * 32 + lane;
+      const size_t o = (size_t)r * ld4 + i * 32 + lane;
       const float4 d = dy[o], yy = y[o], xv = x[o];
       const float gx = yy.x > 0.f ? d.x : 0.f, gy = yy.y > 0.f ? d.y : 0.f, gz = yy.z > 0.f ? d.z : 0.f, gw = yy.w > 0.f ? d.w : 0.f;
       dx[o] = make_float4(k1[i].x * gx - k2[i].x - (xv.x - mu[i].x) * rs[i].x * k3[i].x,
@@ -186,38 +205,50 @@ inline int bn_red_grid(int rows) {                 // kernels that end in a cros
   return g > VDETR_RED_MAX_BLOCKS ? VDETR_RED_MAX_BLOCKS : g;
 }
 
+struct BnLayout {
+  int groups;
+  size_t group_stride, row_stride;      // in floats
+};
+
 template <int VEC>
-int fwd_t(const float* x, const float* gamma, const float* beta, int rows, float eps, float momentum, float* y, float* mean,
-          float* rstd, float* running_mean, float* running_var, float* ws, cudaStream_t st) {
-  const int C = VEC * 128;
-  float* part = ws + 2 * C;
-  unsigned* ticket = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * C);
-  VDETR_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-  bn_stats_kernel<VEC><<<bn_red_grid(rows), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws, ws + C, part, ticket);
+int fwd_t(const float* x, const float* gamma, const float* beta, int rows, const BnLayout& L, float eps, float momentum, float* y,
+          float* mean, float* rstd, float* running_mean, float* running_var, float* ws, cudaStream_t st) {
+  const int cols = VEC * 128 * L.groups, ld4 = (int)(L.row_stride / 4);
+  const size_t gs4 = L.group_stride / 4;
+  float* part = ws + 2 * cols;
+  unsigned* tickets = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols);
+  VDETR_CUDA_TRY(cudaMemsetAsync(tickets, 0, 32 * sizeof(unsigned), st));
+  bn_stats_kernel<VEC><<<dim3(bn_red_grid(rows), L.groups), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws,
+                                                                                    ws + cols, part, tickets, ld4, gs4);
   VDETR_LAUNCH_CHECK();
-  bn_apply_relu_kernel<VEC><<<bn_grid(rows, 2), BN_WARPS * 32, 0, st>>>(
-      reinterpret_cast<const float4*>(x), rows, ws, ws + C, reinterpret_cast<const float4*>(gamma),
-      reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var);
+  bn_apply_relu_kernel<VEC><<<dim3(bn_grid(rows, 2), L.groups), BN_WARPS * 32, 0, st>>>(
+      reinterpret_cast<const float4*>(x), rows, ws, ws + cols, reinterpret_cast<const float4*>(gamma),
+      reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var, ld4, gs4);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
 template <int VEC>
 int bwd_t(const float* dy, const float* y, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
-          float* dx, float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
-  const int C = VEC * 128;
-  float* part = ws + 2 * C;
-  unsigned* ticket = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * C);
-  VDETR_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-  bn_bwd_sums_kernel<VEC><<<bn_red_grid(rows), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(dy),
-                                                                      reinterpret_cast<const float4*>(y),
-                                                                      reinterpret_cast<const float4*>(x), rows, mean, rstd, dgamma, dbeta,
-                                                                      part, ticket);
-  VDETR_LAUNCH_CHECK();
-  bn_bwd_dx_kernel<VEC><<<bn_grid(rows, 2), BN_WARPS * 32, 0, st>>>(
+          const BnLayout& L, float* dx, float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
+  const int cols = VEC * 128 * L.groups, ld4 = (int)(L.row_stride / 4);
+  const size_t gs4 = L.group_stride / 4;
+  float* part = ws + 2 * cols;
+  unsigned* tickets = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols);
+  VDETR_CUDA_TRY(cudaMemsetAsync(tickets, 0, 32 * sizeof(unsigned), st));
+  bn_bwd_sums_kernel<VEC><<<dim3(bn_red_grid(rows), L.groups), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
-      reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx));
+      dgamma, dbeta, part, tickets, ld4, gs4);
+  VDETR_LAUNCH_CHECK();
+  bn_bwd_dx_kernel<VEC><<<dim3(bn_grid(rows, 2), L.groups), BN_WARPS * 32, 0, st>>>(
+      reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
+      reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx), ld4, gs4);
   VDETR_LAUNCH_CHECK();
   return 0;
+}
+
+bool layout_ok(int cols, int groups, long long group_stride, long long row_stride) {
+  return groups >= 1 && groups <= 32 && group_stride % 4 == 0 && row_stride % 4 == 0 && row_stride >= cols &&
+         (groups == 1 || group_stride >= cols);
 }
 
 }  // namespace
@@ -228,31 +259,33 @@ int vdetr_bn_relu_supported(int cols) { return cols == 128 || cols == 256 || col
 
 size_t vdetr_reduce_workspace_floats(int cols) { return cols > 0 ? vdetr_reduce_ws_floats(cols) : 0; }
 
-int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, float eps, float momentum,
-                            float* y, float* mean, float* rstd, float* running_mean, float* running_var, float* workspace,
-                            void* stream) {
-  if (rows < 1 || !vdetr_bn_relu_supported(cols)) return VDETR_ERR_UNSUPPORTED;
+int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, int groups,
+                            long long group_stride, long long row_stride, float eps, float momentum, float* y, float* mean,
+                            float* rstd, float* running_mean, float* running_var, float* workspace, void* stream) {
+  if (rows < 1 || !vdetr_bn_relu_supported(cols) || !layout_ok(cols, groups, group_stride, row_stride)) return VDETR_ERR_UNSUPPORTED;
   if (!x || !gamma || !beta || !y || !mean || !rstd || !workspace) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  const BnLayout L = {groups, (size_t)group_stride, (size_t)row_stride};
   switch (cols / 128) {
-    case 1: return fwd_t<1>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
-    case 2: return fwd_t<2>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
-    case 3: return fwd_t<3>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
-    default: return fwd_t<4>(x, gamma, beta, rows, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    case 1: return fwd_t<1>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    case 2: return fwd_t<2>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    case 3: return fwd_t<3>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    default: return fwd_t<4>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
   }
 }
 
 int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
-                            const float* gamma, int rows, int cols, float* dx, float* dgamma, float* dbeta, float* workspace,
-                            void* stream) {
-  if (rows < 1 || !vdetr_bn_relu_supported(cols)) return VDETR_ERR_UNSUPPORTED;
+                            const float* gamma, int rows, int cols, int groups, long long group_stride, long long row_stride,
+                            float* dx, float* dgamma, float* dbeta, float* workspace, void* stream) {
+  if (rows < 1 || !vdetr_bn_relu_supported(cols) || !layout_ok(cols, groups, group_stride, row_stride)) return VDETR_ERR_UNSUPPORTED;
   if (!dy || !y || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || !workspace) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  const BnLayout L = {groups, (size_t)group_stride, (size_t)row_stride};
   switch (cols / 128) {
-    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
-    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
-    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
-    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, dx, dgamma, dbeta, workspace, st);
+    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
+    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
+    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
+    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
   }
 }
 

@@ -237,32 +237,42 @@ def layer_norm(x, weight, bias, eps=1e-5):
 
 
 class _BnReluTrain(Function):
+    """relu(BatchNorm(x)) for `groups` independent BatchNorm layers of `cols` channels in one pair of kernels.
+    layout "cl": x [rows, groups * cols] (channels last); layout "gm": x [groups, rows, cols] (group major)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum):
-        rows, cols = x.shape
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, groups, layout):
+        if layout == "cl":
+            rows, cols = x.shape[0], x.shape[1] // groups
+            gstride, rstride = cols, x.shape[1]
+        else:
+            rows, cols = x.shape[1], x.shape[2]
+            gstride, rstride = rows * cols, cols
         y = torch.empty_like(x)
-        mean = torch.empty(cols, dtype=torch.float32, device=x.device)
-        rstd = torch.empty(cols, dtype=torch.float32, device=x.device)
+        mean = torch.empty(groups * cols, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(groups * cols, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            ws = _reduce_ws(cols, x.device)
-            _C.check(_C.lib().vdetr_bn_relu_train_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(bias), rows, cols, float(eps), float(momentum),
-                                                      _C.ptr(y), _C.ptr(mean), _C.ptr(rstd), _C.ptr(running_mean),
-                                                      _C.ptr(running_var), _C.ptr(ws), _C.stream_ptr()))
+            ws = _reduce_ws(groups * cols, x.device)
+            _C.check(_C.lib().vdetr_bn_relu_train_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(bias), rows, cols, groups, gstride, rstride,
+                                                      float(eps), float(momentum), _C.ptr(y), _C.ptr(mean), _C.ptr(rstd),
+                                                      _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(ws), _C.stream_ptr()))
         ctx.save_for_backward(x, y, weight, mean, rstd)
+        ctx.geom = (rows, cols, groups, gstride, rstride)
         ctx.mark_non_differentiable(*[t for t in (running_mean, running_var) if t is not None])
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, weight, mean, rstd = ctx.saved_tensors
-        rows, cols = x.shape
+        rows, cols, groups, gstride, rstride = ctx.geom
         dy = dy.contiguous()
         dx, dw, db = torch.empty_like(x), torch.empty_like(weight), torch.empty_like(weight)
         with torch.cuda.device(x.device):
-            ws = _reduce_ws(cols, x.device)
+            ws = _reduce_ws(groups * cols, x.device)
             _C.check(_C.lib().vdetr_bn_relu_train_bwd(_C.ptr(dy), _C.ptr(y), _C.ptr(x), _C.ptr(mean), _C.ptr(rstd), _C.ptr(weight),
-                                                      rows, cols, _C.ptr(dx), _C.ptr(dw), _C.ptr(db), _C.ptr(ws), _C.stream_ptr()))
-        return dx, dw, db, None, None, None, None
+                                                      rows, cols, groups, gstride, rstride, _C.ptr(dx), _C.ptr(dw), _C.ptr(db),
+                                                      _C.ptr(ws), _C.stream_ptr()))
+        return dx, dw, db, None, None, None, None, None, None
 
 
 def bn_relu_train_supported(x, bn) -> bool:
@@ -277,7 +287,40 @@ def bn_relu_train(x, bn):
     rv = bn.running_var if bn.track_running_stats else None
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return _BnReluTrain.apply(x.contiguous(), bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum)
+    return _BnReluTrain.apply(x.contiguous(), bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, 1, "cl")
+
+
+def bn_relu_train_group_supported(x, bns, layout) -> bool:
+    b0 = bns[0]
+    cols = b0.num_features
+    same = all(type(b) is torch.nn.BatchNorm1d and b.training and b.affine and b.num_features == cols and b.eps == b0.eps
+               and b.momentum == b0.momentum and b.momentum is not None and b.track_running_stats == b0.track_running_stats
+               for b in bns)
+    shape_ok = (x.dim() == 2 and x.shape[1] == cols * len(bns) and x.shape[0] > 1) if layout == "cl" else \
+        (x.dim() == 3 and x.shape[0] == len(bns) and x.shape[2] == cols and x.shape[1] > 1)
+    return same and shape_ok and x.is_cuda and x.dtype == torch.float32 and cols in (128, 256, 384, 512) and len(bns) <= 32
+
+
+def bn_relu_train_group(x, bns, layout):
+    """relu(BatchNorm1d_g(x_g)) for several training-mode nn.BatchNorm1d layers of equal width at once: x is
+    [T, G * C] (layout "cl", the output of one GEMM with the G weight matrices concatenated) or [G, T, C] ("gm", the
+    output of a batched GEMM).  Parameters are concatenated for the call (autograd splits the gradients back); the
+    running statistics are updated through one temporary and copied back to the modules."""
+    weight = torch.cat([b.weight for b in bns])
+    bias = torch.cat([b.bias for b in bns])
+    track = bns[0].track_running_stats
+    rm = torch.cat([b.running_mean for b in bns]) if track else None
+    rv = torch.cat([b.running_var for b in bns]) if track else None
+    y = _BnReluTrain.apply(x.contiguous(), weight, bias, rm, rv, bns[0].eps, bns[0].momentum, len(bns), layout)
+    if track:
+        with torch.no_grad():
+            c = bns[0].num_features
+            torch._foreach_copy_([b.running_mean for b in bns] + [b.running_var for b in bns],
+                                 list(rm.split(c)) + list(rv.split(c)))
+            nbt = [b.num_batches_tracked for b in bns if b.num_batches_tracked is not None]
+            if nbt:
+                torch._foreach_add_(nbt, 1)
+    return y
 
 
 class _TokenLinear(Function):

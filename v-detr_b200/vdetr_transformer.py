@@ -510,6 +510,7 @@ class TransformerDecoder(nn.Module):
         self.box_processor = BoxProcessor(dataset_config, cls_loss=cls_loss)
         self.sort_keys = True       # Morton-order the key tokens once per forward (see module docstring)
         self.parallel_heads = os.environ.get("VDETR_B200_PARALLEL_HEADS", "1") != "0"
+        self.group_heads = os.environ.get("VDETR_B200_GROUP_HEADS", "1") != "0"
 
     def _head_factory(self, decoder_dim, mlp_dropout):
         return partial(GenericMLP, norm_fn_name=self.mlp_norm, activation=self.mlp_act, use_conv=True,
@@ -544,13 +545,76 @@ class TransformerDecoder(nn.Module):
 
     HEAD_NAMES = ("sem_cls_head", "center_head", "size_head", "angle_cls_head", "angle_residual_head")
 
+    def _grouped_plan(self, heads):
+        """The 5 heads of a level as one stack when they share the reference's default structure
+        [Conv1d(k=1) - BatchNorm1d - ReLU - Dropout] x 2 - Conv1d(k=1) (models/helpers.py:74-141 with use_conv, bn1d, relu);
+        None otherwise."""
+        stacks = [list(heads[n].layers) for n in self.HEAD_NAMES]
+        kinds = (nn.Conv1d, nn.BatchNorm1d, nn.ReLU, nn.Dropout, nn.Conv1d, nn.BatchNorm1d, nn.ReLU, nn.Dropout, nn.Conv1d)
+        for st in stacks:
+            if len(st) != len(kinds) or any(type(m) is not k for m, k in zip(st, kinds)):
+                return None
+            if any(m.kernel_size != (1,) or m.stride != (1,) or m.groups != 1 for m in (st[0], st[4], st[8])):
+                return None
+        c0 = stacks[0]
+        for st in stacks:
+            if (st[0].weight.shape != c0[0].weight.shape or st[4].weight.shape != c0[4].weight.shape
+                    or (st[0].bias is None) != (c0[0].bias is None) or (st[4].bias is None) != (c0[4].bias is None)
+                    or st[8].bias is None or st[3].p != c0[3].p or st[7].p != c0[7].p):
+                return None
+        return stacks
+
+    @staticmethod
+    def _bn_relu_group(x, bns, layout):
+        """relu(bn_g(x_g)) for the heads' BatchNorm layers: the library's grouped kernels in training, the running
+        statistics as a per-channel affine map otherwise."""
+        if ops.bn_relu_train_group_supported(x, bns, layout):
+            return ops.bn_relu_train_group(x, bns, layout)
+        if any(b.training for b in bns):
+            # widths the kernels do not cover: per-head stock BatchNorm
+            C = bns[0].num_features
+            parts = x.split(C, dim=1) if layout == "cl" else x.unbind(0)
+            ys = [F.relu(b(p)) for b, p in zip(bns, parts)]
+            return torch.cat(ys, dim=1) if layout == "cl" else torch.stack(ys)
+        scale = torch.stack([b.weight * torch.rsqrt(b.running_var + b.eps) for b in bns])           # [G, C]
+        shift = torch.stack([b.bias for b in bns]) - torch.stack([b.running_mean for b in bns]) * scale
+        if layout == "cl":
+            return F.relu(x * scale.reshape(1, -1) + shift.reshape(1, -1))
+        return F.relu(x * scale.unsqueeze(1) + shift.unsqueeze(1))
+
+    def _run_heads_grouped(self, stacks, feats, nQ, B):
+        """feats [T = nQ*B, C] -> {head: [B,nQ,out]}: layer 1 of all heads is ONE GEMM against the concatenated weights
+        ([T, G*C], channels last), layers 2 and 3 are batched GEMMs over the heads ([G, T, C]); each BatchNorm+ReLU level
+        is one grouped kernel pair.  ~4x fewer launches than head-by-head evaluation, same parameters and results."""
+        G, T = len(stacks), feats.shape[0]
+        C = stacks[0][0].out_channels
+        W1 = torch.cat([st[0].weight.squeeze(-1) for st in stacks])                                 # [G*C, Cin]
+        b1 = torch.cat([st[0].bias for st in stacks]) if stacks[0][0].bias is not None else None
+        h = ops.linear(feats, W1, b1)                                                               # [T, G*C]
+        h = stacks[0][3](self._bn_relu_group(h, [st[1] for st in stacks], "cl"))
+        W2 = torch.stack([st[4].weight.squeeze(-1) for st in stacks])                               # [G, C, C]
+        h = torch.bmm(h.view(T, G, C).transpose(0, 1), W2.transpose(1, 2))                          # [G, T, C]
+        if stacks[0][4].bias is not None:
+            h = h + torch.stack([st[4].bias for st in stacks]).unsqueeze(1)
+        h = stacks[0][7](self._bn_relu_group(h, [st[5] for st in stacks], "gm"))
+        outs = [st[8].out_channels for st in stacks]
+        omax = max(outs)
+        W3 = torch.stack([F.pad(st[8].weight.squeeze(-1), (0, 0, 0, omax - o)) for st, o in zip(stacks, outs)])   # [G, omax, C]
+        b3 = torch.stack([F.pad(st[8].bias, (0, omax - o)) for st, o in zip(stacks, outs)])                        # [G, omax]
+        o = torch.baddbmm(b3.unsqueeze(1), h, W3.transpose(1, 2))                                   # [G, T, omax]
+        return {n: o[g, :, :outs[g]].view(nQ, B, outs[g]).transpose(0, 1) for g, n in enumerate(self.HEAD_NAMES)}
+
     def _run_heads(self, heads, box_features):
         """box_features [nQ,B,C] -> {head: [B,nQ,out]} (:256-300).  The heads are evaluated token-major (GEMMs on the
-        contiguous [nQ*B, C] rows instead of Conv1d on a permuted copy, see helpers.pointwise_tokens); the 5 heads of
-        a level read the same features and are independent, so on CUDA they are issued on 5 forked streams and
-        joined: their small kernels (and, through autograd's stream bookkeeping, their backward kernels) overlap."""
+        contiguous [nQ*B, C] rows instead of Conv1d on a permuted copy, see helpers.pointwise_tokens).  Heads of the
+        reference's default structure run as one grouped stack (_run_heads_grouped); otherwise the 5 heads of a level,
+        which read the same features and are independent, are issued on 5 forked streams and joined."""
         nQ, B, C = box_features.shape
         tokens = all(heads[n].supports_tokens for n in self.HEAD_NAMES)
+        if tokens and self.group_heads and box_features.is_cuda:
+            stacks = self._grouped_plan(heads)
+            if stacks is not None:
+                return self._run_heads_grouped(stacks, box_features.reshape(nQ * B, C), nQ, B)
         feats = box_features.reshape(nQ * B, C) if tokens else box_features.permute(1, 2, 0)
 
         def run(n):
