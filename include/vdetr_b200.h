@@ -47,6 +47,16 @@ size_t vdetr_pn2_fps_workspace_bytes(int B, int N, int M);
 int vdetr_pn2_fps(const float* xyz /*[B,N,3]*/, int B, int N, int M, int32_t* idx /*[B,M]*/,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Ragged batch: scene b owns rows [offsets[b], offsets[b+1]) of xyz [total_n,3] (offsets: B+1 int32 on the DEVICE, so no
+ * host synchronisation is needed to call this).  Every scene is sampled exactly like a B = 1 call of vdetr_pn2_fps on its
+ * own points; idx [B,M] holds scene-local indices.  Replaces the Python loop over scenes with one B = 1 launch each at
+ * models/model_vdetr.py:282-316.  max_n = an upper bound of the per-scene point count known to the caller (it sizes the
+ * thread-block clusters); a scene with more points gets idx = -1, an empty scene idx = 0.
+ * workspace: vdetr_pn2_fps_ragged_workspace_bytes(B, total_n, max_n, M) (0 unless max_n exceeds the cluster kernel). */
+size_t vdetr_pn2_fps_ragged_workspace_bytes(int B, int total_n, int max_n, int M);
+int vdetr_pn2_fps_ragged(const float* xyz /*[total_n,3]*/, const int32_t* offsets /*[B+1]*/, int B, int total_n, int max_n, int M,
+                         int32_t* idx /*[B,M]*/, void* workspace, size_t workspace_bytes, void* stream);
+
 /* gather_points(points[B,C,N], idx[B,M]) -> out[B,C,M]        (src/sampling.cpp:17-40, sampling_gpu.cu:11-33) */
 int vdetr_pn2_gather(const float* points, const int32_t* idx, int B, int C, int N, int M, float* out,
                      void* stream);

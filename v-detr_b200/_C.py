@@ -29,6 +29,8 @@ _SIGS = {
     "vdetr_error_string": (ctypes.c_char_p, [c_int]),
     "vdetr_pn2_fps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vdetr_pn2_fps": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vdetr_pn2_fps_ragged_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "vdetr_pn2_fps_ragged": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdetr_pn2_gather": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vdetr_pn2_gather_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vdetr_pn2_ball_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),

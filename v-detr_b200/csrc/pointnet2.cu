@@ -88,14 +88,44 @@ __device__ __forceinline__ void warp_argmax(Cand& c, int width = 32) {
 // One cluster (CLUSTER CTAs) per scene, PPT points per thread.  Coordinates + running min-distance live in
 // registers; a float4 copy of the CTA's coordinates sits in shared memory so that only the 64-bit key travels
 // through the shuffles and the winner's xyz is fetched once per round by one thread.
+// geometry of a scene of n points, computed on the device for the ragged variant: floor(log2 n) equals the host's
+// (int)(log(n) / log(2)) for every n (checked exhaustively below 2^22; S is clamped to 512 anyway)
+__device__ __forceinline__ FpsGeom device_geom(int n, int m) {
+  FpsGeom g;
+  g.n = n; g.m = m;
+  int L = n > 0 ? 31 - __clz(n) : 0;
+  if (L > 9) L = 9;
+  g.L = L; g.S = 1 << L;
+  g.cnt = (n + g.S - 1) / g.S;
+  g.slots = g.S * g.cnt;
+  return g;
+}
+
+// offsets == nullptr: B scenes of g.n points each, xyz [B][n][3].
+// offsets != nullptr: ragged batch, scene b = rows [offsets[b], offsets[b+1]) of xyz [total][3]; every scene is sampled
+// exactly like a B = 1 call on its own points (the reference's per-scene loop, models/model_vdetr.py:282-316).
 template <int PPT>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
-fps_cluster_kernel(const float* __restrict__ xyz, int32_t* __restrict__ idxs, FpsGeom g, int cluster_size) {
+fps_cluster_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offsets, int32_t* __restrict__ idxs, FpsGeom g,
+                   int cluster_size) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int scene = blockIdx.x / cluster_size;
   const float* pts = xyz + (size_t)scene * g.n * 3;
   int32_t* out = idxs + (size_t)scene * g.m;
+  if (offsets) {
+    const int o0 = __ldg(offsets + scene), n = __ldg(offsets + scene + 1) - o0;
+    pts = xyz + (size_t)o0 * 3;
+    const int m = g.m;
+    g = device_geom(n, m);
+    if (n <= 0 || (long long)g.slots > (long long)cluster_size * FPS_THREADS * PPT) {
+      // empty scene, or more points than the caller's bound: mark the row invalid instead of sampling garbage
+      // (cluster-uniform branch: no cluster.sync() has been executed yet)
+      if (rank == 0)
+        for (int j = threadIdx.x; j < m; j += FPS_THREADS) out[j] = n <= 0 ? 0 : -1;
+      return;
+    }
+  }
 
   extern __shared__ float4 spts[];                 // [FPS_THREADS * PPT] this CTA's points, slot order
   __shared__ unsigned long long warp_key[2][FPS_WARPS];
@@ -185,11 +215,23 @@ fps_cluster_kernel(const float* __restrict__ xyz, int32_t* __restrict__ idxs, Fp
 
 // Fallback for very large N: temp lives in global memory (workspace), one 1024-thread CTA per scene.
 __global__ void __launch_bounds__(1024, 1)
-fps_generic_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int32_t* __restrict__ idxs, FpsGeom g) {
+fps_generic_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offsets, float* __restrict__ temp,
+                   int32_t* __restrict__ idxs, FpsGeom g) {
   const int scene = blockIdx.x;
   const float* pts = xyz + (size_t)scene * g.n * 3;
   float* tmp = temp + (size_t)scene * g.n;
   int32_t* out = idxs + (size_t)scene * g.m;
+  if (offsets) {                       // ragged batch: see fps_cluster_kernel
+    const int o0 = __ldg(offsets + scene), n = __ldg(offsets + scene + 1) - o0;
+    pts = xyz + (size_t)o0 * 3;
+    tmp = temp + o0;
+    const int m = g.m;
+    g = device_geom(n, m);
+    if (n <= 0) {
+      for (int j = threadIdx.x; j < m; j += 1024) out[j] = 0;
+      return;
+    }
+  }
   __shared__ Cand warp_cand[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int k = tid; k < g.n; k += 1024) tmp[k] = 1e10f;
@@ -253,8 +295,10 @@ FpsPlan fps_plan(const FpsGeom& g, bool allow16) {
   return FpsPlan{0, 0};
 }
 
+// max_active != nullptr: do not launch, report how many clusters of this shape can be resident at once
 template <int PPT>
-int launch_fps_cluster(const float* xyz, int32_t* idx, const FpsGeom& g, int B, int cluster, cudaStream_t st) {
+int launch_fps_cluster(const float* xyz, const int32_t* offsets, int32_t* idx, const FpsGeom& g, int B, int cluster, cudaStream_t st,
+                       int* max_active = nullptr) {
   auto kern = fps_cluster_kernel<PPT>;
   if (cluster > 8)
     VDETR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -269,8 +313,21 @@ int launch_fps_cluster(const float* xyz, int32_t* idx, const FpsGeom& g, int B, 
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  VDETR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, idx, g, cluster));
+  if (max_active) {
+    VDETR_CUDA_TRY(cudaOccupancyMaxActiveClusters(max_active, kern, &cfg));
+    return 0;
+  }
+  VDETR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, offsets, idx, g, cluster));
   return 0;
+}
+int launch_fps_plan(const FpsPlan& p, const float* xyz, const int32_t* offsets, int32_t* idx, const FpsGeom& g, int B,
+                    cudaStream_t st, int* max_active = nullptr) {
+  switch (p.ppt) {
+    case 4: return launch_fps_cluster<4>(xyz, offsets, idx, g, B, p.cluster, st, max_active);
+    case 8: return launch_fps_cluster<8>(xyz, offsets, idx, g, B, p.cluster, st, max_active);
+    case 16: return launch_fps_cluster<16>(xyz, offsets, idx, g, B, p.cluster, st, max_active);
+    default: return launch_fps_cluster<24>(xyz, offsets, idx, g, B, p.cluster, st, max_active);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ gather / group
@@ -381,15 +438,13 @@ size_t vdetr_pn2_fps_workspace_bytes(int B, int N, int M) {
   return p.cluster == 0 ? (size_t)B * N * sizeof(float) : 0;
 }
 
-int vdetr_pn2_fps(const float* xyz, int B, int N, int M, int32_t* idx, void* workspace, size_t workspace_bytes,
-                  void* stream) {
-  if (B < 0 || N < 0 || M < 0) return VDETR_ERR_BAD_ARG;
-  if (B == 0 || M == 0) return 0;
-  if (N == 0 || !xyz || !idx) return VDETR_ERR_BAD_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  FpsGeom g = make_geom(N, M);
+// Plans and launches FPS for B scenes whose geometry is bounded by g (exact for the dense call, the caller's max_n for
+// the ragged one).  temp_floats = total number of points (workspace of the generic kernel).
+static int fps_dispatch(const float* xyz, const int32_t* offsets, int B, const FpsGeom& g, size_t temp_floats, int32_t* idx,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
   for (int attempt = 0; attempt < 2; ++attempt) {
-    // 16-CTA clusters need 16 free SMs in one GPC: use them only while all scenes can be co-resident.
+    // 16-CTA clusters (non-portable) need 16 free SMs in one GPC: they are used only when all B clusters can be resident
+    // at once (occupancy query below) -- otherwise half the scenes wait for a second wave and B = 8 costs 2 x B = 1.
     const bool allow16 = (attempt == 0) && (B * 16 <= vdetr_num_sms());
     FpsPlan p = fps_plan(g, allow16);
     if (const char* dbg = getenv("VDETR_FPS_PLAN")) {          // debug override "cluster,ppt" (tests only)
@@ -397,22 +452,48 @@ int vdetr_pn2_fps(const float* xyz, int B, int N, int M, int32_t* idx, void* wor
       if (sscanf(dbg, "%d,%d", &c, &pp) == 2 && (long long)c * FPS_THREADS * pp >= g.slots) p = FpsPlan{c, pp};
     }
     if (p.cluster == 0) {
-      if (!workspace || workspace_bytes < (size_t)B * N * sizeof(float)) return VDETR_ERR_WORKSPACE;
-      fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, (float*)workspace, idx, g);
+      if (!workspace || workspace_bytes < temp_floats * sizeof(float)) return VDETR_ERR_WORKSPACE;
+      fps_generic_kernel<<<B, 1024, 0, st>>>(xyz, offsets, (float*)workspace, idx, g);
       VDETR_LAUNCH_CHECK();
       return 0;
     }
-    int rc;
-    switch (p.ppt) {
-      case 4: rc = launch_fps_cluster<4>(xyz, idx, g, B, p.cluster, st); break;
-      case 8: rc = launch_fps_cluster<8>(xyz, idx, g, B, p.cluster, st); break;
-      case 16: rc = launch_fps_cluster<16>(xyz, idx, g, B, p.cluster, st); break;
-      default: rc = launch_fps_cluster<24>(xyz, idx, g, B, p.cluster, st); break;
+    if (p.cluster > 8) {
+      int active = 0;
+      const int qrc = launch_fps_plan(p, xyz, offsets, idx, g, B, st, &active);
+      if (qrc != 0 || active < B) {
+        (void)cudaGetLastError();
+        continue;                                              // portable plan: 8-CTA clusters, more points per thread
+      }
     }
+    const int rc = launch_fps_plan(p, xyz, offsets, idx, g, B, st);
+    if (rc == 0) ++g_vdetr_launches;
     if (rc == 0 || p.cluster <= 8) return rc;
     (void)cudaGetLastError();   // non-portable cluster refused: retry with the portable plan
   }
   return VDETR_ERR_UNSUPPORTED;
+}
+
+int vdetr_pn2_fps(const float* xyz, int B, int N, int M, int32_t* idx, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (B < 0 || N < 0 || M < 0) return VDETR_ERR_BAD_ARG;
+  if (B == 0 || M == 0) return 0;
+  if (N == 0 || !xyz || !idx) return VDETR_ERR_BAD_ARG;
+  return fps_dispatch(xyz, nullptr, B, make_geom(N, M), (size_t)B * N, idx, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t vdetr_pn2_fps_ragged_workspace_bytes(int B, int total_n, int max_n, int M) {
+  if (B <= 0 || total_n <= 0 || max_n <= 0 || M <= 0) return 0;
+  FpsGeom g = make_geom(max_n, M);
+  FpsPlan p = fps_plan(g, false);
+  return p.cluster == 0 ? (size_t)total_n * sizeof(float) : 0;
+}
+
+int vdetr_pn2_fps_ragged(const float* xyz, const int32_t* offsets, int B, int total_n, int max_n, int M, int32_t* idx,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || total_n < 0 || max_n < 0 || M < 0) return VDETR_ERR_BAD_ARG;
+  if (B == 0 || M == 0) return 0;
+  if (!xyz || !offsets || !idx || max_n == 0) return VDETR_ERR_BAD_ARG;
+  return fps_dispatch(xyz, offsets, B, make_geom(max_n, M), (size_t)total_n, idx, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 static inline dim3 rows_grid(int work, int C, int B) {

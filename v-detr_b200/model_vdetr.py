@@ -54,6 +54,7 @@ class ModelVDETR(nn.Module):
         self.npoint = npoint
         # the reference reads args.random_fps although main.py never defines it
         self.random_fps = getattr(args, "random_fps", False)
+        self.max_points_per_scene = getattr(args, "max_points_per_scene", None)     # bound for the sync-free ragged FPS
         self.use_color = getattr(args, "use_color", False)
         self.xyz_color = getattr(args, "xyz_color", False)
         self.hard_anchor = getattr(args, "hard_anchor", False)
@@ -103,25 +104,27 @@ class ModelVDETR(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def sample_backbone_output(self, coords, feats, num_sample):
+    def sample_backbone_output(self, coords, feats, num_sample, batch_size=None):
         """Per-scene FPS + gather on the sparse tensor's (batch_index, x, y, z) coordinates and features (:280-316).
-        Scenes with the same voxel count go through ONE batched kernel launch instead of the
-        reference's Python loop of B=1 calls; ragged batches are processed scene by scene."""
-        batch_ids = coords[:, 0]
-        nb = int(batch_ids.max().item()) + 1
-        xyz_all = coords[:, 1:].float() * self.voxel_size
-        per_scene = [torch.nonzero(batch_ids == b, as_tuple=False).squeeze(1) for b in range(nb)]
-        counts = {int(p.numel()) for p in per_scene}
-        if len(counts) == 1:
-            idx = torch.stack(per_scene)
-            xyz = xyz_all[idx]
-            f = feats[idx].transpose(1, 2).contiguous()
-            return self.fps_module(xyz.contiguous(), f, num_sample)
-        xs, fs, inds = [], [], []
-        for p in per_scene:
-            x, f, i = self.fps_module(xyz_all[p].unsqueeze(0).contiguous(), feats[p].t().unsqueeze(0).contiguous(), num_sample)
-            xs.append(x); fs.append(f); inds.append(i)
-        return torch.cat(xs), torch.cat(fs), torch.cat(inds)
+        The reference loops over the scenes in Python (torch.where + one B = 1 FPS launch + a host synchronisation per
+        scene).  Here the rows are grouped by scene with one stable sort, the per-scene offsets stay on the device, and ONE
+        ragged FPS launch samples every scene; the gathers are two index_select calls.  With
+        ``batch_size`` given and ``self.max_points_per_scene`` set (an upper bound of the voxel count of a scene) the call
+        does not synchronise with the host at all; otherwise the two numbers are read back once."""
+        if self.random_fps:
+            raise NotImplementedError("args.random_fps (a host-side randperm per scene, models/model_vdetr.py:299-303; never set by "
+                                      "main.py) is not implemented")
+        batch_ids = coords[:, 0].long()
+        nb = int(batch_size) if batch_size is not None else int(batch_ids.max().item()) + 1
+        order = torch.argsort(batch_ids, stable=True)                  # rows of scene b keep their relative order (torch.where)
+        offsets = torch.searchsorted(batch_ids[order], torch.arange(nb + 1, device=coords.device)).to(torch.int32)
+        max_n = self.max_points_per_scene if self.max_points_per_scene else int((offsets[1:] - offsets[:-1]).max().item())
+        xyz_sorted = (coords[order, 1:].float() * self.voxel_size).contiguous()
+        inds = pointnet2_utils._ext.furthest_point_sampling_ragged(xyz_sorted, offsets, num_sample, max_n)       # [B, M] scene-local
+        rows = order[(inds.long() + offsets[:-1, None].long()).reshape(-1)]                                       # rows of coords / feats
+        new_xyz = (coords[rows, 1:].float() * self.voxel_size).view(nb, num_sample, 3)
+        new_features = feats[rows].view(nb, num_sample, -1).transpose(1, 2).contiguous()
+        return new_xyz, new_features, inds
 
     def run_encoder(self, point_clouds):
         import MinkowskiEngine as ME
@@ -142,15 +145,22 @@ class ModelVDETR(nn.Module):
                 x = inputs[i]
             if i == self.layer_idx:
                 out = self.__getattr__(f"out_block_{i}")(x)
-        enc_xyz, enc_features, enc_inds = self.sample_backbone_output(out.C, out.F, self.npoint)
+        enc_xyz, enc_features, enc_inds = self.sample_backbone_output(out.C, out.F, self.npoint, batch_size=len(point_clouds))
         return enc_xyz, enc_features.permute(2, 0, 1), enc_inds
 
     def forward_from_backbone(self, enc_xyz, enc_features, enc_inds, point_cloud_dims):
         """Everything after ``run_encoder`` (:337-381).  enc_xyz [B,N,3], enc_features [N,B,C], enc_inds [B,N]."""
         bs, npoints, _ = enc_xyz.shape
-        enc_features = self.encoder_to_decoder_projection(enc_features.permute(1, 2, 0)).permute(2, 0, 1)
-        logits = self.decoder.pointcls_heads(enc_features.permute(1, 2, 0).contiguous()).transpose(1, 2) \
-            .reshape((bs, npoints, -1)).contiguous()
+        proj, cls = self.encoder_to_decoder_projection, self.decoder.pointcls_heads
+        if enc_features.is_cuda and proj.supports_tokens and cls.supports_tokens:
+            # [N,B,C] is already token-major: the Conv1d(k=1)-BN-ReLU stacks run as GEMMs + the fused BN kernels on the
+            # contiguous [N*B, C] rows, without the permuted copies (SURVEY 8f rank 4)
+            tok = proj.forward_tokens(enc_features.reshape(npoints * bs, -1))
+            enc_features = tok.view(npoints, bs, -1)
+            logits = cls.forward_tokens(tok).view(npoints, bs, -1).transpose(0, 1).contiguous()
+        else:
+            enc_features = proj(enc_features.permute(1, 2, 0)).permute(2, 0, 1)
+            logits = cls(enc_features.permute(1, 2, 0).contiguous()).transpose(1, 2).reshape((bs, npoints, -1)).contiguous()
         class_idx = logits.sigmoid().max(dim=-1)[1]
         sizes = self.dataset_config.mean_size_arr_hard_anchor if self.hard_anchor else self.dataset_config.mean_size_arr
         size_unnormalized = enc_features.new_tensor(sizes)[class_idx]

@@ -28,6 +28,25 @@ class _Ext:
         return out
 
     @staticmethod
+    def furthest_point_sampling_ragged(points, offsets, nsamples, max_n):
+        """points [total,3] f32, offsets [B+1] int32 (device), max_n = upper bound of the per-scene count (host int).
+        -> int32 [B, nsamples] of scene-local indices.  No counterpart in the reference's _ext: it replaces the per-scene
+        loop of B = 1 calls at models/model_vdetr.py:282-316."""
+        _C.require_cuda("points", points, torch.float32)
+        _C.require_cuda("offsets", offsets, torch.int32)
+        if points.dim() != 2 or points.shape[1] != 3 or offsets.dim() != 1 or offsets.numel() < 2:
+            raise RuntimeError("points must be [total,3] and offsets [B+1]")
+        B, total = offsets.numel() - 1, points.shape[0]
+        out = torch.zeros(B, nsamples, dtype=torch.int32, device=points.device)
+        L = _C.lib()
+        ws_bytes = L.vdetr_pn2_fps_ragged_workspace_bytes(B, total, int(max_n), nsamples)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=points.device) if ws_bytes else None
+        with torch.cuda.device(points.device):
+            _C.check(L.vdetr_pn2_fps_ragged(_C.ptr(points), _C.ptr(offsets), B, total, int(max_n), nsamples, _C.ptr(out),
+                                            _C.ptr(ws), ws_bytes, _C.stream_ptr()))
+        return out
+
+    @staticmethod
     def gather_points(points, idx):
         _C.require_cuda("points", points, torch.float32)
         _C.require_cuda("idx", idx, torch.int32)
