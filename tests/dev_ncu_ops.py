@@ -24,6 +24,9 @@ for it in range(2):
     if mode != "fwd":
         o.backward(torch.ones_like(o) * 1e-3)
 torch.cuda.synchronize()
+import ctypes
+from vdetr_b200 import _C
+_C.lib().vdetr_timing_enable(1)
 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
 a.record()
 for it in range(5):
@@ -32,9 +35,10 @@ for it in range(5):
         o.backward(torch.ones_like(o) * 1e-3)
 b.record(); torch.cuda.synchronize()
 print(mode, "B", B, "ms per call", a.elapsed_time(b) / 5)
+tot = (ctypes.c_float * 4)(); cnt = (ctypes.c_int * 4)()
+_C.lib().vdetr_timing_read(tot, cnt)
+print("kernel ms per launch:", {n: round(t / max(c, 1), 4) for n, t, c in zip(["fwd", "bwd_pass1", "dtables(all kernels)", "dkdv"], tot, cnt)})
 if os.environ.get("VDETR_DT_CLOCKS") == "1":
-    import ctypes
-    from vdetr_b200 import _C
     buf = (ctypes.c_ulonglong * 8)()
     _C.check(_C.lib().vdetr_debug_dt_clocks(buf))
     tot = sum(buf) or 1

@@ -93,7 +93,7 @@ def test_product_decoder_matches_reference_golden(name, seed, B, nK, nq, L, shar
             rel = np.abs(got - want).max() / (np.abs(want).max() + 1e-6)
             report.append((rel, li, k))
     _log(f"{name} worst output", max(r[0] for r in report))
-    bad = [r for r in report if r[0] > 6e-3]         # 6e-3 of the tensor's max after 2 layers (fp16 S / PV operands)
+    bad = [r for r in report if r[0] > 3e-3]         # 3e-3 of the tensor's max after 2 layers (measured: 1.9e-3 / 4e-4)
     assert not bad, "max |err| / max |ref| per (layer, output): " + ", ".join(f"l{li}.{k}={rel:.2e}" for rel, li, k in report)
 
 
@@ -130,10 +130,10 @@ def test_product_decoder_train_matches_reference_golden_gradients(monkeypatch):
     """Whole product path.  This golden case is deliberately harsh (random O(1) weights, |logits| up to 20, BatchNorm
     on 64 samples): the 1e-3 forward difference of the fp16 S/PV products moves the point at which the gradient is
     evaluated, and the gradient there differs by ~4 % although the backward kernels themselves are exact to 2e-3
-    (previous test).  Tolerance: 8 % of the tensor's max; loss 3 %."""
+    (previous test).  Tolerance: 8 % of the tensor's max (measured 3-7 %); loss 0.5 % (measured 0.2 %)."""
     gold = dict(np.load(os.path.join(G, "decoder_train.npz")))
     dec, feat, loss = _train_case(monkeypatch, 0, 0)
-    assert abs(loss.item() - float(gold["loss"])) <= 3e-2 * abs(float(gold["loss"])) + 1e-2, (loss.item(), float(gold["loss"]))
+    assert abs(loss.item() - float(gold["loss"])) <= 5e-3 * abs(float(gold["loss"])) + 1e-2, (loss.item(), float(gold["loss"]))
     g = feat.grad.cpu().numpy()
     _log("decoder_train loss (rel)", abs(loss.item() - float(gold["loss"])) / abs(float(gold["loss"])))
     _log("decoder_train dfeat", np.abs(g - gold["dfeat"]).max() / np.abs(gold["dfeat"]).max())
@@ -174,7 +174,7 @@ def test_product_decoder_vs_oracle_port_c1_size():
                 w = dw[k].numpy()
                 gg = dg[k].float().cpu().numpy()
                 _log(f"oracle-port B{B} nK{nK} layer {li} {k}", np.abs(gg - w).max() / (np.abs(w).max() + 1e-6))
-                tol = 6e-3 * (np.abs(w).max() + 1e-6)      # fp16 S / PV operands and fp16 tables, up to 2 layers deep
+                tol = (1e-3 if li <= 1 else 3e-3) * (np.abs(w).max() + 1e-6)      # 1e-3 through one decoder layer (north_star), 3e-3 after two
                 assert np.abs(gg - w).max() <= tol, f"B{B} layer {li} {k}: {np.abs(gg - w).max():.3e} > {tol:.3e}"
 
 

@@ -559,6 +559,10 @@ static_assert(NP % THREADS == 0 && (NP / 4) % THREADS == 0 && KC == THREADS, "un
 constexpr int XI = 12;                                   // x index values of a sort bin: cells 0..10, 11 = vertex A outside the table
 constexpr int SORT_PAD = 64;                             // dummy entries behind the sorted list (whole steps + the prefetch)
 constexpr int STAGE_BYTES = 3 * 32 * 16;                 // per warp: A weights, B weights, dS (16 B per pair each)
+#ifndef VDETR_DT4_CHUNK
+#define VDETR_DT4_CHUNK 4
+#endif
+constexpr int CHUNK = VDETR_DT4_CHUNK;                   // steps per unit of dynamically scheduled accumulate work
 
 __host__ __device__ inline int nbins_of(int n) { return (n + 1) * (n + 1) * XI * 4; }
 __host__ __device__ inline size_t region_bytes(int n) {
@@ -788,13 +792,15 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_mma_kernel(const Param
         if (bin >= 0) s_sorted[base + rank] = (uint16_t)(it * THREADS + tid);
       }
       if (tid < SORT_PAD) s_sorted[nsorted + tid] = (uint16_t)NP;
+      if (tid == 0) s_misc[1] = 0;                       // chunk counter of the accumulate phase
       __syncthreads();
       tick(4);
 
-      // ---- B4: accumulate.  Warp w owns the steps [s0, s1) of 32 sorted pairs.
+      // ---- B4: accumulate.  The sorted list is cut into chunks of CHUNK steps (32 pairs each) that the warps draw from a
+      // shared counter: the cost of a step depends on how many cells it straddles, and equal static shares left most
+      // warps waiting at the barrier for the few that own the fragmented end of the list.
       {
         const int steps = (nsorted + 31) >> 5;
-        const int s0 = (steps * warp) / WARPS, s1 = (steps * (warp + 1)) / WARPS;
         float* tabA = my_priv + (size_t)vertA * cells_pad * 4;
         float* tabB = my_priv + (size_t)vertB * cells_pad * 4;
         float d[4] = {0.f, 0.f, 0.f, 0.f};                 // d[0..1]: A's corner fg, heads 2ft, 2ft+1; d[2..3]: B's
@@ -808,6 +814,13 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_mma_kernel(const Param
         };
 
         const unsigned sely = ys ? 0x7432u : 0x7410u, selz = zs ? 0x7432u : 0x7410u;
+        for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(s_misc + 1, 1);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        const int s0 = chunk * CHUNK;
+        if (s0 >= steps) break;
+        const int s1 = min(steps, s0 + CHUNK);
         const uint16_t* sp = s_sorted + s0 * 32 + lane;
         unsigned ent_n = *sp;
         uint4 rec_n = s_recs[ent_n];
@@ -885,6 +898,8 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_mma_kernel(const Param
         }
         flush(curA, tabA, d[0], d[1]);
         flush(curB, tabB, d[2], d[3]);
+        curA = 0xFFFFu; curB = 0xFFFFu;
+        }
       }
       __syncthreads();                    // hist / sorted are rewritten by the next round
       tick(5);
