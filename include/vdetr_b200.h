@@ -197,6 +197,23 @@ int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, con
                             const float* gamma, int rows, int cols, int groups, long long group_stride, long long row_stride,
                             float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
 
+/* Box decode of one decoder level (models/vdetr_transformer.py:244-333 for num_angle_bin = 1, angle == 0): head outputs
+ * center_reg / size_reg [B,nQ,3] + the proposal boxes pre_*_normalized [B,nQ,3] + the scene extent dims_min / dims_max [B,3]
+ * -> center, center_normalized, size, size_normalized, pre_center, pre_size [B,nQ,3], the 8 camera-frame corners
+ * [B,nQ,8,3] (dataset_config.box_parametrization_to_corners, utils/box_util.py:294-358) and the lidar-frame corners
+ * (convert_corners_camera2lidar, :98-102) that are the next layer's reference_point.  One kernel per direction instead of
+ * ~35 elementwise launches.  Backward: gradients of center_reg / size_reg from the gradients of the five differentiable
+ * outputs (any of them may be NULL = zero); the proposal boxes and the scene extent receive no gradient (detached in the
+ * reference, :369-412). */
+int vdetr_box_decode_fwd(const float* center_reg, const float* size_reg, const float* pre_center_normalized,
+                         const float* pre_size_normalized, const float* dims_min, const float* dims_max, int B, int nQ,
+                         float* center, float* center_normalized, float* size, float* size_normalized, float* pre_center,
+                         float* pre_size, float* corners, float* ref_lidar, void* stream);
+int vdetr_box_decode_bwd(const float* size, const float* pre_size, const float* dims_min, const float* dims_max,
+                         const float* g_center, const float* g_center_normalized, const float* g_size,
+                         const float* g_size_normalized, const float* g_corners, int B, int nQ, float* g_center_reg,
+                         float* g_size_reg, void* stream);
+
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call
  * copies the 8 counters to the host and clears them (synchronises the device). */

@@ -248,3 +248,30 @@ def test_decoder_layer_return_attn_weights_path():
     for k in KEYS:
         w = o2["outputs"][k].float()
         assert (o1["outputs"][k].float() - w).abs().max().item() <= 2e-3 * (w.abs().max().item() + 1e-6), k
+
+
+def test_fused_box_decode_and_grouped_heads_equal_the_plain_paths():
+    """The fused box-decode kernel (csrc/boxdecode.cu) and the grouped evaluation of the 5 heads of a level against the
+    op-by-op PyTorch formulation of the same decoder: outputs, corners and the gradient of the encoder features."""
+    c = recipe.decoder_case(42, 2, 96)
+    results = {}
+    for fuse, group in ((True, True), (False, False)):
+        dec = build_product_decoder(2, 32, dropout=0.0, mlp_dropout=0.0)
+        _load(dec, 41)
+        dec = dec.cuda().train()
+        dec.fuse_box_decode, dec.group_heads = fuse, group
+        out, feat = _run_product(dec, c, True)
+        loss = odt.synthetic_loss(out) + sum(d["box_corners"].square().sum() + d["size_unnormalized"].sum()
+                                             for d in out["aux_outputs"] + [out["outputs"]])
+        loss.backward()
+        results[fuse] = (out, feat.grad.clone(), {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None})
+    (oa, ga, pa), (ob, gb, pb) = results[True], results[False]
+    for da, db in zip(oa["aux_outputs"] + [oa["outputs"]], ob["aux_outputs"] + [ob["outputs"]]):
+        assert "_reference_point_lidar" not in da
+        for k in KEYS + ("box_corners_axis_align", "pre_box_center_unnormalized", "pre_box_size_unnormalized"):
+            w = db[k].float()
+            assert (da[k].float() - w).abs().max().item() <= 2e-5 * (w.abs().max().item() + 1e-6), k
+    assert (ga - gb).abs().max().item() <= 1e-4 * gb.abs().max().item()
+    for n in pb:
+        if n.endswith("center_head.layers.8.weight") or n.endswith("size_head.layers.8.weight"):
+            assert (pa[n] - pb[n]).abs().max().item() <= 1e-4 * (pb[n].abs().max().item() + 1e-9), n

@@ -58,6 +58,8 @@ _SIGS = {
     "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong,
                                         c_float, c_float] + [c_void_p] * 7),
     "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong] + [c_void_p] * 5),
+    "vdetr_box_decode_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 8 + [c_void_p]),
+    "vdetr_box_decode_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int] + [c_void_p] * 2 + [c_void_p]),
     "vdetr_debug_dt_clocks": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "vdetr_rpe_dtables_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape)]),
     "vdetr_rpe_dtables": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),

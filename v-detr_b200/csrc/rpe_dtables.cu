@@ -909,6 +909,384 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_mma_kernel(const Param
 
 }  // namespace dt4
 
+// =====================================================================================================================
+// dt5 = dt4 with three changes that remove most of what dt4 spends outside the MMAs (ncu, profiles/r2_ncu_dtables.md):
+//   * vertex B (x-) accumulates into an x WINDOW: its 16 MMA rows are (4 (z,y) corners) x (4 consecutive x points).
+//     Inside one cell of vertex A the cell of B is x_A - delta with delta in {0,1,2} for all but a handful of pairs, so
+//     with the window based at x_A - 2 vertex B never changes accumulators inside A's segment: no masking, no extra
+//     flushes.  Two MMAs per 16 pairs (A: 8 rows used, B: 16 rows) instead of one plus masked repeats.
+//   * sort bins with >= 16 pairs ("large", 93 % of the pairs) are laid out first, each padded with dummy pairs to a
+//     multiple of 16: every 16-pair block of that region belongs to exactly one cell.  The other bins (and the rare pairs
+//     with delta > 2 or vertex A outside the table, class 1) follow unpadded and go through the masked path, with the
+//     window of B based at its own cell.
+//   * accumulate work is drawn in chunks from a shared counter (as dt4 after its first profile).
+namespace dt5 {
+
+using dt3::axis_rec;
+using dt3::FULL;
+using dt3::Params;
+using dt4::keep_halves;
+using dt4::ldmatrix_x2_trans;
+using dt4::ldmatrix_x4_trans;
+using dt4::mma_16816;
+using dt4::red_add_v2;
+using dt4::run_pack13;
+
+constexpr int QB = 12, KC = 512, NP = QB * KC;
+constexpr int THREADS = 512, WARPS = 16, ITEMS = NP / THREADS;
+constexpr int XI = 12;
+constexpr int SORT_CAP = NP + (NP / 16) * 15 + 128;      // large bins padded to 16 (at most NP/16 of them) + trailing dummies / prefetch
+constexpr int STAGE_BYTES = 4 * 32 * 16;                 // per warp: A weights | B window halves 0-7 | 8-15 | dS  (16 B per pair each)
+constexpr int CHUNK = VDETR_DT4_CHUNK;
+constexpr unsigned WILD = 0xFFFFu;
+static_assert((SORT_CAP * 2) % 16 == 0 && ((NP + 2) * 24) % 16 == 0, "16-byte alignment of the shared-memory regions");
+
+__host__ __device__ inline int nbins_of(int n) { return (n + 1) * (n + 1) * XI * 2; }
+__host__ __device__ inline size_t region_bytes(int n) {
+  const size_t r = ((size_t)nbins_of(n) + 1 + 3) / 4 * 16;
+  return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
+}
+__host__ __device__ inline size_t smem_bytes(int n) {
+  return (size_t)(NP + 2) * 24 + (size_t)SORT_CAP * 2 + region_bytes(n) + WARPS * STAGE_BYTES + QB * 2 * 16 + 64 * 4 + 64;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Params P) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint4* s_recs = reinterpret_cast<uint4*>(sm);                                     // [NP + 2], entry NP = dummy
+  uint2* s_dsv = reinterpret_cast<uint2*>(sm + (size_t)(NP + 2) * 16);
+  uint16_t* s_sorted = reinterpret_cast<uint16_t*>(sm + (size_t)(NP + 2) * 24);     // [SORT_CAP]
+  uint8_t* region = sm + (size_t)(NP + 2) * 24 + (size_t)SORT_CAP * 2;
+  int* s_hist = reinterpret_cast<int*>(region);                                     // [nbins + 1] counts -> cursors
+  float4* s_xyz = reinterpret_cast<float4*>(region);                                // [KC] phase A only (aliases hist)
+  uint8_t* s_stage = region + region_bytes(P.n);
+  float4* s_geo = reinterpret_cast<float4*>(s_stage + WARPS * STAGE_BYTES);         // [QB][2]
+  int* s_q = reinterpret_cast<int*>(s_geo + QB * 2);                                // [QB]
+  int* s_misc = s_q + 16;      // [0] end of the sorted list  [1] chunk counter  [2] end of the large region  [4..4+2*WARPS) scan scratch
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbins = nbins_of(P.n);
+  const int R = P.R;
+  const int cells_pad = P.P3 * P.P3 * P.P3;
+  float* my_priv = P.priv + (size_t)blockIdx.x * 8 * cells_pad * 4;
+  long long t_prev = clock64();
+  auto tick = [&](int phase) {
+    if (P.phase_clocks && tid == 0) {
+      const long long t = clock64();
+      atomicAdd(P.phase_clocks + phase, (unsigned long long)(t - t_prev));
+      t_prev = t;
+    }
+  };
+  const int fg = lane >> 2, ft = lane & 3;                        // fragment row / column pair of this lane
+  uint8_t* my_stage = s_stage + warp * STAGE_BYTES;
+  const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(my_stage);
+  // ldmatrix row addresses (+ 256 for the second 16-pair block of a step)
+  const uint32_t rowA = stage_u32 + (((lane >> 3) & 1) * 8 + (lane & 7)) * 16;                                      // x2: WA k0-7, k8-15
+  const uint32_t rowB = stage_u32 + 512 + ((lane >> 3) & 1) * 512 + (((lane >> 4) & 1) * 8 + (lane & 7)) * 16;     // x4: WB0 k0-7, WB1 k0-7, WB0 k8-15, WB1 k8-15
+  const uint32_t rowS = stage_u32 + 1536 + (((lane >> 3) & 1) * 8 + (lane & 7)) * 16;                              // x2: dS k0-7, k8-15
+
+  if (tid == 0) {
+    s_recs[NP] = make_uint4(0u, 0u, 0u, 0x000000FFu);
+    s_dsv[NP] = make_uint2(0u, 0u);
+  }
+
+  for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+    int r = u;
+    const int kc = r % P.kchunks; r /= P.kchunks;
+    const int qb = r % P.qblocks;
+    const int b = r / P.qblocks;
+    const int q0 = qb * QB, k0 = kc * KC;
+
+    __syncthreads();
+    if (tid < QB) {
+      const int qi = q0 + tid;
+      int q = -1;
+      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+      if (qi < P.nQ) {
+        q = __ldg(P.qperm + (size_t)b * P.nQ + qi);
+        const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
+        hi = __ldg(g); lo = __ldg(g + 1);
+        if (__float_as_int(hi.w) == 0) q = -1;                    // not axis aligned: handled by the dt3 kernel
+      }
+      s_geo[tid * 2] = hi; s_geo[tid * 2 + 1] = lo;
+      s_q[tid] = q;
+    }
+    for (int i = tid; i < KC; i += THREADS) {
+      float4 kx = make_float4(1e9f, 1e9f, 1e9f, 0.f);
+      if (k0 + i < P.nK) kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + i);
+      s_xyz[i] = kx;
+    }
+    __syncthreads();
+
+    // ---- phase A: records + dS (identical to dt4)
+    {
+      constexpr int KG = KC / 4, GI = NP / 4 / THREADS;
+#pragma unroll 1
+      for (int gi = 0; gi < GI; ++gi) {
+        const int g = gi * THREADS + tid, ql = g / KG, kl0 = (g % KG) * 4;
+        const int q = s_q[ql];
+        uint2 hd[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) hd[h] = make_uint2(0u, 0u);
+        const bool any = q >= 0 && k0 + kl0 < P.nK;
+        if (any) {
+          const __half* dp = P.dsb + ((size_t)b * P.nQp + q) * 4 * P.nKp + k0 + kl0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) hd[h] = __ldg(reinterpret_cast<const uint2*>(dp + (size_t)h * P.nKp));
+        }
+        const float4 hi = s_geo[ql * 2], lo = s_geo[ql * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kl = kl0 + j, p = ql * KC + kl;
+          uint4 rec = make_uint4(0u, 0u, 0u, 0x00FFFFFFu);
+          uint2 dv = make_uint2(0u, 0u);
+          if (any && k0 + kl < P.nK) {
+            const int sh = 16 * (j & 1);
+            const unsigned w0 = (j < 2) ? hd[0].x : hd[0].y, w1 = (j < 2) ? hd[1].x : hd[1].y;
+            const unsigned w2 = (j < 2) ? hd[2].x : hd[2].y, w3 = (j < 2) ? hd[3].x : hd[3].y;
+            dv = make_uint2(((w0 >> sh) & 0xFFFFu) | (((w1 >> sh) & 0xFFFFu) << 16), ((w2 >> sh) & 0xFFFFu) | (((w3 >> sh) & 0xFFFFu) << 16));
+            const float4 kx = s_xyz[kl];
+            unsigned nxp, nxm, nyp, nym, nzp, nzm, fxp, fxm, fyp, fym, fzp, fzm;
+            axis_rec(hi.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxp, fxp);
+            axis_rec(lo.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxm, fxm);
+            axis_rec(hi.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nyp, fyp);
+            axis_rec(lo.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nym, fym);
+            axis_rec(hi.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzp, fzp);
+            axis_rec(lo.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzm, fzm);
+            rec.x = fxp | (fxm << 16); rec.y = fyp | (fym << 16); rec.z = fzp | (fzm << 16);
+            rec.w = nxp | (nxm << 4) | (nyp << 8) | (nym << 12) | (nzp << 16) | (nzm << 20);
+          }
+          s_recs[p] = rec;
+          s_dsv[p] = dv;
+        }
+      }
+    }
+    __syncthreads();
+    tick(0);
+
+    for (int round = 0; round < 4; ++round) {
+      const int ys = round & 1, zs = (round < 2) ? 1 : 0;
+      const int vertA = (round < 2 ? 0 : 4) + ys, vertB = (round < 2 ? 3 : 7) - ys;
+      const int nby = 8 + 4 * ys, nbz = 16 + 4 * zs;
+
+      for (int i = tid; i <= nbins; i += THREADS) s_hist[i] = 0;
+      {                                   // the whole sorted array starts as dummy entries (padding of the large bins)
+        const uint32_t dd = (uint32_t)NP | ((uint32_t)NP << 16);
+        uint4* so = reinterpret_cast<uint4*>(s_sorted);
+        for (int i = tid; i < SORT_CAP / 8; i += THREADS) so[i] = make_uint4(dd, dd, dd, dd);
+      }
+      __syncthreads();
+      tick(1);
+
+      // ---- B1: histogram.  bin = (z, y, x_A | 11, class); class 0: A inside the table and B inside A's window (or outside
+      // the table: zero weights); class 1: everything else that touches the table.
+      unsigned myrun[ITEMS];
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const unsigned w = s_recs[it * THREADS + tid].w;
+        const int xa = w & 15, xb = (w >> 4) & 15, ny = (w >> nby) & 15, nz = (w >> nbz) & 15;
+        const bool a_ok = xa != 15, b_ok = xb != 15;
+        int bin = -1;
+        if (max(ny, nz) != 15 && (a_ok || b_ok)) {
+          const int cls = (a_ok && (!b_ok || (unsigned)(xa - xb) <= 2u)) ? 0 : 1;
+          bin = (((nz * R + ny) * XI + (a_ok ? xa : XI - 1)) << 1) | cls;
+        }
+        const unsigned rp = run_pack13(bin, lane);
+        myrun[it] = rp;
+        if ((rp & 0x3E000u) == 0u && bin >= 0) atomicAdd(s_hist + bin, (int)(rp >> 18));
+      }
+      __syncthreads();
+      tick(2);
+
+      // ---- B2: two exclusive scans in one pass: large class-0 bins (>= 16 pairs) padded to multiples of 16 first, the
+      // other bins behind them
+      {
+        const int per = (nbins + THREADS - 1) / THREADS;
+        const int lo = tid * per, hi = min(nbins, lo + per);
+        int mineL = 0, mineS = 0;
+        for (int i = lo; i < hi; ++i) {
+          const int c = s_hist[i];
+          if (c >= 16 && !(i & 1)) mineL += (c + 15) & ~15; else mineS += c;
+        }
+        int xL = mineL, xS = mineS;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int yL = __shfl_up_sync(FULL, xL, o), yS = __shfl_up_sync(FULL, xS, o);
+          if (lane >= o) { xL += yL; xS += yS; }
+        }
+        if (lane == 31) { s_misc[4 + warp] = xL; s_misc[4 + WARPS + warp] = xS; }
+        __syncthreads();
+        int baseL = 0, baseS = 0, totL = 0;
+        for (int w = 0; w < WARPS; ++w) {
+          if (w < warp) { baseL += s_misc[4 + w]; baseS += s_misc[4 + WARPS + w]; }
+          totL += s_misc[4 + w];
+        }
+        const int large_end = (totL + 31) & ~31;               // the masked region starts on a step boundary
+        int runL = baseL + xL - mineL, runS = large_end + baseS + xS - mineS;
+        for (int i = lo; i < hi; ++i) {
+          const int c = s_hist[i];
+          if (c >= 16 && !(i & 1)) { s_hist[i] = runL; runL += (c + 15) & ~15; }
+          else { s_hist[i] = runS; runS += c; }
+        }
+        if (tid == THREADS - 1) { s_misc[0] = runS; s_misc[2] = large_end; s_misc[1] = 0; }
+      }
+      __syncthreads();
+      tick(3);
+
+      // ---- B3: scatter
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const unsigned rp = myrun[it];
+        const int bin = (int)(rp & 0x1FFFu) - 1, rank = (int)((rp >> 13) & 31u);
+        int base = 0;
+        if (rank == 0 && bin >= 0) base = atomicAdd(s_hist + bin, (int)(rp >> 18));
+        base = __shfl_sync(FULL, base, lane - rank);
+        if (bin >= 0) s_sorted[base + rank] = (uint16_t)(it * THREADS + tid);
+      }
+      __syncthreads();
+      tick(4);
+
+      // ---- B4: accumulate
+      {
+        const int list_end = s_misc[0], large_steps = s_misc[2] >> 5;
+        const int steps = (list_end + 31) >> 5;
+        float* tabA = my_priv + (size_t)vertA * cells_pad * 4;
+        float* tabB = my_priv + (size_t)vertB * cells_pad * 4;
+        float dA[2] = {0.f, 0.f};                  // A: corner fg, heads 2ft, 2ft+1
+        float dB[4] = {0.f, 0.f, 0.f, 0.f};        // B window: rows fg and fg + 8 = ((z,y) corner, x slot)
+        unsigned curA = WILD, curB = WILD;         // cell keys nz << 8 | ny << 4 | x ; for B: x = window base + 2
+
+        auto flushA = [&]() {
+          if (curA != WILD) {
+            const int nx = curA & 15, ny = (curA >> 4) & 15, nz = (curA >> 8) & 15;
+            if (nx <= P.n && ft < 2 && (dA[0] != 0.f || dA[1] != 0.f))
+              red_add_v2(tabA + ((((nz + (fg >> 2)) * P.P3 + (ny + ((fg >> 1) & 1))) * P.P3 + (nx + (fg & 1))) << 2) + 2 * ft, dA[0], dA[1]);
+          }
+          dA[0] = 0.f; dA[1] = 0.f;
+        };
+        auto flushB = [&]() {
+          if (curB != WILD && ft < 2) {
+            const int xp = (int)(curB & 15) - 2 + (fg & 3), ny = (curB >> 4) & 15, nz = (curB >> 8) & 15;
+            if (xp >= 0 && xp < P.P3) {
+              const int zyc = fg >> 2;             // rows fg: (z,y) corners 0,1 ; rows fg + 8: corners 2,3 (z + 1)
+              float* a0 = tabB + ((((nz) * P.P3 + (ny + (zyc & 1))) * P.P3 + xp) << 2) + 2 * ft;
+              if (dB[0] != 0.f || dB[1] != 0.f) red_add_v2(a0, dB[0], dB[1]);
+              if (dB[2] != 0.f || dB[3] != 0.f) red_add_v2(a0 + ((P.P3 * P.P3) << 2), dB[2], dB[3]);
+            }
+          }
+          dB[0] = 0.f; dB[1] = 0.f; dB[2] = 0.f; dB[3] = 0.f;
+        };
+        auto mmaA = [&](uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+          float t[4] = {dA[0], dA[1], 0.f, 0.f};
+          mma_16816(t, a0, 0u, a2, 0u, b0, b1);
+          dA[0] = t[0]; dA[1] = t[1];
+        };
+
+        const unsigned sely = ys ? 0x7432u : 0x7410u, selz = zs ? 0x7432u : 0x7410u;
+        for (;;) {
+          int chunk = 0;
+          if (lane == 0) chunk = atomicAdd(s_misc + 1, 1);
+          chunk = __shfl_sync(FULL, chunk, 0);
+          const int s0 = chunk * CHUNK;
+          if (s0 >= steps) break;
+          const int s1 = min(steps, s0 + CHUNK);
+          const uint16_t* sp = s_sorted + s0 * 32 + lane;
+          unsigned ent_n = *sp;
+          uint4 rec_n = s_recs[ent_n];
+          uint2 dv_n = s_dsv[ent_n];
+          for (int st = s0; st < s1; ++st) {
+            const unsigned ent = ent_n;
+            const uint4 rec = rec_n;
+            const uint2 dv = dv_n;
+            sp += 32;
+            ent_n = *sp;
+            rec_n = s_recs[ent_n];
+            dv_n = s_dsv[ent_n];
+            const bool tail = st >= large_steps;             // warp-uniform: masked region, B's window based at its own cell
+
+            const unsigned xa = rec.w & 15u, xb = (rec.w >> 4) & 15u;
+            const unsigned zy = (((rec.w >> nbz) & 15u) << 8) | (((rec.w >> nby) & 15u) << 4);
+            const unsigned xa1 = xa == 15u ? 11u : xa;
+            unsigned keyA = zy | xa1, keyB = zy | (tail ? (xb == 15u ? 13u : xb + 2u) : xa1);
+            if (ent == (unsigned)NP) { keyA = WILD; keyB = WILD; }
+            const unsigned slot = (tail || xb == 15u) ? 0u : (2u - (xa - xb));        // class 0 in the large region: xa - xb in {0,1,2}
+            const float fz = fmaf(__uint_as_float(__byte_perm(rec.z, 0x4B000000u, selz)), 0x1p-16f, -128.f);
+            const float fy = fmaf(__uint_as_float(__byte_perm(rec.y, 0x4B000000u, sely)), 0x1p-16f, -128.f);
+            const float fa = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, 0x7410u)), 0x1p-16f, -128.f);
+            const float fb = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, 0x7432u)), 0x1p-16f, -128.f);
+            {
+              const float2 wy = make_float2(1.f - fy, fy);
+              const float2 z0 = dt3::fmul2(1.f - fz, wy), z1 = dt3::fmul2(fz, wy);
+              const float2 wa = xa == 15u ? make_float2(0.f, 0.f) : make_float2(1.f - fa, fa);
+              const float2 wb = xb == 15u ? make_float2(0.f, 0.f) : make_float2(1.f - fb, fb);
+              const float2 a01 = dt3::fmul2(z0.x, wa), a23 = dt3::fmul2(z0.y, wa), a45 = dt3::fmul2(z1.x, wa), a67 = dt3::fmul2(z1.y, wa);
+              const float2 b0 = dt3::fmul2(z0.x, wb), b1 = dt3::fmul2(z0.y, wb), b2 = dt3::fmul2(z1.x, wb), b3 = dt3::fmul2(z1.y, wb);
+              // B window row: halves [(z,y) corner j][x slot 0..3], the pair (x0, x1) of corner j sits at slots (slot, slot + 1)
+              const unsigned sh = 16u * slot;
+              const unsigned long long v0 = (unsigned long long)tc::pack_f16x2(b0.x, b0.y) << sh, v1 = (unsigned long long)tc::pack_f16x2(b1.x, b1.y) << sh;
+              const unsigned long long v2 = (unsigned long long)tc::pack_f16x2(b2.x, b2.y) << sh, v3 = (unsigned long long)tc::pack_f16x2(b3.x, b3.y) << sh;
+              __syncwarp();                                 // the previous step's ldmatrix reads are complete
+              uint4* stg = reinterpret_cast<uint4*>(my_stage);
+              stg[lane] = make_uint4(tc::pack_f16x2(a01.x, a01.y), tc::pack_f16x2(a23.x, a23.y), tc::pack_f16x2(a45.x, a45.y),
+                                     tc::pack_f16x2(a67.x, a67.y));
+              stg[32 + lane] = make_uint4((uint32_t)v0, (uint32_t)(v0 >> 32), (uint32_t)v1, (uint32_t)(v1 >> 32));
+              stg[64 + lane] = make_uint4((uint32_t)v2, (uint32_t)(v2 >> 32), (uint32_t)v3, (uint32_t)(v3 >> 32));
+              stg[96 + lane] = make_uint4(dv.x, dv.y, 0u, 0u);
+              __syncwarp();
+            }
+            // per 16-pair block: is it one cell for A and one window for B?  (dummy pairs match anything)
+            const unsigned refA = __shfl_sync(FULL, keyA, lane & 16), refB = __shfl_sync(FULL, keyB, lane & 16);
+            const unsigned eqA = __ballot_sync(FULL, keyA == refA || keyA == WILD), eqB = __ballot_sync(FULL, keyB == refB || keyB == WILD);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const unsigned kA = __shfl_sync(FULL, keyA, 16 * h), kB = __shfl_sync(FULL, keyB, 16 * h);
+              if (kA == WILD && ((eqA >> (16 * h)) & 0xFFFFu) == 0xFFFFu) continue;          // a block of dummy pairs only
+              uint32_t a0, a2, w0, w1, w2, w3, b0, b1;
+              ldmatrix_x2_trans(rowA + h * 256, a0, a2);
+              ldmatrix_x4_trans(rowB + h * 256, w0, w1, w2, w3);
+              ldmatrix_x2_trans(rowS + h * 256, b0, b1);
+              const bool uniA = kA != WILD && ((eqA >> (16 * h)) & 0xFFFFu) == 0xFFFFu;
+              const bool uniB = kB != WILD && ((eqB >> (16 * h)) & 0xFFFFu) == 0xFFFFu;
+              if (uniA && uniB) {
+                if (kA != curA) { flushA(); curA = kA; }
+                if (kB != curB) { flushB(); curB = kB; }
+                mmaA(a0, a2, b0, b1);
+                mma_16816(dB, w0, w1, w2, w3, b0, b1);
+                continue;
+              }
+              // a block that straddles cells (only behind the large region): one masked MMA per distinct key and vertex
+#pragma unroll 1
+              for (int v = 0; v < 2; ++v) {
+                const unsigned key = v ? keyB : keyA;
+                unsigned todo = __ballot_sync(FULL, key != WILD) & (0xFFFFu << (16 * h));
+                while (todo) {
+                  const int leader = __ffs(todo) - 1;
+                  const unsigned ksel = __shfl_sync(FULL, key, leader);
+                  const unsigned grp = __ballot_sync(FULL, key == ksel) & (0xFFFFu << (16 * h));
+                  todo &= ~grp;
+                  const unsigned bits = (grp >> (16 * h)) >> (2 * ft);
+                  if (v == 0) {
+                    if (ksel != curA) { flushA(); curA = ksel; }
+                    mmaA(keep_halves(a0, bits), keep_halves(a2, bits >> 8), b0, b1);
+                  } else {
+                    if (ksel != curB) { flushB(); curB = ksel; }
+                    mma_16816(dB, keep_halves(w0, bits), keep_halves(w1, bits), keep_halves(w2, bits >> 8), keep_halves(w3, bits >> 8), b0, b1);
+                  }
+                }
+              }
+            }
+          }
+          flushA(); flushB();
+          curA = WILD; curB = WILD;
+        }
+      }
+      __syncthreads();
+      tick(5);
+    }
+  }
+}
+
+}  // namespace dt5
+
 namespace dt3 {
 
 // sum of the per-CTA private tables, without the padding cells, times 1 / scale.  A CTA owns 32 consecutive output
@@ -1115,9 +1493,11 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   }();
   P.cost = cost;
   P.slow_count = slow_count;
-  // VDETR_DT_IMPL=3: the dt3 kernel for every query (the kernel of round 1); default: dt4 (tensor-core accumulation) for
-  // axis-aligned boxes + dt3 for the others (exits at once when there are none)
-  static const bool use_dt4 = []() { const char* e = getenv("VDETR_DT_IMPL"); return !(e && e[0] == '3'); }();
+  // VDETR_DT_IMPL=3: the dt3 kernel for every query (the kernel of round 1); 4: dt4 (tensor-core accumulation, B masked);
+  // default 5: dt5 (x window for vertex B, padded large bins) for axis-aligned boxes + dt3 for the others (exits at once
+  // when there are none)
+  static const int impl = []() { const char* e = getenv("VDETR_DT_IMPL"); return (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 5; }();
+  const bool use_dt4 = impl >= 4;
   P.only_slow = use_dt4 ? 1 : 0;
   const int grid3 = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
   dt3::Params P4 = P;
@@ -1125,7 +1505,7 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   P4.kchunks = (s->nK + dt4::KC - 1) / dt4::KC;
   P4.units = s->B * P4.qblocks * P4.kchunks;
   const int grid4 = P4.units < vdetr_num_sms() ? P4.units : vdetr_num_sms();
-  const size_t smem4 = dt4::smem_bytes(n);
+  const size_t smem4 = impl == 5 ? dt5::smem_bytes(n) : dt4::smem_bytes(n);
   if (use_dt4 && smem4 > 232448) return VDETR_ERR_UNSUPPORTED;
   const int copies = (use_dt4 && grid4 > grid3) ? grid4 : grid3;
   const size_t copy_bytes = (size_t)8 * P.P3 * P.P3 * P.P3 * 4 * sizeof(float);
@@ -1135,7 +1515,11 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   VDETR_CUDA_TRY(cudaMemsetAsync(slow_count, 0, sizeof(int), st));
   dt3::rpe_dtables_qorder_kernel<<<s->B, 1024, 0, st>>>(geo, s->nQ, nQp, qperm, slow_count);
   VDETR_LAUNCH_CHECK();
-  if (use_dt4) {
+  if (impl == 5) {
+    VDETR_CUDA_TRY(cudaFuncSetAttribute(dt5::rpe_dtables_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    dt5::rpe_dtables_win_kernel<<<grid4, dt5::THREADS, smem4, st>>>(P4);
+    VDETR_LAUNCH_CHECK();
+  } else if (impl == 4) {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(dt4::rpe_dtables_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
     dt4::rpe_dtables_mma_kernel<<<grid4, dt4::THREADS, smem4, st>>>(P4);
     VDETR_LAUNCH_CHECK();

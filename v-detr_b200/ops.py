@@ -359,3 +359,49 @@ def linear(x, weight, bias=None):
             and (x.requires_grad or weight.requires_grad) and x.shape[-1] == weight.shape[1]):
         return _TokenLinear.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)
+
+
+class _BoxDecode(Function):
+    """models/vdetr_transformer.py:244-333 for angle == 0 in one kernel per direction (csrc/boxdecode.cu)."""
+
+    @staticmethod
+    def forward(ctx, center_reg, size_reg, pre_cn, pre_sn, lo, hi):
+        B, nQ, _ = center_reg.shape
+        mk = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=center_reg.device)      # noqa: E731
+        center, center_norm, size, size_norm, pre_center, pre_size = (mk(B, nQ, 3) for _ in range(6))
+        corners, ref_lidar = mk(B, nQ, 8, 3), mk(B, nQ, 8, 3)
+        with torch.cuda.device(center_reg.device):
+            _C.check(_C.lib().vdetr_box_decode_fwd(_C.ptr(center_reg), _C.ptr(size_reg), _C.ptr(pre_cn), _C.ptr(pre_sn), _C.ptr(lo),
+                                                   _C.ptr(hi), B, nQ, _C.ptr(center), _C.ptr(center_norm), _C.ptr(size),
+                                                   _C.ptr(size_norm), _C.ptr(pre_center), _C.ptr(pre_size), _C.ptr(corners),
+                                                   _C.ptr(ref_lidar), _C.stream_ptr()))
+        ctx.save_for_backward(size, pre_size, lo, hi)
+        ctx.mark_non_differentiable(pre_center, pre_size, ref_lidar)
+        return center, center_norm, size, size_norm, corners, pre_center, pre_size, ref_lidar
+
+    @staticmethod
+    def backward(ctx, g_center, g_center_norm, g_size, g_size_norm, g_corners, _g5, _g6, _g7):
+        size, pre_size, lo, hi = ctx.saved_tensors
+        B, nQ, _ = size.shape
+        c = lambda t: None if t is None else t.contiguous()      # noqa: E731
+        g_center, g_center_norm, g_size, g_size_norm, g_corners = (c(t) for t in (g_center, g_center_norm, g_size, g_size_norm, g_corners))
+        d_center_reg, d_size_reg = torch.empty_like(size), torch.empty_like(size)
+        with torch.cuda.device(size.device):
+            _C.check(_C.lib().vdetr_box_decode_bwd(_C.ptr(size), _C.ptr(pre_size), _C.ptr(lo), _C.ptr(hi), _C.ptr(g_center),
+                                                   _C.ptr(g_center_norm), _C.ptr(g_size), _C.ptr(g_size_norm), _C.ptr(g_corners), B, nQ,
+                                                   _C.ptr(d_center_reg), _C.ptr(d_size_reg), _C.stream_ptr()))
+        return d_center_reg, d_size_reg, None, None, None, None
+
+
+def box_decode_supported(center_reg, size_reg, pre_cn, pre_sn, lo, hi) -> bool:
+    ts = (center_reg, size_reg, pre_cn, pre_sn, lo, hi)
+    return all(t.is_cuda and t.dtype == torch.float32 for t in ts) and center_reg.dim() == 3 and center_reg.shape[-1] == 3 \
+        and size_reg.shape == center_reg.shape and pre_cn.shape == center_reg.shape and pre_sn.shape == center_reg.shape \
+        and tuple(lo.shape) == (center_reg.shape[0], 3) and tuple(hi.shape) == (center_reg.shape[0], 3)
+
+
+def box_decode(center_reg, size_reg, pre_center_normalized, pre_size_normalized, dims_min, dims_max):
+    """-> center, center_normalized, size, size_normalized, corners (camera frame), pre_center, pre_size, ref_lidar.
+    Gradients flow to center_reg / size_reg only (the proposals and the scene extent are detached in the reference)."""
+    return _BoxDecode.apply(center_reg.contiguous(), size_reg.contiguous(), pre_center_normalized.detach().contiguous(),
+                            pre_size_normalized.detach().contiguous(), dims_min.detach().contiguous(), dims_max.detach().contiguous())

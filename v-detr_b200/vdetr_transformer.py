@@ -511,6 +511,9 @@ class TransformerDecoder(nn.Module):
         self.sort_keys = True       # Morton-order the key tokens once per forward (see module docstring)
         self.parallel_heads = os.environ.get("VDETR_B200_PARALLEL_HEADS", "1") != "0"
         self.group_heads = os.environ.get("VDETR_B200_GROUP_HEADS", "1") != "0"
+        self.fuse_box_decode = os.environ.get("VDETR_B200_FUSE_BOX_DECODE", "1") != "0"
+        # the fused box decode hard-codes utils/box_util.py:294-358 (what both dataset configs of the reference use)
+        self.standard_corners = type(dataset_config).__name__ in ("ScanNetBoxConfig", "ScannetDatasetConfig", "SunrgbdDatasetConfig")
 
     def _head_factory(self, decoder_dim, mlp_dropout):
         return partial(GenericMLP, norm_fn_name=self.mlp_norm, activation=self.mlp_act, use_conv=True,
@@ -645,24 +648,34 @@ class TransformerDecoder(nn.Module):
         origin = lo.unsqueeze(1)
         raw = self._run_heads(heads, box_features)
         cls_logits = raw["sem_cls_head"]
-        pre_center = pre_center_normalized * scene + origin
-        pre_size = pre_size_normalized * scene
         center_reg = raw["center_head"].contiguous()
-        center = center_reg * pre_size + pre_center
-        center_norm = (center - origin) / scene
         size_reg = raw["size_head"].contiguous()
-        size = torch.exp(size_reg) * pre_size
-        size_norm = size / scene
         angle_logits = raw["angle_cls_head"]
         angle_res_norm = raw["angle_residual_head"]
         angle_res = angle_res_norm * (np.pi / angle_res_norm.shape[-1])
         angle, angle_prob = self.box_processor.compute_predicted_angle(angle_logits, angle_res)
-        corners = self.box_processor.box_parametrization_to_corners(center, size, angle)
-        angle0, _ = self.box_processor.compute_predicted_angle(angle_logits, angle_res, zero_angle=True)
-        corners0 = self.box_processor.box_parametrization_to_corners(center, size, angle0)
+        ref_lidar = None
+        if (self.fuse_box_decode and angle_logits.shape[-1] == 1 and self.standard_corners
+                and ops.box_decode_supported(center_reg, size_reg, pre_center_normalized, pre_size_normalized, lo, hi)):
+            # num_angle_bin == 1: the angle is identically zero (:49-59), rotated and axis-aligned corners coincide, and the
+            # whole decode is one kernel (csrc/boxdecode.cu); it also leaves the next layer's lidar-frame reference_point
+            center, center_norm, size, size_norm, corners, pre_center, pre_size, ref_lidar = ops.box_decode(
+                center_reg, size_reg, pre_center_normalized, pre_size_normalized, lo, hi)
+            corners0 = corners
+        else:
+            pre_center = pre_center_normalized * scene + origin
+            pre_size = pre_size_normalized * scene
+            center = center_reg * pre_size + pre_center
+            center_norm = (center - origin) / scene
+            size = torch.exp(size_reg) * pre_size
+            size_norm = size / scene
+            corners = self.box_processor.box_parametrization_to_corners(center, size, angle)
+            angle0, _ = self.box_processor.compute_predicted_angle(angle_logits, angle_res, zero_angle=True)
+            corners0 = self.box_processor.box_parametrization_to_corners(center, size, angle0)
         with torch.no_grad():
             semcls_prob, objectness = self.box_processor.compute_objectness_and_cls_prob(cls_logits)
-        return {"sem_cls_logits": cls_logits, "center_normalized": center_norm.contiguous(),
+        extra = {} if ref_lidar is None else {"_reference_point_lidar": ref_lidar}      # popped by forward()
+        return {**extra, "sem_cls_logits": cls_logits, "center_normalized": center_norm.contiguous(),
                 "center_unnormalized": center, "size_normalized": size_norm, "size_unnormalized": size,
                 "angle_logits": angle_logits, "angle_prob": angle_prob, "angle_residual": angle_res,
                 "angle_residual_normalized": angle_res_norm, "angle_continuous": angle,
@@ -679,6 +692,8 @@ class TransformerDecoder(nn.Module):
             0, query_xyz, point_cloud_dims, self.norm(output),
             pre_center_normalized=enc_box_predictions["center_normalized"],
             pre_size_normalized=enc_box_predictions["size_normalized"])
+        pred.pop("_reference_point_lidar", None)
+        ref_lidar = None
         if self.return_intermediate:
             preds.append(pred)
         score = pred["objectness_prob"].clone().detach()
@@ -716,7 +731,8 @@ class TransformerDecoder(nn.Module):
 
         for idx, layer in enumerate(self.layers):
             if idx > 0:
-                reference_point = convert_corners_camera2lidar(pred["box_corners"].clone().detach())
+                reference_point = ref_lidar if ref_lidar is not None else \
+                    convert_corners_camera2lidar(pred["box_corners"].clone().detach())
                 reference_center = pred["center_unnormalized"].clone().detach()
                 reference_size = pred["size_unnormalized"].clone().detach()
                 reference_angle = pred["angle_continuous"].clone().detach()
@@ -731,6 +747,7 @@ class TransformerDecoder(nn.Module):
             pred = self.get_proposal_box_predictions_refine(
                 idx + 1, query_xyz, point_cloud_dims, self.norm(output),
                 pre_center_normalized=proposal_center_normalized, pre_size_normalized=proposal_size_normalized)
+            ref_lidar = pred.pop("_reference_point_lidar", None)      # lidar-frame corners left by the fused box decode
             if self.return_intermediate:
                 preds.append(pred)
             if return_attn_weights:
