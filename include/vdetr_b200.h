@@ -188,14 +188,18 @@ int vdetr_colsum(const float* x, int rows, int cols, float* out, float* workspac
  * gamma, beta, mean, rstd, running_mean, running_var, dgamma, dbeta are [groups * cols].  Batch statistics over the rows;
  * running_mean / running_var (may be NULL) are updated in place with `momentum` and the unbiased variance, like
  * nn.BatchNorm1d.  y is the forward output (its sign is the ReLU mask).  cols: vdetr_bn_relu_supported (128, 256, 384,
- * 512).  workspace (both directions): vdetr_reduce_workspace_floats(groups * cols) floats. */
+ * 512).  workspace (both directions): vdetr_reduce_workspace_floats(groups * cols) floats.
+ * dropout_p > 0 fuses the nn.Dropout that follows the ReLU in the reference's stacks (models/helpers.py:118-120,
+ * --mlp_dropout): y = relu(bn(x)) * keep / (1 - p) with a Philox mask from the 64-bit seed at the DEVICE pointer
+ * dropout_seed; the backward takes the same dropout_p and needs no mask (a dropped element is stored as 0). */
 int vdetr_bn_relu_supported(int cols);
 int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, int groups,
-                            long long group_stride, long long row_stride, float eps, float momentum, float* y, float* mean,
-                            float* rstd, float* running_mean, float* running_var, float* workspace, void* stream);
+                            long long group_stride, long long row_stride, float eps, float momentum, float dropout_p,
+                            const uint64_t* dropout_seed, float* y, float* mean, float* rstd, float* running_mean,
+                            float* running_var, float* workspace, void* stream);
 int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
                             const float* gamma, int rows, int cols, int groups, long long group_stride, long long row_stride,
-                            float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
+                            float dropout_p, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
 
 /* Box decode of one decoder level (models/vdetr_transformer.py:244-333 for num_angle_bin = 1, angle == 0): head outputs
  * center_reg / size_reg [B,nQ,3] + the proposal boxes pre_*_normalized [B,nQ,3] + the scene extent dims_min / dims_max [B,3]

@@ -574,3 +574,37 @@ def test_reductions_are_bit_reproducible():
             base = cur
         for a_, c_ in zip(base, cur):
             assert torch.equal(a_, c_)
+
+
+def test_bn_relu_dropout_fusion():
+    """Dropout fused into the BatchNorm+ReLU kernels (models/helpers.py:118-120): outputs are 0 or relu(bn(x)) / (1 - p), the
+    keep rate is 1 - p, and the backward (which stores no mask) equals autograd with the mask read off the output."""
+    from vdetr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rows, cols, p = 4096, 256, 0.3
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 1.0).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(cols).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(cols, device="cuda", generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(cols, device="cuda", generator=g) * 0.3)
+    dy = torch.randn(rows, cols, device="cuda", generator=g)
+    y0 = ops.bn_relu_train(x, bn, 0.0).detach()
+    torch.manual_seed(5)
+    y1 = ops.bn_relu_train(x, bn, p)
+    act = y0 > 0
+    kept = (y1 != 0) & act
+    assert torch.all((y1 == 0) | kept)
+    assert torch.allclose(y1[kept], y0[kept] / (1 - p), rtol=1e-6, atol=1e-7)
+    rate = kept.sum().item() / act.sum().item()
+    assert abs(rate - (1 - p)) < 5e-3, rate
+    gg = torch.autograd.grad(y1, (x, bn.weight, bn.bias), dy)
+    ref = torch.nn.BatchNorm1d(cols).cuda().double().train()
+    ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    xd = x.detach().double().requires_grad_(True)
+    want = torch.relu(ref(xd)) * kept.double() / (1 - p)
+    gw = torch.autograd.grad(want, (xd, ref.weight, ref.bias), dy.double())
+    for a, r, name in zip(gg, gw, ("dx", "dgamma", "dbeta")):
+        assert (a.double() - r).abs().max().item() <= 2e-4 * r.abs().max().item() + 1e-6, name
+    torch.manual_seed(6)
+    y2 = ops.bn_relu_train(x, bn, p)
+    assert not torch.equal(y2, y1)                      # a fresh seed per call

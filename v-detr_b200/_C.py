@@ -56,8 +56,9 @@ _SIGS = {
     "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vdetr_bn_relu_supported": (c_int, [c_int]),
     "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong,
-                                        c_float, c_float] + [c_void_p] * 7),
-    "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong] + [c_void_p] * 5),
+                                        c_float, c_float, c_float, c_void_p] + [c_void_p] * 7),
+    "vdetr_bn_relu_train_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong, c_float] +
+                                [c_void_p] * 5),
     "vdetr_box_decode_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 8 + [c_void_p]),
     "vdetr_box_decode_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int] + [c_void_p] * 2 + [c_void_p]),
     "vdetr_debug_dt_clocks": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),

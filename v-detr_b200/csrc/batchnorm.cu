@@ -7,13 +7,17 @@
 //   apply   : y = relu((x - mean) * rstd * gamma + beta); block 0 also updates running_mean / running_var (unbiased)
 //   bwd sums: dbeta = sum g, dgamma = sum g * xhat with g = dy * [y > 0]  (the two column sums the input gradient needs)
 //   bwd dx  : dx = gamma * rstd * (g - dbeta / T - xhat * dgamma / T)
-// Stock PyTorch runs 3 kernels forward (statistics, transform, ReLU) and 3 backward; here the ReLU rides along.
+// Stock PyTorch runs 3 kernels forward (statistics, transform, ReLU) and 3 backward; here the ReLU rides along -- and so
+// does the nn.Dropout that follows it in the reference's stacks (models/helpers.py:118-120, --mlp_dropout 0.3): the apply
+// kernel multiplies by keep / (1 - p) (Philox mask, philox.cuh), and because a dropped or clipped element is stored as 0 the
+// backward needs no mask at all: g = dy * [y > 0] / (1 - p).
 // Several independent BatchNorm layers of the same width are normalised by ONE launch (the 5 box heads of a decoder level
 // evaluated together): blockIdx.y = group; element (row r, group g, channel c) is x[g * group_stride + r * row_stride + c],
 // which covers both the channels-last [tokens, G * C] output of a concatenated GEMM and the head-major [G, tokens, C]
 // output of a batched one.  gs4 / ld4 below are group_stride / 4 and row_stride / 4.
 #include "common.cuh"
 #include "det_reduce.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -79,9 +83,16 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const floa
                                                                       const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                       float eps, float momentum, float4* __restrict__ y,
                                                                       float* __restrict__ mean, float* __restrict__ rstd,
-                                                                      float* running_mean, float* running_var, int ld4, size_t gs4) {
+                                                                      float* running_mean, float* running_var, int ld4, size_t gs4,
+                                                                      uint32_t drop_thresh, float inv_keep,
+                                                                      const unsigned long long* __restrict__ drop_seed) {
   constexpr int C4 = VEC * 32, C = C4 * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2 dkey = make_uint2(0u, 0u);
+  if (drop_thresh) {
+    const unsigned long long sd = __ldg(drop_seed);
+    dkey = make_uint2((uint32_t)sd, (uint32_t)(sd >> 32));
+  }
   x += blockIdx.y * gs4; y += blockIdx.y * gs4; gamma += blockIdx.y * C4; beta += blockIdx.y * C4;
   sum += blockIdx.y * C; sumsq += blockIdx.y * C; mean += blockIdx.y * C; rstd += blockIdx.y * C;
   if (running_mean) { running_mean += blockIdx.y * C; running_var += blockIdx.y * C; }
@@ -114,12 +125,22 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const floa
   }
   (void)C;
   for (int r = blockIdx.x * BN_WARPS + warp; r < rows; r += gridDim.x * BN_WARPS) {
+    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float4 v = x[(size_t)r * ld4 + i * 32 + lane];
-      y[(size_t)r * ld4 + i * 32 + lane] =
-          make_float4(fmaxf(fmaf(v.x, sc[i].x, sh[i].x), 0.f), fmaxf(fmaf(v.y, sc[i].y, sh[i].y), 0.f),
-                      fmaxf(fmaf(v.z, sc[i].z, sh[i].z), 0.f), fmaxf(fmaf(v.w, sc[i].w, sh[i].w), 0.f));
+      float4 o = make_float4(fmaxf(fmaf(v.x, sc[i].x, sh[i].x), 0.f), fmaxf(fmaf(v.y, sc[i].y, sh[i].y), 0.f),
+                             fmaxf(fmaf(v.z, sc[i].z, sh[i].z), 0.f), fmaxf(fmaf(v.w, sc[i].w, sh[i].w), 0.f));
+      if (drop_thresh) {
+        // one Philox call = eight 16-bit numbers = the two float4 (i even / odd) of this lane; counter = (row, group, column pair)
+        if ((i & 1) == 0) rnd = philox::philox4x32_10(make_uint4((uint32_t)r, blockIdx.y, (uint32_t)((i >> 1) * 32 + lane), 0x42u), dkey);
+        const uint32_t w0 = (i & 1) ? rnd.z : rnd.x, w1 = (i & 1) ? rnd.w : rnd.y;
+        o.x = (w0 & 0xFFFFu) >= drop_thresh ? o.x * inv_keep : 0.f;
+        o.y = (w0 >> 16) >= drop_thresh ? o.y * inv_keep : 0.f;
+        o.z = (w1 & 0xFFFFu) >= drop_thresh ? o.z * inv_keep : 0.f;
+        o.w = (w1 >> 16) >= drop_thresh ? o.w * inv_keep : 0.f;
+      }
+      y[(size_t)r * ld4 + i * 32 + lane] = o;
     }
   }
 }
@@ -130,7 +151,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                     float* __restrict__ part, unsigned* __restrict__ ticket, int ld4,
-                                                                    size_t gs4) {
+                                                                    size_t gs4, float inv_keep) {
   constexpr int C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   dy += blockIdx.y * gs4; y += blockIdx.y * gs4; x += blockIdx.y * gs4;
@@ -149,7 +170,8 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_sums_kernel(const float4
     for (int i = 0; i < VEC; ++i) {
       const size_t o = (size_t)r * ld4 + i * 32 + lane;
       const float4 d = dy[o], yy = y[o], xv = x[o];
-      const float gx = yy.x > 0.f ? d.x : 0.f, gy = yy.y > 0.f ? d.y : 0.f, gz = yy.z > 0.f ? d.z : 0.f, gw = yy.w > 0.f ? d.w : 0.f;
+      const float gx = yy.x > 0.f ? d.x * inv_keep : 0.f, gy = yy.y > 0.f ? d.y * inv_keep : 0.f;
+      const float gz = yy.z > 0.f ? d.z * inv_keep : 0.f, gw = yy.w > 0.f ? d.w * inv_keep : 0.f;
       ab[i].x += gx; ab[i].y += gy; ab[i].z += gz; ab[i].w += gw;
       ag[i].x += gx * (xv.x - mu[i].x) * rs[i].x; ag[i].y += gy * (xv.y - mu[i].y) * rs[i].y;
       ag[i].z += gz * (xv.z - mu[i].z) * rs[i].z; ag[i].w += gw * (xv.w - mu[i].w) * rs[i].w;
@@ -164,7 +186,7 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* 
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float4* __restrict__ gamma, const float* __restrict__ dgamma,
                                                                   const float* __restrict__ dbeta, float4* __restrict__ dx, int ld4,
-                                                                  size_t gs4) {
+                                                                  size_t gs4, float inv_keep) {
   constexpr int C4 = VEC * 32, C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   dy += blockIdx.y * gs4; y += blockIdx.y * gs4; x += blockIdx.y * gs4; dx += blockIdx.y * gs4; gamma += blockIdx.y * C4;
@@ -187,7 +209,8 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* 
     for (int i = 0; i < VEC; ++i) {
       const size_t o = (size_t)r * ld4 + i * 32 + lane;
       const float4 d = dy[o], yy = y[o], xv = x[o];
-      const float gx = yy.x > 0.f ? d.x : 0.f, gy = yy.y > 0.f ? d.y : 0.f, gz = yy.z > 0.f ? d.z : 0.f, gw = yy.w > 0.f ? d.w : 0.f;
+      const float gx = yy.x > 0.f ? d.x * inv_keep : 0.f, gy = yy.y > 0.f ? d.y * inv_keep : 0.f;
+      const float gz = yy.z > 0.f ? d.z * inv_keep : 0.f, gw = yy.w > 0.f ? d.w * inv_keep : 0.f;
       dx[o] = make_float4(k1[i].x * gx - k2[i].x - (xv.x - mu[i].x) * rs[i].x * k3[i].x,
                           k1[i].y * gy - k2[i].y - (xv.y - mu[i].y) * rs[i].y * k3[i].y,
                           k1[i].z * gz - k2[i].z - (xv.z - mu[i].z) * rs[i].z * k3[i].z,
@@ -212,7 +235,8 @@ struct BnLayout {
 
 template <int VEC>
 int fwd_t(const float* x, const float* gamma, const float* beta, int rows, const BnLayout& L, float eps, float momentum, float* y,
-          float* mean, float* rstd, float* running_mean, float* running_var, float* ws, cudaStream_t st) {
+          float* mean, float* rstd, float* running_mean, float* running_var, float* ws, float drop_p,
+          const unsigned long long* drop_seed, cudaStream_t st) {
   const int cols = VEC * 128 * L.groups, ld4 = (int)(L.row_stride / 4);
   const size_t gs4 = L.group_stride / 4;
   float* part = ws + 2 * cols;
@@ -223,13 +247,15 @@ int fwd_t(const float* x, const float* gamma, const float* beta, int rows, const
   VDETR_LAUNCH_CHECK();
   bn_apply_relu_kernel<VEC><<<dim3(bn_grid(rows, 2), L.groups), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(x), rows, ws, ws + cols, reinterpret_cast<const float4*>(gamma),
-      reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var, ld4, gs4);
+      reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var, ld4, gs4,
+      drop_p > 0.f ? philox::thresh_of(drop_p) : 0u, 1.0f / (1.0f - drop_p), drop_seed);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
 template <int VEC>
 int bwd_t(const float* dy, const float* y, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
-          const BnLayout& L, float* dx, float* dgamma, float* dbeta, float* ws, cudaStream_t st) {
+          const BnLayout& L, float* dx, float* dgamma, float* dbeta, float* ws, float drop_p, cudaStream_t st) {
+  const float inv_keep = 1.0f / (1.0f - drop_p);
   const int cols = VEC * 128 * L.groups, ld4 = (int)(L.row_stride / 4);
   const size_t gs4 = L.group_stride / 4;
   float* part = ws + 2 * cols;
@@ -237,11 +263,11 @@ int bwd_t(const float* dy, const float* y, const float* x, const float* mean, co
   VDETR_CUDA_TRY(cudaMemsetAsync(tickets, 0, 32 * sizeof(unsigned), st));
   bn_bwd_sums_kernel<VEC><<<dim3(bn_red_grid(rows), L.groups), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
-      dgamma, dbeta, part, tickets, ld4, gs4);
+      dgamma, dbeta, part, tickets, ld4, gs4, inv_keep);
   VDETR_LAUNCH_CHECK();
   bn_bwd_dx_kernel<VEC><<<dim3(bn_grid(rows, 2), L.groups), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
-      reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx), ld4, gs4);
+      reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx), ld4, gs4, inv_keep);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
@@ -260,32 +286,36 @@ int vdetr_bn_relu_supported(int cols) { return cols == 128 || cols == 256 || col
 size_t vdetr_reduce_workspace_floats(int cols) { return cols > 0 ? vdetr_reduce_ws_floats(cols) : 0; }
 
 int vdetr_bn_relu_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int cols, int groups,
-                            long long group_stride, long long row_stride, float eps, float momentum, float* y, float* mean,
-                            float* rstd, float* running_mean, float* running_var, float* workspace, void* stream) {
+                            long long group_stride, long long row_stride, float eps, float momentum, float dropout_p,
+                            const uint64_t* dropout_seed, float* y, float* mean, float* rstd, float* running_mean,
+                            float* running_var, float* workspace, void* stream) {
   if (rows < 1 || !vdetr_bn_relu_supported(cols) || !layout_ok(cols, groups, group_stride, row_stride)) return VDETR_ERR_UNSUPPORTED;
   if (!x || !gamma || !beta || !y || !mean || !rstd || !workspace) return VDETR_ERR_BAD_ARG;
+  if (!(dropout_p >= 0.f) || dropout_p >= 1.f || (dropout_p > 0.f && !dropout_seed)) return VDETR_ERR_BAD_ARG;
+  const unsigned long long* seed = reinterpret_cast<const unsigned long long*>(dropout_seed);
   cudaStream_t st = (cudaStream_t)stream;
   const BnLayout L = {groups, (size_t)group_stride, (size_t)row_stride};
   switch (cols / 128) {
-    case 1: return fwd_t<1>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
-    case 2: return fwd_t<2>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
-    case 3: return fwd_t<3>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
-    default: return fwd_t<4>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, st);
+    case 1: return fwd_t<1>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, dropout_p, seed, st);
+    case 2: return fwd_t<2>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, dropout_p, seed, st);
+    case 3: return fwd_t<3>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, dropout_p, seed, st);
+    default: return fwd_t<4>(x, gamma, beta, rows, L, eps, momentum, y, mean, rstd, running_mean, running_var, workspace, dropout_p, seed, st);
   }
 }
 
 int vdetr_bn_relu_train_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
                             const float* gamma, int rows, int cols, int groups, long long group_stride, long long row_stride,
-                            float* dx, float* dgamma, float* dbeta, float* workspace, void* stream) {
+                            float dropout_p, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream) {
   if (rows < 1 || !vdetr_bn_relu_supported(cols) || !layout_ok(cols, groups, group_stride, row_stride)) return VDETR_ERR_UNSUPPORTED;
+  if (!(dropout_p >= 0.f) || dropout_p >= 1.f) return VDETR_ERR_BAD_ARG;
   if (!dy || !y || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || !workspace) return VDETR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const BnLayout L = {groups, (size_t)group_stride, (size_t)row_stride};
   switch (cols / 128) {
-    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
-    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
-    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
-    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, st);
+    case 1: return bwd_t<1>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, dropout_p, st);
+    case 2: return bwd_t<2>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, dropout_p, st);
+    case 3: return bwd_t<3>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, dropout_p, st);
+    default: return bwd_t<4>(dy, y, x, mean, rstd, gamma, rows, L, dx, dgamma, dbeta, workspace, dropout_p, st);
   }
 }
 

@@ -30,8 +30,10 @@ def pointwise_tokens(seq, x):
             x = ops.linear(x, m.weight.squeeze(-1), m.bias)
         elif (type(m) is nn.BatchNorm1d and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
               and ops.bn_relu_train_supported(x, m)):
-            x = ops.bn_relu_train(x, m)           # batch statistics + running-stat update + ReLU fused (csrc/batchnorm.cu)
-            i += 1
+            # batch statistics + running-stat update + ReLU (+ the Dropout behind it) fused (csrc/batchnorm.cu)
+            drop = mods[i + 2] if i + 2 < len(mods) and type(mods[i + 2]) is nn.Dropout and mods[i + 2].training else None
+            x = ops.bn_relu_train(x, m, drop.p if drop is not None else 0.0)
+            i += 1 if drop is None else 2
         else:
             x = m(x)
         i += 1

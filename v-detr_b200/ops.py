@@ -241,7 +241,7 @@ class _BnReluTrain(Function):
     layout "cl": x [rows, groups * cols] (channels last); layout "gm": x [groups, rows, cols] (group major)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, groups, layout):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, groups, layout, dropout_p, dropout_seed):
         if layout == "cl":
             rows, cols = x.shape[0], x.shape[1] // groups
             gstride, rstride = cols, x.shape[1]
@@ -254,25 +254,26 @@ class _BnReluTrain(Function):
         with torch.cuda.device(x.device):
             ws = _reduce_ws(groups * cols, x.device)
             _C.check(_C.lib().vdetr_bn_relu_train_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(bias), rows, cols, groups, gstride, rstride,
-                                                      float(eps), float(momentum), _C.ptr(y), _C.ptr(mean), _C.ptr(rstd),
-                                                      _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(ws), _C.stream_ptr()))
+                                                      float(eps), float(momentum), float(dropout_p), _C.ptr(dropout_seed), _C.ptr(y),
+                                                      _C.ptr(mean), _C.ptr(rstd), _C.ptr(running_mean), _C.ptr(running_var),
+                                                      _C.ptr(ws), _C.stream_ptr()))
         ctx.save_for_backward(x, y, weight, mean, rstd)
-        ctx.geom = (rows, cols, groups, gstride, rstride)
+        ctx.geom = (rows, cols, groups, gstride, rstride, float(dropout_p))
         ctx.mark_non_differentiable(*[t for t in (running_mean, running_var) if t is not None])
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, weight, mean, rstd = ctx.saved_tensors
-        rows, cols, groups, gstride, rstride = ctx.geom
+        rows, cols, groups, gstride, rstride, dropout_p = ctx.geom
         dy = dy.contiguous()
         dx, dw, db = torch.empty_like(x), torch.empty_like(weight), torch.empty_like(weight)
         with torch.cuda.device(x.device):
             ws = _reduce_ws(groups * cols, x.device)
             _C.check(_C.lib().vdetr_bn_relu_train_bwd(_C.ptr(dy), _C.ptr(y), _C.ptr(x), _C.ptr(mean), _C.ptr(rstd), _C.ptr(weight),
-                                                      rows, cols, groups, gstride, rstride, _C.ptr(dx), _C.ptr(dw), _C.ptr(db),
-                                                      _C.ptr(ws), _C.stream_ptr()))
-        return dx, dw, db, None, None, None, None, None, None
+                                                      rows, cols, groups, gstride, rstride, dropout_p, _C.ptr(dx), _C.ptr(dw),
+                                                      _C.ptr(db), _C.ptr(ws), _C.stream_ptr()))
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 def bn_relu_train_supported(x, bn) -> bool:
@@ -280,14 +281,20 @@ def bn_relu_train_supported(x, bn) -> bool:
             and bn.momentum is not None and x.shape[1] in (128, 256, 384, 512) and bn.weight.dtype == torch.float32)
 
 
-def bn_relu_train(x, bn):
-    """relu(BatchNorm1d(x)) for a training-mode nn.BatchNorm1d `bn` on token-major x [T, C] (fp32, CUDA): batch statistics,
-    running-statistics update and ReLU in two kernels forward / two backward (csrc/batchnorm.cu)."""
+def _drop_args(dropout_p, device):
+    dropout_p = float(dropout_p)
+    return (dropout_p, new_dropout_seed(device)) if dropout_p > 0.0 else (0.0, None)
+
+
+def bn_relu_train(x, bn, dropout_p=0.0):
+    """dropout(relu(BatchNorm1d(x))) for a training-mode nn.BatchNorm1d `bn` on token-major x [T, C] (fp32, CUDA): batch
+    statistics, running-statistics update, ReLU and (dropout_p > 0) the Dropout that follows in the reference's stacks, in two
+    kernels forward / two backward (csrc/batchnorm.cu)."""
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return _BnReluTrain.apply(x.contiguous(), bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, 1, "cl")
+    return _BnReluTrain.apply(x.contiguous(), bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, 1, "cl", *_drop_args(dropout_p, x.device))
 
 
 def bn_relu_train_group_supported(x, bns, layout) -> bool:
@@ -301,7 +308,7 @@ def bn_relu_train_group_supported(x, bns, layout) -> bool:
     return same and shape_ok and x.is_cuda and x.dtype == torch.float32 and cols in (128, 256, 384, 512) and len(bns) <= 32
 
 
-def bn_relu_train_group(x, bns, layout):
+def bn_relu_train_group(x, bns, layout, dropout_p=0.0):
     """relu(BatchNorm1d_g(x_g)) for several training-mode nn.BatchNorm1d layers of equal width at once: x is
     [T, G * C] (layout "cl", the output of one GEMM with the G weight matrices concatenated) or [G, T, C] ("gm", the
     output of a batched GEMM).  Parameters are concatenated for the call (autograd splits the gradients back); the
@@ -311,7 +318,8 @@ def bn_relu_train_group(x, bns, layout):
     track = bns[0].track_running_stats
     rm = torch.cat([b.running_mean for b in bns]) if track else None
     rv = torch.cat([b.running_var for b in bns]) if track else None
-    y = _BnReluTrain.apply(x.contiguous(), weight, bias, rm, rv, bns[0].eps, bns[0].momentum, len(bns), layout)
+    y = _BnReluTrain.apply(x.contiguous(), weight, bias, rm, rv, bns[0].eps, bns[0].momentum, len(bns), layout,
+                           *_drop_args(dropout_p, x.device))
     if track:
         with torch.no_grad():
             c = bns[0].num_features

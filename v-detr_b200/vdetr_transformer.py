@@ -568,11 +568,15 @@ class TransformerDecoder(nn.Module):
         return stacks
 
     @staticmethod
-    def _bn_relu_group(x, bns, layout):
-        """relu(bn_g(x_g)) for the heads' BatchNorm layers: the library's grouped kernels in training, the running
-        statistics as a per-channel affine map otherwise."""
+    def _bn_relu_group(x, bns, layout, drop):
+        """drop(relu(bn_g(x_g))) for the heads' BatchNorm layers and the nn.Dropout behind them: the library's grouped kernels
+        in training (dropout fused), the running statistics as a per-channel affine map otherwise."""
         if ops.bn_relu_train_group_supported(x, bns, layout):
-            return ops.bn_relu_train_group(x, bns, layout)
+            return ops.bn_relu_train_group(x, bns, layout, drop.p if drop.training else 0.0)
+        return drop(TransformerDecoder._bn_relu_group_plain(x, bns, layout))
+
+    @staticmethod
+    def _bn_relu_group_plain(x, bns, layout):
         if any(b.training for b in bns):
             # widths the kernels do not cover: per-head stock BatchNorm
             C = bns[0].num_features
@@ -594,12 +598,12 @@ class TransformerDecoder(nn.Module):
         W1 = torch.cat([st[0].weight.squeeze(-1) for st in stacks])                                 # [G*C, Cin]
         b1 = torch.cat([st[0].bias for st in stacks]) if stacks[0][0].bias is not None else None
         h = ops.linear(feats, W1, b1)                                                               # [T, G*C]
-        h = stacks[0][3](self._bn_relu_group(h, [st[1] for st in stacks], "cl"))
+        h = self._bn_relu_group(h, [st[1] for st in stacks], "cl", stacks[0][3])
         W2 = torch.stack([st[4].weight.squeeze(-1) for st in stacks])                               # [G, C, C]
         h = torch.bmm(h.view(T, G, C).transpose(0, 1), W2.transpose(1, 2))                          # [G, T, C]
         if stacks[0][4].bias is not None:
             h = h + torch.stack([st[4].bias for st in stacks]).unsqueeze(1)
-        h = stacks[0][7](self._bn_relu_group(h, [st[5] for st in stacks], "gm"))
+        h = self._bn_relu_group(h, [st[5] for st in stacks], "gm", stacks[0][7])
         outs = [st[8].out_channels for st in stacks]
         omax = max(outs)
         W3 = torch.stack([F.pad(st[8].weight.squeeze(-1), (0, 0, 0, omax - o)) for st, o in zip(stacks, outs)])   # [G, omax, C]
