@@ -218,6 +218,15 @@ int vdetr_box_decode_bwd(const float* size, const float* pre_size, const float* 
                          const float* g_size_normalized, const float* g_corners, int B, int nQ, float* g_center_reg,
                          float* g_size_reg, void* stream);
 
+/* Batched rectangular linear sum assignment (the Hungarian matching of criterion.py:205-228, which calls
+ * scipy.optimize.linear_sum_assignment per scene on the host): cost [B,nQ,ngt] f32; nactual_gt [B] int32 on the DEVICE (NULL:
+ * all ngt columns are real).  Scene b assigns every ground-truth column g < nactual_gt[b] a distinct query minimising the
+ * total cost.  Outputs as the reference builds them: per_prop_gt_inds [B,nQ] int64 (0 where unmatched),
+ * proposal_matched_mask [B,nQ] f32.  ngt <= nQ <= 4096, ngt <= 512.  Same algorithm and FP64 duals as scipy; exact ties
+ * may resolve differently (same total cost). */
+int vdetr_lsap(const float* cost, const int32_t* nactual_gt, int B, int nQ, int ngt, long long* per_prop_gt_inds,
+               float* proposal_matched_mask, void* stream);
+
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call
  * copies the 8 counters to the host and clears them (synchronises the device). */

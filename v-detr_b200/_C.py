@@ -61,6 +61,7 @@ _SIGS = {
                                 [c_void_p] * 5),
     "vdetr_box_decode_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 8 + [c_void_p]),
     "vdetr_box_decode_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int] + [c_void_p] * 2 + [c_void_p]),
+    "vdetr_lsap": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vdetr_debug_dt_clocks": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "vdetr_rpe_dtables_workspace_bytes": (c_size_t, [ctypes.POINTER(XattnShape)]),
     "vdetr_rpe_dtables": (c_int, [ctypes.POINTER(XattnShape)] + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),
