@@ -608,3 +608,24 @@ def test_bn_relu_dropout_fusion():
     torch.manual_seed(6)
     y2 = ops.bn_relu_train(x, bn, p)
     assert not torch.equal(y2, y1)                      # a fresh seed per call
+
+
+@pytest.mark.parametrize("B,nQ,nK,rot,far", [(2, 37, 150, False, 0.2), (1, 1024, 4096, False, 0.0), (1, 20, 90, True, 0.1)])
+def test_dtables_tensor_core_variant_matches_oracle(B, nQ, nK, rot, far, monkeypatch):
+    """VDETR_DT_IMPL=5 (mma.sync accumulation for axis-aligned boxes, dt3 for the others) against the fp64 oracle, at a small
+    ragged size, at the benchmark's per-scene size on a query subset, and with rotated boxes (all queries go to dt3)."""
+    from vdetr_b200 import ops
+    monkeypatch.setenv("VDETR_DT_IMPL", "5")
+    c = recipe.xattn_case(200 + nQ, B, nQ, nK, rot, far)
+    ref = ora.box_vertices(c["center"], c["size"]).astype(np.float32)
+    rs = np.random.RandomState(nQ)
+    sel = np.arange(nQ) if nQ <= 64 else np.arange(3, nQ, 37)[:24]
+    ds = np.zeros((B, 4, nQ, nK), np.float32)
+    ds[:, :, sel] = rs.standard_normal((B, 4, len(sel), nK)).astype(np.float32)
+    want = ora.rpe_bias_backward_tables(ref[:, sel], c["xyz"], (8, 10, 10, 10, 4), ds[:, :, sel].astype(np.float64),
+                                        None if c["angle"] is None else c["angle"][:, sel])
+    got = ops.rpe_bias_grad_tables(torch.from_numpy(c["xyz"]).cuda(), torch.from_numpy(ref).cuda(),
+                                   None if c["angle"] is None else torch.from_numpy(c["angle"]).cuda(),
+                                   torch.zeros(8, 10, 10, 10, 4, device="cuda"), torch.from_numpy(ds).cuda()).cpu().numpy()
+    _report(f"dt5 {B}x{nQ}x{nK} rot={rot} dT", got, want)
+    _cmp(got, want, 1e-3, 1e-6, "dtables (tensor-core variant)")      # weights enter the MMA as fp16 (2^-12 relative)

@@ -53,7 +53,7 @@ struct Params {
   const unsigned* absmax_bits;            // -> scale
   float* priv;                            // [gridDim.x][8][P3^3][4]
   int4 cost;                              // per-segment cost model of the accumulation phase (see seg_cost)
-  int only_slow;                          // dt3 as the companion of dt4: only queries whose box is not axis aligned
+  int only_slow;                          // dt3 as the companion of dt5: only queries whose box is not axis aligned
   const int* slow_count;                  // [1] number of such queries in the whole call (only_slow: 0 -> nothing to do)
   unsigned long long* phase_clocks;       // [8] optional (developer): cycles per phase summed over CTAs, else null
 };
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
         const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
         hi = __ldg(g); lo = __ldg(g + 1);
         slow = __float_as_int(hi.w) == 0;
-        if (P.only_slow && !slow) q = -1;                    // axis-aligned boxes are the dt4 kernel's
+        if (P.only_slow && !slow) q = -1;                    // axis-aligned boxes are the dt5 kernel's
       }
       S.sgeo[tid * 2] = hi; S.sgeo[tid * 2 + 1] = lo;
       S.sq[tid] = q; s_slow[tid] = slow;
@@ -531,47 +531,37 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_kernel(const Params P)
 }  // namespace dt3
 
 // =====================================================================================================================
-// dt4: the same adjoint for AXIS-ALIGNED boxes (every query of the ScanNet configuration: num_angle_bin = 1) with the
-// accumulation done by warp-level tensor-core MMAs instead of per-lane register accumulators + shuffle transposes.
+// dt5 (opt-in: VDETR_DT_IMPL=5): the same adjoint for AXIS-ALIGNED boxes with the accumulation done by warp-level
+// tensor-core MMAs (mma.sync.m16n8k16 + ldmatrix) instead of per-lane register accumulators + shuffle transposes.
+// Measured on B200 at 8 x 1024 x 4096: 3.8 ms against dt3's 3.7 ms -- see DESIGN.md 4.3 for why it does not win: staging
+// the fp16 weight fragments through shared memory costs as many instructions as the FFMA2s it replaces, and the sort
+// (halved here) was the smaller half of dt3.  Kept as a tested alternative.
 //
 //   unit      = (scene, 12 Morton-adjacent queries, 512 Morton-adjacent keys) = 6144 pairs; phase A as in dt3.
 //   round     = a PAIR of vertices that differ only in the x sign (0,3) (1,2) (4,7) (5,6): they share the y and z
-//               transforms, hence the (z, y) part of their table cell and 4 of the 6 weight factors.  ONE counting sort
-//               per round, by (z, y, x+ cell, min(x+ cell - x- cell, 3)): vertex A (x+) is perfectly sorted and vertex B
-//               (x-) is sorted inside A's segments.
-//   accumulate: a warp walks its share of the sorted list 32 pairs per step; lane = pair computes the 8 corner weights of
-//               A and of B (fp32, rounded once to fp16) and leaves them with the 4 heads' dS in a per-warp staging
-//               tile; per 16 pairs ldmatrix builds the fragments of ONE mma.sync.m16n8k16:
-//                   D[16 x 8] += W^T[16 x 16 pairs] * dS[16 pairs x 8]     rows 0-7 = A's corners, 8-15 = B's corners,
-//                                                                          columns 0-3 = heads
-//               D stays in registers while the cell of the vertex does not change; a cell change costs one vector RED
-//               per lane (no transposition), a block that straddles cells is handled by masking the fragment rows.
+//               transforms, hence the (z, y) part of their table cell and 4 of the 6 weight factors: ONE counting sort
+//               per round, by the cell of vertex A (x+).
+//   vertex B (x-) accumulates into an x WINDOW: its 16 MMA rows are (4 (z,y) corners) x (4 consecutive x points).  Inside
+//               one cell of A the cell of B is x_A - delta with delta in {0,1,2} for all but a handful of pairs (class 1),
+//               so with the window based at x_A - 2 vertex B never changes accumulators inside A's segment.
+//   layout    : class-0 bins are laid out first, each padded with dummy pairs to a multiple of 16, so that every 16-pair
+//               MMA block of that region belongs to exactly one cell; class-1 pairs follow unpadded and go through a
+//               masked path with B's window based at its own cell.
+//   accumulate: lane = pair computes the 8 corner weights of A and the 16 window weights of B (fp32, rounded once to
+//               fp16) and leaves them with the 4 heads' dS in a per-warp staging tile; per 16 pairs ldmatrix builds the
+//               fragments of two MMAs  D[16 x 8] += W^T[16 x 16 pairs] * dS[16 pairs x 8].  D stays in registers while
+//               the cell does not change; a cell change costs one vector RED per lane (keys are linear table offsets).
+//               Work is drawn in chunks from a shared counter, the expensive unpadded end of the list first.
 // Queries whose box is not axis aligned are skipped here (zero weights) and handled by dt3 with only_slow = 1.
-namespace dt4 {
+namespace dt5 {
 
 using dt3::axis_rec;
 using dt3::FULL;
 using dt3::Params;
 
-constexpr int QB = 12, KC = 512, NP = QB * KC;          // 6144 pairs per unit
-constexpr int THREADS = 512, WARPS = 16, ITEMS = NP / THREADS;
-static_assert(NP % THREADS == 0 && (NP / 4) % THREADS == 0 && KC == THREADS, "unit shape");
-constexpr int XI = 12;                                   // x index values of a sort bin: cells 0..10, 11 = vertex A outside the table
-constexpr int SORT_PAD = 64;                             // dummy entries behind the sorted list (whole steps + the prefetch)
-constexpr int STAGE_BYTES = 3 * 32 * 16;                 // per warp: A weights, B weights, dS (16 B per pair each)
-#ifndef VDETR_DT4_CHUNK
-#define VDETR_DT4_CHUNK 4
+#ifndef VDETR_DT5_CHUNK
+#define VDETR_DT5_CHUNK 4
 #endif
-constexpr int CHUNK = VDETR_DT4_CHUNK;                   // steps per unit of dynamically scheduled accumulate work
-
-__host__ __device__ inline int nbins_of(int n) { return (n + 1) * (n + 1) * XI * 4; }
-__host__ __device__ inline size_t region_bytes(int n) {
-  const size_t r = ((size_t)nbins_of(n) + 1 + 3) / 4 * 16;
-  return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
-}
-__host__ __device__ inline size_t smem_bytes(int n) {
-  return (size_t)(NP + 2) * 24 + (size_t)(NP + SORT_PAD) * 2 + region_bytes(n) + WARPS * STAGE_BYTES + QB * 2 * 16 + 64 * 4 + 64;
-}
 
 // run structure of a warp's 32 bins (see dt3::run_pack); bins need 13 bits here:
 //   bits [0,13) bin + 1 (0 = pair outside the table)   [13,18) rank inside the run   [18,24) run length
@@ -606,339 +596,13 @@ __device__ __forceinline__ uint32_t keep_halves(uint32_t v, unsigned bits) {
   return v & m;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) rpe_dtables_mma_kernel(const Params P) {
-  extern __shared__ __align__(16) uint8_t sm[];
-  // [NP + 2] records / dS (entry NP = dummy; NP + 2 keeps every later region 16-byte aligned), [NP + SORT_PAD] sorted ids
-  static_assert(((NP + 2) * 24) % 16 == 0 && ((NP + SORT_PAD) * 2) % 16 == 0, "16-byte alignment of the shared-memory regions");
-  uint4* s_recs = reinterpret_cast<uint4*>(sm);
-  uint2* s_dsv = reinterpret_cast<uint2*>(sm + (size_t)(NP + 2) * 16);
-  uint16_t* s_sorted = reinterpret_cast<uint16_t*>(sm + (size_t)(NP + 2) * 24);
-  uint8_t* region = sm + (size_t)(NP + 2) * 24 + (size_t)(NP + SORT_PAD) * 2;
-  int* s_hist = reinterpret_cast<int*>(region);                                     // [nbins + 1] counts -> cursors
-  float4* s_xyz = reinterpret_cast<float4*>(region);                                // [KC] phase A only (aliases hist)
-  uint8_t* s_stage = region + region_bytes(P.n);                                    // [WARPS][STAGE_BYTES]
-  float4* s_geo = reinterpret_cast<float4*>(s_stage + WARPS * STAGE_BYTES);         // [QB][2]
-  int* s_q = reinterpret_cast<int*>(s_geo + QB * 2);                                // [QB] query index or -1 (also -1: not axis aligned)
-  int* s_misc = s_q + 16;                                                           // [0] sorted count, [2..2+WARPS) scan scratch
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nbins = nbins_of(P.n);
-  const int R = P.R;
-  const int cells_pad = P.P3 * P.P3 * P.P3;
-  float* my_priv = P.priv + (size_t)blockIdx.x * 8 * cells_pad * 4;
-  long long t_prev = clock64();
-  auto tick = [&](int phase) {
-    if (P.phase_clocks && tid == 0) {
-      const long long t = clock64();
-      atomicAdd(P.phase_clocks + phase, (unsigned long long)(t - t_prev));
-      t_prev = t;
-    }
-  };
-  // fragment roles of this lane in the accumulate phase
-  const int fg = lane >> 2, ft = lane & 3;                        // D row (corner) / column pair
-  const int fcz = fg >> 2, fcy = (fg >> 1) & 1, fcx = fg & 1;
-  uint8_t* my_stage = s_stage + warp * STAGE_BYTES;
-  const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(my_stage);
-  // ldmatrix row addresses: A fragment tiles (WA k0-7, WB k0-7, WA k8-15, WB k8-15), B fragment tiles (dS k0-7, dS k8-15)
-  const uint32_t a_row = stage_u32 + ((lane >> 3) & 1) * 512 + (((lane >> 4) & 1) * 8 + (lane & 7)) * 16;
-  const uint32_t b_row = stage_u32 + 1024 + (((lane >> 3) & 1) * 8 + (lane & 7)) * 16;
-
-  if (tid == 0) {                                                 // dummy record: contributes nothing, x cells invalid
-    s_recs[NP] = make_uint4(0u, 0u, 0u, 0x000000FFu);
-    s_dsv[NP] = make_uint2(0u, 0u);
-  }
-
-  for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
-    int r = u;
-    const int kc = r % P.kchunks; r /= P.kchunks;
-    const int qb = r % P.qblocks;
-    const int b = r / P.qblocks;
-    const int q0 = qb * QB, k0 = kc * KC;
-
-    __syncthreads();                      // previous unit completely done with shared memory
-    if (tid < QB) {
-      const int qi = q0 + tid;
-      int q = -1;
-      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-      if (qi < P.nQ) {
-        q = __ldg(P.qperm + (size_t)b * P.nQ + qi);
-        const float4* g = P.geo + ((size_t)b * P.nQp + q) * 9;
-        hi = __ldg(g); lo = __ldg(g + 1);
-        if (__float_as_int(hi.w) == 0) q = -1;                    // not axis aligned: handled by the dt3 kernel
-      }
-      s_geo[tid * 2] = hi; s_geo[tid * 2 + 1] = lo;
-      s_q[tid] = q;
-    }
-    for (int i = tid; i < KC; i += THREADS) {
-      float4 kx = make_float4(1e9f, 1e9f, 1e9f, 0.f);
-      if (k0 + i < P.nK) kx = __ldg(P.xyz4 + (size_t)b * P.nKp + k0 + i);
-      s_xyz[i] = kx;
-    }
-    __syncthreads();
-
-    // ---- phase A: records (6 axis transforms per pair) + the 4 heads' scaled fp16 dS; 4 consecutive keys per thread
-    {
-      constexpr int KG = KC / 4, GI = NP / 4 / THREADS;
-#pragma unroll 1
-      for (int gi = 0; gi < GI; ++gi) {
-        const int g = gi * THREADS + tid, ql = g / KG, kl0 = (g % KG) * 4;
-        const int q = s_q[ql];
-        uint2 hd[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) hd[h] = make_uint2(0u, 0u);
-        const bool any = q >= 0 && k0 + kl0 < P.nK;
-        if (any) {
-          const __half* dp = P.dsb + ((size_t)b * P.nQp + q) * 4 * P.nKp + k0 + kl0;
-#pragma unroll
-          for (int h = 0; h < 4; ++h) hd[h] = __ldg(reinterpret_cast<const uint2*>(dp + (size_t)h * P.nKp));
-        }
-        const float4 hi = s_geo[ql * 2], lo = s_geo[ql * 2 + 1];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kl = kl0 + j, p = ql * KC + kl;
-          uint4 rec = make_uint4(0u, 0u, 0u, 0x00FFFFFFu);
-          uint2 dv = make_uint2(0u, 0u);
-          if (any && k0 + kl < P.nK) {
-            const int sh = 16 * (j & 1);
-            const unsigned w0 = (j < 2) ? hd[0].x : hd[0].y, w1 = (j < 2) ? hd[1].x : hd[1].y;
-            const unsigned w2 = (j < 2) ? hd[2].x : hd[2].y, w3 = (j < 2) ? hd[3].x : hd[3].y;
-            dv = make_uint2(((w0 >> sh) & 0xFFFFu) | (((w1 >> sh) & 0xFFFFu) << 16), ((w2 >> sh) & 0xFFFFu) | (((w3 >> sh) & 0xFFFFu) << 16));
-            const float4 kx = s_xyz[kl];
-            unsigned nxp, nxm, nyp, nym, nzp, nzm, fxp, fxm, fyp, fym, fzp, fzm;
-            axis_rec(hi.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxp, fxp);
-            axis_rec(lo.x - kx.x, P.log_scale, P.c1, P.c0, P.n, nxm, fxm);
-            axis_rec(hi.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nyp, fyp);
-            axis_rec(lo.y - kx.y, P.log_scale, P.c1, P.c0, P.n, nym, fym);
-            axis_rec(hi.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzp, fzp);
-            axis_rec(lo.z - kx.z, P.log_scale, P.c1, P.c0, P.n, nzm, fzm);
-            rec.x = fxp | (fxm << 16); rec.y = fyp | (fym << 16); rec.z = fzp | (fzm << 16);
-            rec.w = nxp | (nxm << 4) | (nyp << 8) | (nym << 12) | (nzp << 16) | (nzm << 20);
-          }
-          s_recs[p] = rec;
-          s_dsv[p] = dv;
-        }
-      }
-    }
-    __syncthreads();                      // records complete; the xyz staging area becomes the histogram
-    tick(0);
-
-    for (int round = 0; round < 4; ++round) {
-      // round -> (y slot, z slot) and the two vertices: A has x+, B has x-  (sign table in dt3::vertex_slots)
-      const int ys = round & 1, zs = (round < 2) ? 1 : 0;
-      const int vertA = (round < 2 ? 0 : 4) + ys, vertB = (round < 2 ? 3 : 7) - ys;
-      const int shy = 16 * ys, shz = 16 * zs;
-      const int nby = 8 + 4 * ys, nbz = 16 + 4 * zs;
-
-      for (int i = tid; i <= nbins; i += THREADS) s_hist[i] = 0;
-      __syncthreads();
-      tick(1);
-
-      // ---- B1: histogram of the sort bins
-      unsigned myrun[ITEMS];
-#pragma unroll
-      for (int it = 0; it < ITEMS; ++it) {
-        const unsigned w = s_recs[it * THREADS + tid].w;
-        const int xa = w & 15, xb = (w >> 4) & 15, ny = (w >> nby) & 15, nz = (w >> nbz) & 15;
-        const bool a_ok = xa != 15, b_ok = xb != 15;
-        int bin = -1;
-        if (max(ny, nz) != 15 && (a_ok || b_ok)) {
-          const int xi = a_ok ? xa : XI - 1;
-          const int d = (a_ok && b_ok) ? min(max(xa - xb, 0), 3) : 0;
-          bin = (((nz * R + ny) * XI + xi) << 2) + d;
-        }
-        const unsigned rp = run_pack13(bin, lane);
-        myrun[it] = rp;
-        if ((rp & 0x3E000u) == 0u && bin >= 0) atomicAdd(s_hist + bin, (int)(rp >> 18));        // run head
-      }
-      __syncthreads();
-      tick(2);
-
-      // ---- B2: exclusive scan of the histogram, in place (counts -> scatter cursors)
-      {
-        const int per = (nbins + THREADS - 1) / THREADS;
-        const int lo = tid * per, hi = min(nbins, lo + per);
-        int mine = 0;
-        for (int i = lo; i < hi; ++i) mine += s_hist[i];
-        int x = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(FULL, x, o);
-          if (lane >= o) x += y;
-        }
-        if (lane == 31) s_misc[2 + warp] = x;
-        __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += s_misc[2 + w];
-        int run = wbase + x - mine;
-        for (int i = lo; i < hi; ++i) {
-          const int c = s_hist[i];
-          s_hist[i] = run;
-          run += c;
-        }
-        if (tid == THREADS - 1) s_misc[0] = run;             // number of sorted pairs
-      }
-      __syncthreads();
-      tick(3);
-
-      // ---- B3: counting-sort scatter; dummy entries behind the list (whole 32-pair steps + the prefetch of the walk)
-      const int nsorted = s_misc[0];
-#pragma unroll
-      for (int it = 0; it < ITEMS; ++it) {
-        const unsigned rp = myrun[it];
-        const int bin = (int)(rp & 0x1FFFu) - 1, rank = (int)((rp >> 13) & 31u);
-        int base = 0;
-        if (rank == 0 && bin >= 0) base = atomicAdd(s_hist + bin, (int)(rp >> 18));
-        base = __shfl_sync(FULL, base, lane - rank);
-        if (bin >= 0) s_sorted[base + rank] = (uint16_t)(it * THREADS + tid);
-      }
-      if (tid < SORT_PAD) s_sorted[nsorted + tid] = (uint16_t)NP;
-      if (tid == 0) s_misc[1] = 0;                       // chunk counter of the accumulate phase
-      __syncthreads();
-      tick(4);
-
-      // ---- B4: accumulate.  The sorted list is cut into chunks of CHUNK steps (32 pairs each) that the warps draw from a
-      // shared counter: the cost of a step depends on how many cells it straddles, and equal static shares left most
-      // warps waiting at the barrier for the few that own the fragmented end of the list.
-      {
-        const int steps = (nsorted + 31) >> 5;
-        float* tabA = my_priv + (size_t)vertA * cells_pad * 4;
-        float* tabB = my_priv + (size_t)vertB * cells_pad * 4;
-        float d[4] = {0.f, 0.f, 0.f, 0.f};                 // d[0..1]: A's corner fg, heads 2ft, 2ft+1; d[2..3]: B's
-        unsigned curA = 0xFFFFu, curB = 0xFFFFu;           // cell (nz << 8 | ny << 4 | nx) being accumulated; 0xFFFF = none
-
-        auto flush = [&](unsigned key, float* tab, float& v0, float& v1) {
-          const int nx = key & 15, ny = (key >> 4) & 15, nz = (key >> 8) & 15;
-          if (key != 0xFFFFu && nx <= P.n && ft < 2 && (v0 != 0.f || v1 != 0.f))
-            red_add_v2(tab + ((((nz + fcz) * P.P3 + (ny + fcy)) * P.P3 + (nx + fcx)) << 2) + 2 * ft, v0, v1);
-          v0 = 0.f; v1 = 0.f;
-        };
-
-        const unsigned sely = ys ? 0x7432u : 0x7410u, selz = zs ? 0x7432u : 0x7410u;
-        for (;;) {
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(s_misc + 1, 1);
-        chunk = __shfl_sync(FULL, chunk, 0);
-        const int s0 = chunk * CHUNK;
-        if (s0 >= steps) break;
-        const int s1 = min(steps, s0 + CHUNK);
-        const uint16_t* sp = s_sorted + s0 * 32 + lane;
-        unsigned ent_n = *sp;
-        uint4 rec_n = s_recs[ent_n];
-        uint2 dv_n = s_dsv[ent_n];
-        for (int st = s0; st < s1; ++st) {
-          const uint4 rec = rec_n;
-          const uint2 dv = dv_n;
-          sp += 32;
-          ent_n = *sp;
-          rec_n = s_recs[ent_n];
-          dv_n = s_dsv[ent_n];
-
-          const unsigned xa = rec.w & 15u, xb = (rec.w >> 4) & 15u;
-          const unsigned zy = (((rec.w >> nbz) & 15u) << 8) | (((rec.w >> nby) & 15u) << 4);
-          const unsigned keyA = zy | (xa == 15u ? 11u : xa), keyB = zy | (xb == 15u ? 11u : xb);
-          // fractions u / 65536 without I2F: bytes (u.lo, u.hi, 0x00, 0x4B) = 2^23 + u ;  (2^23 + u) * 2^-16 - 128
-          const float fz = fmaf(__uint_as_float(__byte_perm(rec.z, 0x4B000000u, selz)), 0x1p-16f, -128.f);
-          const float fy = fmaf(__uint_as_float(__byte_perm(rec.y, 0x4B000000u, sely)), 0x1p-16f, -128.f);
-          const float fa = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, 0x7410u)), 0x1p-16f, -128.f);
-          const float fb = fmaf(__uint_as_float(__byte_perm(rec.x, 0x4B000000u, 0x7432u)), 0x1p-16f, -128.f);
-          {
-            const float2 wy = make_float2(1.f - fy, fy);
-            const float2 z0 = dt3::fmul2(1.f - fz, wy), z1 = dt3::fmul2(fz, wy);       // (z0y0, z0y1) (z1y0, z1y1)
-            const float2 wa = xa == 15u ? make_float2(0.f, 0.f) : make_float2(1.f - fa, fa);
-            const float2 wb = xb == 15u ? make_float2(0.f, 0.f) : make_float2(1.f - fb, fb);
-            // corner index = cz * 4 + cy * 2 + cx  -> halves 0..7 of the pair's row
-            const float2 a01 = dt3::fmul2(z0.x, wa), a23 = dt3::fmul2(z0.y, wa), a45 = dt3::fmul2(z1.x, wa), a67 = dt3::fmul2(z1.y, wa);
-            const float2 b01 = dt3::fmul2(z0.x, wb), b23 = dt3::fmul2(z0.y, wb), b45 = dt3::fmul2(z1.x, wb), b67 = dt3::fmul2(z1.y, wb);
-            __syncwarp();                                 // the previous step's ldmatrix reads are complete
-            uint4* stg = reinterpret_cast<uint4*>(my_stage);
-            stg[lane] = make_uint4(tc::pack_f16x2(a01.x, a01.y), tc::pack_f16x2(a23.x, a23.y), tc::pack_f16x2(a45.x, a45.y),
-                                   tc::pack_f16x2(a67.x, a67.y));
-            stg[32 + lane] = make_uint4(tc::pack_f16x2(b01.x, b01.y), tc::pack_f16x2(b23.x, b23.y), tc::pack_f16x2(b45.x, b45.y),
-                                        tc::pack_f16x2(b67.x, b67.y));
-            stg[64 + lane] = make_uint4(dv.x, dv.y, 0u, 0u);
-            __syncwarp();
-          }
-          // uniformity of the two 16-pair blocks of this step, per vertex
-          const unsigned refA = __shfl_sync(FULL, keyA, lane & 16), refB = __shfl_sync(FULL, keyB, lane & 16);
-          const unsigned eqA = __ballot_sync(FULL, keyA == refA), eqB = __ballot_sync(FULL, keyB == refB);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t a0, a1, a2, a3, b0, b1;
-            ldmatrix_x4_trans(a_row + h * 256, a0, a1, a2, a3);
-            ldmatrix_x2_trans(b_row + h * 256, b0, b1);
-            const bool uniA = ((eqA >> (16 * h)) & 0xFFFFu) == 0xFFFFu, uniB = ((eqB >> (16 * h)) & 0xFFFFu) == 0xFFFFu;
-            if (uniA && uniB) {
-              const unsigned kA = __shfl_sync(FULL, keyA, 16 * h), kB = __shfl_sync(FULL, keyB, 16 * h);
-              if (kA != curA) { flush(curA, tabA, d[0], d[1]); curA = kA; }
-              if (kB != curB) { flush(curB, tabB, d[2], d[3]); curB = kB; }
-              mma_16816(d, a0, a1, a2, a3, b0, b1);
-              continue;
-            }
-            // a block that straddles cells: one masked MMA per distinct cell and vertex
-#pragma unroll 1
-            for (int v = 0; v < 2; ++v) {
-              const unsigned key = v ? keyB : keyA;
-              unsigned todo = 0xFFFFu << (16 * h);
-              while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const unsigned ksel = __shfl_sync(FULL, key, leader);
-                const unsigned grp = __ballot_sync(FULL, key == ksel) & (0xFFFFu << (16 * h));
-                todo &= ~grp;
-                const unsigned bits = (grp >> (16 * h)) >> (2 * ft);          // membership of pairs 2ft, 2ft+1 (bits 0,1), 2ft+8, 2ft+9 (bits 8,9)
-                if (v == 0) {
-                  if (ksel != curA) { flush(curA, tabA, d[0], d[1]); curA = ksel; }
-                  mma_16816(d, keep_halves(a0, bits), 0u, keep_halves(a2, bits >> 8), 0u, b0, b1);
-                } else {
-                  if (ksel != curB) { flush(curB, tabB, d[2], d[3]); curB = ksel; }
-                  mma_16816(d, 0u, keep_halves(a1, bits), 0u, keep_halves(a3, bits >> 8), b0, b1);
-                }
-              }
-            }
-          }
-        }
-        flush(curA, tabA, d[0], d[1]);
-        flush(curB, tabB, d[2], d[3]);
-        curA = 0xFFFFu; curB = 0xFFFFu;
-        }
-      }
-      __syncthreads();                    // hist / sorted are rewritten by the next round
-      tick(5);
-    }
-  }
-}
-
-}  // namespace dt4
-
-// =====================================================================================================================
-// dt5 = dt4 with three changes that remove most of what dt4 spends outside the MMAs (ncu, profiles/r2_ncu_dtables.md):
-//   * vertex B (x-) accumulates into an x WINDOW: its 16 MMA rows are (4 (z,y) corners) x (4 consecutive x points).
-//     Inside one cell of vertex A the cell of B is x_A - delta with delta in {0,1,2} for all but a handful of pairs, so
-//     with the window based at x_A - 2 vertex B never changes accumulators inside A's segment: no masking, no extra
-//     flushes.  Two MMAs per 16 pairs (A: 8 rows used, B: 16 rows) instead of one plus masked repeats.
-//   * sort bins with >= 16 pairs ("large", 93 % of the pairs) are laid out first, each padded with dummy pairs to a
-//     multiple of 16: every 16-pair block of that region belongs to exactly one cell.  The other bins (and the rare pairs
-//     with delta > 2 or vertex A outside the table, class 1) follow unpadded and go through the masked path, with the
-//     window of B based at its own cell.
-//   * accumulate work is drawn in chunks from a shared counter (as dt4 after its first profile).
-namespace dt5 {
-
-using dt3::axis_rec;
-using dt3::FULL;
-using dt3::Params;
-using dt4::keep_halves;
-using dt4::ldmatrix_x2_trans;
-using dt4::ldmatrix_x4_trans;
-using dt4::mma_16816;
-using dt4::red_add_v2;
-using dt4::run_pack13;
-
 constexpr int QB = 12, KC = 512, NP = QB * KC;
 constexpr int THREADS = 512, WARPS = 16, ITEMS = NP / THREADS;
 constexpr int XI = 12;
 constexpr int SORT_CAP = NP + (NP / 16) * 15 + 128;      // large bins padded to 16 (at most NP/16 of them) + trailing dummies / prefetch
 constexpr int STAGE_BYTES = 4 * 32 * 16;                 // per warp: A weights | B window halves 0-7 | 8-15 | dS  (16 B per pair each)
-constexpr int CHUNK = VDETR_DT4_CHUNK;
-constexpr unsigned WILD = 0xFFFFu;
+constexpr int CHUNK = VDETR_DT5_CHUNK;                   // steps per unit of dynamically scheduled accumulate work
+constexpr unsigned WILD = 0xFFFFFFFFu;
 static_assert((SORT_CAP * 2) % 16 == 0 && ((NP + 2) * 24) % 16 == 0, "16-byte alignment of the shared-memory regions");
 
 __host__ __device__ inline int nbins_of(int n) { return (n + 1) * (n + 1) * XI * 2; }
@@ -947,7 +611,7 @@ __host__ __device__ inline size_t region_bytes(int n) {
   return r < (size_t)KC * 16 ? (size_t)KC * 16 : r;
 }
 __host__ __device__ inline size_t smem_bytes(int n) {
-  return (size_t)(NP + 2) * 24 + (size_t)SORT_CAP * 2 + region_bytes(n) + WARPS * STAGE_BYTES + QB * 2 * 16 + 64 * 4 + 64;
+  return (size_t)(NP + 2) * 24 + (size_t)SORT_CAP * 2 + region_bytes(n) + WARPS * STAGE_BYTES + QB * 2 * 16 + 64 * 4 + 128;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Params P) {
@@ -961,7 +625,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Param
   uint8_t* s_stage = region + region_bytes(P.n);
   float4* s_geo = reinterpret_cast<float4*>(s_stage + WARPS * STAGE_BYTES);         // [QB][2]
   int* s_q = reinterpret_cast<int*>(s_geo + QB * 2);                                // [QB]
-  int* s_misc = s_q + 16;      // [0] end of the sorted list  [1] chunk counter  [2] end of the large region  [4..4+2*WARPS) scan scratch
+  int* s_misc = s_q + 16;      // [0] end of the sorted list  [1] chunk counter  [2] end of the padded region  [4..4+4*WARPS) scan scratch
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nbins = nbins_of(P.n);
@@ -1017,7 +681,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Param
     }
     __syncthreads();
 
-    // ---- phase A: records + dS (identical to dt4)
+    // ---- phase A: records + dS (as in dt3)
     {
       constexpr int KG = KC / 4, GI = NP / 4 / THREADS;
 #pragma unroll 1
@@ -1097,34 +761,45 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Param
       __syncthreads();
       tick(2);
 
-      // ---- B2: two exclusive scans in one pass: large class-0 bins (>= 16 pairs) padded to multiples of 16 first, the
-      // other bins behind them
+      // ---- B2: two exclusive scans in one pass: class-0 bins with >= th pairs, each padded to a multiple of 16, first; the
+      // other bins behind them.  th = 1 (every class-0 bin padded: no block of the padded region ever straddles two cells)
+      // unless the padding would overflow the sorted array, then 16 (always fits: at most NP / 16 such bins).
       {
         const int per = (nbins + THREADS - 1) / THREADS;
         const int lo = tid * per, hi = min(nbins, lo + per);
-        int mineL = 0, mineS = 0;
+        // per thread: padded size of the front region and pair count of the rest, for th = 1 and for th = 16
+        int mL1 = 0, mS1 = 0, mL16 = 0, mS16 = 0;
         for (int i = lo; i < hi; ++i) {
           const int c = s_hist[i];
-          if (c >= 16 && !(i & 1)) mineL += (c + 15) & ~15; else mineS += c;
+          const int a = (c + 15) & ~15;
+          if (!(i & 1)) { mL1 += a; if (c >= 16) mL16 += a; else mS16 += c; }
+          else { mS1 += c; mS16 += c; }
         }
-        int xL = mineL, xS = mineS;
+        int xL1 = mL1, xS1 = mS1, xL16 = mL16, xS16 = mS16;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int yL = __shfl_up_sync(FULL, xL, o), yS = __shfl_up_sync(FULL, xS, o);
-          if (lane >= o) { xL += yL; xS += yS; }
+          const int a = __shfl_up_sync(FULL, xL1, o), b2 = __shfl_up_sync(FULL, xS1, o);
+          const int c2 = __shfl_up_sync(FULL, xL16, o), d2 = __shfl_up_sync(FULL, xS16, o);
+          if (lane >= o) { xL1 += a; xS1 += b2; xL16 += c2; xS16 += d2; }
         }
-        if (lane == 31) { s_misc[4 + warp] = xL; s_misc[4 + WARPS + warp] = xS; }
+        if (lane == 31) { s_misc[4 + warp] = xL1; s_misc[4 + WARPS + warp] = xS1; s_misc[4 + 2 * WARPS + warp] = xL16; s_misc[4 + 3 * WARPS + warp] = xS16; }
         __syncthreads();
-        int baseL = 0, baseS = 0, totL = 0;
+        int bL1 = 0, bS1 = 0, bL16 = 0, bS16 = 0, tL1 = 0, tS1 = 0, tL16 = 0;
         for (int w = 0; w < WARPS; ++w) {
-          if (w < warp) { baseL += s_misc[4 + w]; baseS += s_misc[4 + WARPS + w]; }
-          totL += s_misc[4 + w];
+          const int a = s_misc[4 + w], b2 = s_misc[4 + WARPS + w], c2 = s_misc[4 + 2 * WARPS + w], d2 = s_misc[4 + 3 * WARPS + w];
+          if (w < warp) { bL1 += a; bS1 += b2; bL16 += c2; bS16 += d2; }
+          tL1 += a; tS1 += b2; tL16 += c2;
         }
+        // padded region (rounded up to a whole step) + unpadded remainder + trailing dummies / prefetch must fit
+        const int th = (((tL1 + 31) & ~31) + tS1 + 96 <= SORT_CAP) ? 1 : 16;
+        const int mineL = th == 1 ? mL1 : mL16, mineS = th == 1 ? mS1 : mS16;
+        const int xL = th == 1 ? xL1 : xL16, xS = th == 1 ? xS1 : xS16;
+        const int baseL = th == 1 ? bL1 : bL16, baseS = th == 1 ? bS1 : bS16, totL = th == 1 ? tL1 : tL16;
         const int large_end = (totL + 31) & ~31;               // the masked region starts on a step boundary
         int runL = baseL + xL - mineL, runS = large_end + baseS + xS - mineS;
         for (int i = lo; i < hi; ++i) {
           const int c = s_hist[i];
-          if (c >= 16 && !(i & 1)) { s_hist[i] = runL; runL += (c + 15) & ~15; }
+          if (c >= th && !(i & 1)) { s_hist[i] = runL; runL += (c + 15) & ~15; }
           else { s_hist[i] = runS; runS += c; }
         }
         if (tid == THREADS - 1) { s_misc[0] = runS; s_misc[2] = large_end; s_misc[1] = 0; }
@@ -1151,44 +826,41 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Param
         const int steps = (list_end + 31) >> 5;
         float* tabA = my_priv + (size_t)vertA * cells_pad * 4;
         float* tabB = my_priv + (size_t)vertB * cells_pad * 4;
-        float dA[2] = {0.f, 0.f};                  // A: corner fg, heads 2ft, 2ft+1
+        float dA[4] = {0.f, 0.f, 0.f, 0.f};        // A: corner fg, heads 2ft, 2ft+1 ([2], [3]: the unused rows 8-15, always 0)
         float dB[4] = {0.f, 0.f, 0.f, 0.f};        // B window: rows fg and fg + 8 = ((z,y) corner, x slot)
-        unsigned curA = WILD, curB = WILD;         // cell keys nz << 8 | ny << 4 | x ; for B: x = window base + 2
+        // Cell keys are LINEAR table offsets ((nz * P3 + ny) * P3 + x, in cells of the zero-padded private table; for B: x =
+        // window base + 2), so a flush is one add per lane: element = key * 4 + a lane-constant offset of this lane's row.
+        // A fragment element that maps outside the table (window slots left of x = 0 / right of the padding, vertices
+        // outside the table) never receives a weight, so "value != 0" is also the bounds check.
+        unsigned curA = WILD, curB = WILD;
+        const int offA = ((((fg >> 2) * P.P3 + ((fg >> 1) & 1)) * P.P3 + (fg & 1)) << 2) + 2 * ft;
+        const int offB = (((((fg >> 2) & 1) * P.P3) + (fg & 3) - 2) << 2) + 2 * ft;       // rows fg: z corner 0, y corner fg >> 2
+        const int offB2 = (P.P3 * P.P3) << 2;                                              // rows fg + 8: z corner 1
 
         auto flushA = [&]() {
-          if (curA != WILD) {
-            const int nx = curA & 15, ny = (curA >> 4) & 15, nz = (curA >> 8) & 15;
-            if (nx <= P.n && ft < 2 && (dA[0] != 0.f || dA[1] != 0.f))
-              red_add_v2(tabA + ((((nz + (fg >> 2)) * P.P3 + (ny + ((fg >> 1) & 1))) * P.P3 + (nx + (fg & 1))) << 2) + 2 * ft, dA[0], dA[1]);
-          }
+          if (curA != WILD && ft < 2 && (dA[0] != 0.f || dA[1] != 0.f)) red_add_v2(tabA + (int)(curA << 2) + offA, dA[0], dA[1]);
           dA[0] = 0.f; dA[1] = 0.f;
         };
         auto flushB = [&]() {
           if (curB != WILD && ft < 2) {
-            const int xp = (int)(curB & 15) - 2 + (fg & 3), ny = (curB >> 4) & 15, nz = (curB >> 8) & 15;
-            if (xp >= 0 && xp < P.P3) {
-              const int zyc = fg >> 2;             // rows fg: (z,y) corners 0,1 ; rows fg + 8: corners 2,3 (z + 1)
-              float* a0 = tabB + ((((nz) * P.P3 + (ny + (zyc & 1))) * P.P3 + xp) << 2) + 2 * ft;
-              if (dB[0] != 0.f || dB[1] != 0.f) red_add_v2(a0, dB[0], dB[1]);
-              if (dB[2] != 0.f || dB[3] != 0.f) red_add_v2(a0 + ((P.P3 * P.P3) << 2), dB[2], dB[3]);
-            }
+            float* a0 = tabB + (int)(curB << 2) + offB;
+            if (dB[0] != 0.f || dB[1] != 0.f) red_add_v2(a0, dB[0], dB[1]);
+            if (dB[2] != 0.f || dB[3] != 0.f) red_add_v2(a0 + offB2, dB[2], dB[3]);
           }
           dB[0] = 0.f; dB[1] = 0.f; dB[2] = 0.f; dB[3] = 0.f;
         };
-        auto mmaA = [&](uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-          float t[4] = {dA[0], dA[1], 0.f, 0.f};
-          mma_16816(t, a0, 0u, a2, 0u, b0, b1);
-          dA[0] = t[0]; dA[1] = t[1];
-        };
+        auto mmaA = [&](uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) { mma_16816(dA, a0, 0u, a2, 0u, b0, b1); };
 
         const unsigned sely = ys ? 0x7432u : 0x7410u, selz = zs ? 0x7432u : 0x7410u;
         for (;;) {
           int chunk = 0;
           if (lane == 0) chunk = atomicAdd(s_misc + 1, 1);
           chunk = __shfl_sync(FULL, chunk, 0);
-          const int s0 = chunk * CHUNK;
-          if (s0 >= steps) break;
-          const int s1 = min(steps, s0 + CHUNK);
+          // chunks are handed out from the END of the list: the unpadded tail (many cells per step) is the expensive part and
+          // must not be what the last warps are still working on while the others wait at the barrier
+          const int s1 = steps - chunk * CHUNK;
+          if (s1 <= 0) break;
+          const int s0 = max(0, s1 - CHUNK);
           const uint16_t* sp = s_sorted + s0 * 32 + lane;
           unsigned ent_n = *sp;
           uint4 rec_n = s_recs[ent_n];
@@ -1204,9 +876,10 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Param
             const bool tail = st >= large_steps;             // warp-uniform: masked region, B's window based at its own cell
 
             const unsigned xa = rec.w & 15u, xb = (rec.w >> 4) & 15u;
-            const unsigned zy = (((rec.w >> nbz) & 15u) << 8) | (((rec.w >> nby) & 15u) << 4);
-            const unsigned xa1 = xa == 15u ? 11u : xa;
-            unsigned keyA = zy | xa1, keyB = zy | (tail ? (xb == 15u ? 13u : xb + 2u) : xa1);
+            const unsigned zy = (((rec.w >> nbz) & 15u) * (unsigned)P.P3 + ((rec.w >> nby) & 15u)) * (unsigned)P.P3;
+            // (a vertex outside the table has zero weights: its key only has to be a harmless in-range cell)
+            const unsigned xa1 = xa == 15u ? 0u : xa;
+            unsigned keyA = zy + xa1, keyB = zy + (tail ? (xb == 15u ? 2u : xb + 2u) : xa1);
             if (ent == (unsigned)NP) { keyA = WILD; keyB = WILD; }
             const unsigned slot = (tail || xb == 15u) ? 0u : (2u - (xa - xb));        // class 0 in the large region: xa - xb in {0,1,2}
             const float fz = fmaf(__uint_as_float(__byte_perm(rec.z, 0x4B000000u, selz)), 0x1p-16f, -128.f);
@@ -1233,12 +906,18 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_win_kernel(const Param
               stg[96 + lane] = make_uint4(dv.x, dv.y, 0u, 0u);
               __syncwarp();
             }
-            // per 16-pair block: is it one cell for A and one window for B?  (dummy pairs match anything)
-            const unsigned refA = __shfl_sync(FULL, keyA, lane & 16), refB = __shfl_sync(FULL, keyB, lane & 16);
-            const unsigned eqA = __ballot_sync(FULL, keyA == refA || keyA == WILD), eqB = __ballot_sync(FULL, keyB == refB || keyB == WILD);
+            // per 16-pair block: is it one cell for A and one window for B?  (dummy pairs match anything.)  In the padded
+            // region every block is, by construction; only the unpadded tail has to look.
+            unsigned eqA = FULL, eqB = FULL;
+            if (tail) {
+              const unsigned refA = __shfl_sync(FULL, keyA, lane & 16), refB = __shfl_sync(FULL, keyB, lane & 16);
+              eqA = __ballot_sync(FULL, keyA == refA || keyA == WILD);
+              eqB = __ballot_sync(FULL, keyB == refB || keyB == WILD);
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const unsigned kA = __shfl_sync(FULL, keyA, 16 * h), kB = __shfl_sync(FULL, keyB, 16 * h);
+              const unsigned kA = __shfl_sync(FULL, keyA, 16 * h);
+              const unsigned kB = tail ? __shfl_sync(FULL, keyB, 16 * h) : kA;      // padded region: B's window hangs on A's cell
               if (kA == WILD && ((eqA >> (16 * h)) & 0xFFFFu) == 0xFFFFu) continue;          // a block of dummy pairs only
               uint32_t a0, a2, w0, w1, w2, w3, b0, b1;
               ldmatrix_x2_trans(rowA + h * 256, a0, a2);
@@ -1493,21 +1172,21 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   }();
   P.cost = cost;
   P.slow_count = slow_count;
-  // VDETR_DT_IMPL=3: the dt3 kernel for every query (the kernel of round 1); 4: dt4 (tensor-core accumulation, B masked);
-  // default 5: dt5 (x window for vertex B, padded large bins) for axis-aligned boxes + dt3 for the others (exits at once
-  // when there are none)
-  static const int impl = []() { const char* e = getenv("VDETR_DT_IMPL"); return (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 5; }();
-  const bool use_dt4 = impl >= 4;
-  P.only_slow = use_dt4 ? 1 : 0;
+  // default: the dt3 kernel for every query; VDETR_DT_IMPL=5: dt5 (tensor-core accumulation) for axis-aligned boxes + dt3
+  // for the others (exits at once when there are none)
+  const char* impl_env = getenv("VDETR_DT_IMPL");          // read per call: tests switch it at run time
+  const int impl = (impl_env && impl_env[0] == '5') ? 5 : 3;
+  const bool use_dt5 = impl == 5;
+  P.only_slow = use_dt5 ? 1 : 0;
   const int grid3 = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
   dt3::Params P4 = P;
-  P4.qblocks = (s->nQ + dt4::QB - 1) / dt4::QB;
-  P4.kchunks = (s->nK + dt4::KC - 1) / dt4::KC;
+  P4.qblocks = (s->nQ + dt5::QB - 1) / dt5::QB;
+  P4.kchunks = (s->nK + dt5::KC - 1) / dt5::KC;
   P4.units = s->B * P4.qblocks * P4.kchunks;
   const int grid4 = P4.units < vdetr_num_sms() ? P4.units : vdetr_num_sms();
-  const size_t smem4 = impl == 5 ? dt5::smem_bytes(n) : dt4::smem_bytes(n);
-  if (use_dt4 && smem4 > 232448) return VDETR_ERR_UNSUPPORTED;
-  const int copies = (use_dt4 && grid4 > grid3) ? grid4 : grid3;
+  const size_t smem4 = dt5::smem_bytes(n);
+  if (use_dt5 && smem4 > 232448) return VDETR_ERR_UNSUPPORTED;
+  const int copies = (use_dt5 && grid4 > grid3) ? grid4 : grid3;
   const size_t copy_bytes = (size_t)8 * P.P3 * P.P3 * P.P3 * 4 * sizeof(float);
 
   VdetrTimingScope timing(VDETR_T_DTABLES, st);
@@ -1518,10 +1197,6 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   if (impl == 5) {
     VDETR_CUDA_TRY(cudaFuncSetAttribute(dt5::rpe_dtables_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
     dt5::rpe_dtables_win_kernel<<<grid4, dt5::THREADS, smem4, st>>>(P4);
-    VDETR_LAUNCH_CHECK();
-  } else if (impl == 4) {
-    VDETR_CUDA_TRY(cudaFuncSetAttribute(dt4::rpe_dtables_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-    dt4::rpe_dtables_mma_kernel<<<grid4, dt4::THREADS, smem4, st>>>(P4);
     VDETR_LAUNCH_CHECK();
   }
   VDETR_CUDA_TRY(cudaFuncSetAttribute(dt3::rpe_dtables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
