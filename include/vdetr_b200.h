@@ -99,7 +99,8 @@ typedef struct VdetrXattnShape {
 } VdetrXattnShape;
 
 /* Forward:  O = softmax_k(Q K^T + rpe(ref_pts, xyz, tables)) V        (fp32 in / fp32 out interface)
- *   q       [B,nQ,H,hd] f32, ALREADY multiplied by hd^-0.5            (vdetr_transformer.py:736-738)
+ *   q       [B,nQ,H,hd] f32, ALREADY multiplied by hd^-0.5            (vdetr_transformer.py:736-738); q, k, v (and dout in
+ *           the backward) must be 16-byte aligned
  *   k, v    [B,nK,kv_heads,hd] f32                                    (:734-735)
  *   xyz     [B,nK,3] f32 ; ref_pts [B,nQ,8,3] f32 ; ref_angle [B,nQ] f32 or NULL   (:708-720)
  *   tables  [8,grid_n,grid_n,grid_n,H] f32 = cpb_mlps[i](relative_coords_table), a=z,b=y,c=x (:725)

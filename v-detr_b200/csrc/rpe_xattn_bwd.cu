@@ -544,6 +544,8 @@ int tc_xattn_bwd(const VdetrXattnShape* s, const float* q, const float* k, const
   const bool mqa = s->kv_heads == 1;
   if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
   if (!(drop_p >= 0.f) || drop_p >= 1.f || (drop_p > 0.f && !drop_seed)) return VDETR_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout)) & 15)
+    return VDETR_ERR_BAD_ARG;                                 // the pack kernel uses float4 loads
   const bool recompute = s->has_bias && bias_saved == nullptr;
   const BwdPlan pl = make_plan(s, recompute);
   if (!ws || ws_bytes < pl.total || (reinterpret_cast<uintptr_t>(ws) & 255) != 0) return VDETR_ERR_WORKSPACE;

@@ -430,61 +430,65 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(xs - __half2float(hi));
 }
 
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_f16(v.x, h0, l0); split_f16(v.y, h1, l1); split_f16(v.z, h2, l2); split_f16(v.w, h3, l3);
+  const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+}
+__device__ __forceinline__ uint2 sat4(const float4 v, float s) {
+  const __half2 a = __floats2half2_rn(fminf(fmaxf(v.x * s, -65504.f), 65504.f), fminf(fmaxf(v.y * s, -65504.f), 65504.f));
+  const __half2 b = __floats2half2_rn(fminf(fmaxf(v.z * s, -65504.f), 65504.f), fminf(fmaxf(v.w * s, -65504.f), 65504.f));
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+// Row operands (Q / dO, K / row-major V), key xyz and query geometry.  One thread per group of 4 consecutive channels:
+// float4 loads, 8-byte fp16 stores.  (V^T has its own kernel: it is a transposition.)
 __global__ void vdetr_pack_kernel(VdetrPack K) {
   const float gscale = K.dout ? vdetr_grad_scale(*K.dout_absmax_bits) : 1.f;
-  const size_t nq = K.qp ? (size_t)K.B * K.nQp * 4 * 64 : 0;           // destination elements of Qp
-  const size_t nk = K.kp ? (size_t)K.B * K.kvh * K.nKp * 64 : 0;
+  const size_t nq = K.qp ? (size_t)K.B * K.nQp * 4 * 16 : 0;           // float4 groups of Qp
+  const size_t nk = K.kp ? (size_t)K.B * K.kvh * K.nKp * 16 : 0;
   const size_t nx = K.has_bias ? (size_t)K.B * K.nKp : 0;
   const size_t ng = K.has_bias ? (size_t)K.B * K.nQp : 0;
-  const size_t total = nq + 2 * nk + nx + ng;
+  const size_t total = nq + nk + nx + ng;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     if (i < nq) {
       // destination row-major [rows][64]; MQA rows = (b*nQp + q)*4 + h ; MHA rows = (b*4 + h)*nQp + q
-      const int d = (int)(i & 63);
-      const size_t r = i >> 6;
+      const int d4 = (int)(i & 15);
+      const size_t r = i >> 4;
       int b, q, h;
       if (K.kvh == 1) { h = (int)(r & 3); q = (int)((r >> 2) % K.nQp); b = (int)((r >> 2) / K.nQp); }
       else { q = (int)(r % K.nQp); h = (int)((r / K.nQp) & 3); b = (int)(r / ((size_t)K.nQp * 4)); }
-      float val = 0.f;
-      if (q < K.nQ) val = K.q[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
-      __half vh, vl;
-      split_f16(val, vh, vl);
-      K.qp[i] = vh;
-      if (K.qpl) K.qpl[i] = vl;
+      const size_t src = ((((size_t)b * K.nQ + q) * 4 + h) * 64) / 4 + d4;
+      const float4 val = q < K.nQ ? __ldg(reinterpret_cast<const float4*>(K.q) + src) : zero4;
+      uint2 hi, lo;
+      split4(val, hi, lo);
+      reinterpret_cast<uint2*>(K.qp)[i] = hi;
+      if (K.qpl) reinterpret_cast<uint2*>(K.qpl)[i] = lo;
       if (K.dout) {
-        float dv = 0.f;
-        if (q < K.nQ) dv = K.dout[(((size_t)b * K.nQ + q) * 4 + h) * 64 + d];
-        K.dop[i] = __float2half_rn(dv * gscale);
+        const float4 dv = q < K.nQ ? __ldg(reinterpret_cast<const float4*>(K.dout) + src) : zero4;
+        reinterpret_cast<uint2*>(K.dop)[i] = sat4(dv, gscale);
       }
     } else if (i < nq + nk) {
-      const size_t e = i - nq;                               // Kp [b][hk][key][d]
-      const int d = (int)(e & 63);
-      const size_t r = e >> 6;
+      const size_t e = i - nq;                               // Kp [b][hk][key][64]
+      const int d4 = (int)(e & 15);
+      const size_t r = e >> 4;
       const int key = (int)(r % K.nKp);
       const int hk = (int)((r / K.nKp) % K.kvh), b = (int)(r / ((size_t)K.nKp * K.kvh));
-      float val = 0.f;
-      if (key < K.nK) val = K.k[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-      __half vh, vl;
-      split_f16(val, vh, vl);
-      K.kp[e] = vh;
-      if (K.kpl) K.kpl[e] = vl;
+      const size_t src = ((((size_t)b * K.nK + key) * K.kvh + hk) * 64) / 4 + d4;
+      const float4 val = key < K.nK ? __ldg(reinterpret_cast<const float4*>(K.k) + src) : zero4;
+      uint2 hi, lo;
+      split4(val, hi, lo);
+      reinterpret_cast<uint2*>(K.kp)[e] = hi;
+      if (K.kpl) reinterpret_cast<uint2*>(K.kpl)[e] = lo;
       if (K.vp) {                                            // row-major V as well (backward: dP = dO V^T)
-        float vv = 0.f;
-        if (key < K.nK) vv = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-        K.vp[e] = __float2half_rn(fminf(fmaxf(vv, -65504.f), 65504.f));
+        const float4 vv = key < K.nK ? __ldg(reinterpret_cast<const float4*>(K.v) + src) : zero4;
+        reinterpret_cast<uint2*>(K.vp)[e] = sat4(vv, 1.f);
       }
-    } else if (i < nq + 2 * nk) {
-      if (!K.vtp) continue;
-      const size_t e = i - nq - nk;                          // Vtp [b][hk][d][key]
-      const int key = (int)(e % K.nKp);
-      const size_t r = e / K.nKp;
-      const int d = (int)(r & 63);
-      const int hk = (int)((r >> 6) % K.kvh), b = (int)((r >> 6) / K.kvh);
-      float val = 0.f;
-      if (key < K.nK) val = K.v[(((size_t)b * K.nK + key) * K.kvh + hk) * 64 + d];
-      K.vtp[e] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
-    } else if (i < nq + 2 * nk + nx) {
-      const size_t e = i - nq - 2 * nk;
+    } else if (i < nq + nk + nx) {
+      const size_t e = i - nq - nk;
       const int key = (int)(e % K.nKp), b = (int)(e / K.nKp);
       float4 o = make_float4(1e9f, 1e9f, 1e9f, 0.f);
       if (key < K.nK) {
@@ -493,7 +497,7 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       }
       K.xyz4[e] = o;
     } else {
-      const size_t e = i - nq - 2 * nk - nx;
+      const size_t e = i - nq - nk - nx;
       const int q = (int)(e % K.nQp), b = (int)(e / K.nQp);
       float v[24];
 #pragma unroll
@@ -521,6 +525,29 @@ __global__ void vdetr_pack_kernel(VdetrPack K) {
       for (int t = 0; t < 6; ++t) dst[2 + t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
       dst[8] = make_float4(c, s, 0.f, 0.f);
     }
+  }
+}
+
+// V^T operand of the forward's P V product: v [B][nK][kvh][64] f32 -> vtp [B][kvh][64][nKp] fp16 (keys contiguous, zero padded).
+// A CTA transposes a 64-key x 64-channel tile through shared memory: coalesced float4 reads along the channels, coalesced
+// half2 stores along the keys (a thread-per-output-element kernel reads V with a 256-byte stride).
+__global__ void __launch_bounds__(256) vdetr_pack_vt_kernel(VdetrPack K) {
+  __shared__ float tile[64][65];
+  const int ktiles = K.nKp / 64;
+  const int t = blockIdx.x % ktiles, bh = blockIdx.x / ktiles;
+  const int hk = bh % K.kvh, b = bh / K.kvh;
+  const int key0 = t * 64;
+  for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    const int kl = i >> 4, d4 = i & 15, key = key0 + kl;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (key < K.nK) v = __ldg(reinterpret_cast<const float4*>(K.v + (((size_t)b * K.nK + key) * K.kvh + hk) * 64) + d4);
+    tile[kl][d4 * 4 + 0] = v.x; tile[kl][d4 * 4 + 1] = v.y; tile[kl][d4 * 4 + 2] = v.z; tile[kl][d4 * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    const int d = i >> 5, k2 = (i & 31) * 2;
+    const float a = fminf(fmaxf(tile[k2][d], -65504.f), 65504.f), c = fminf(fmaxf(tile[k2 + 1][d], -65504.f), 65504.f);
+    *reinterpret_cast<__half2*>(K.vtp + (((size_t)b * K.kvh + hk) * 64 + d) * K.nKp + key0 + k2) = __floats2half2_rn(a, c);
   }
 }
 
@@ -586,6 +613,7 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   const bool mqa = s->kv_heads == 1;
   if (s->has_bias && !mqa) return VDETR_ERR_UNSUPPORTED;
   if (!(drop_p >= 0.f) || drop_p >= 1.f || (drop_p > 0.f && !drop_seed)) return VDETR_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return VDETR_ERR_BAD_ARG;   // float4 loads
   const FwdPlan pl = make_plan(s);
   if (!ws || ws_bytes < pl.total) return VDETR_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return VDETR_ERR_WORKSPACE;      // cudaMalloc / torch give >= 256 B
@@ -602,6 +630,8 @@ int tc_xattn_fwd(const VdetrXattnShape* s, const float* q, const float* k, const
   pk.xyz4 = reinterpret_cast<float4*>(w + pl.off_xyz);
   pk.geo = reinterpret_cast<float4*>(w + pl.off_geo);
   vdetr_pack_kernel<<<vdetr_num_sms() * 4, 256, 0, st>>>(pk);
+  VDETR_LAUNCH_CHECK();
+  vdetr_pack_vt_kernel<<<s->B * s->kv_heads * (pl.nKp / 64), 256, 0, st>>>(pk);
   VDETR_LAUNCH_CHECK();
 
   CUtensorMap tmQ, tmQl, tmK, tmKl, tmVt;
