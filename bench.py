@@ -422,28 +422,56 @@ def main():
     config["launch"] = ("CUDA graph replay (fwd+bwd graph, eager NCCL all-reduce, optimizer graph)" if graph is not None
                         else "eager launches")
     fwd_ms = tot[0] / max(cnt[0], 1)
+    dt_ms = tot[2] / max(cnt[2], 1)
     achieved = flops_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
-    evals = 8.0 * NQ * NK * a.batch                            # vertex evaluations per fused-forward launch
+    evals = 8.0 * NQ * NK * a.batch                            # vertex evaluations per launch (forward bias / dTables adjoint)
+    pairs = float(NQ) * NK * a.batch
+    # ncu --set full captures of the same kernels at this batch (profiles/r2_ncu_traffic.json): DRAM bytes and executed
+    # warp-instructions per launch
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+    except Exception:
+        pass
+    full = a.batch == PER_GPU_BATCH
+    peak_bw = peaks.get("hbm_gbs", 6450.0)
+    # dTables (adjoint of the bias gather) is the dominant kernel of the step.  Its mandatory HBM traffic is the scaled fp16 dS
+    # of the 4 heads (8 B per pair) + key xyz + query geometry + the 128 KB result; the arithmetic minimum is 256 FMA per pair
+    # (8 vertices x 8 corners x 4 heads) = 8 warp-instructions per pair.
+    dt_bytes = pairs * 8 + a.batch * (NK * 16 + NQ * 144) + 8 * 1000 * 4 * 4
+    dt_gbs = dt_bytes / (dt_ms * 1e-3) / 1e9 if dt_ms > 0 else 0.0
+    dt_inst = ncu.get("dtables", {}).get("warp_inst")
     line = {"metric": "scenes/sec fwd+bwd, 4096 keys x 1024 queries x 8 dec layers", "value": value, "unit": "scenes/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16/bf16 tensor-core operands (fp16: S=QK^T, O=PV; bf16: gradient GEMMs), fp32 bias/softmax/accumulate",
+            "dtype": "fp16 tensor-core operands (QK^T from hi/lo fp16 splits of fp32 q and k; P, V, dO, dS as (scaled) fp16), "
+                     "fp32 bias / softmax / accumulators; TF32 for the nn.Linear GEMMs",
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": own_launches_per_step * a.steps,
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "rpe_xattn_fwd_kernel<bias,MQA> (fused Vertex-RPE cross attention, forward)",
-                         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this batch, one ncu --set full
-                         # capture (profiles/r1_ncu_kernels.csv): 18.3 MB read + 516.5 MB written, the write being the
-                         # per-pair bias kept for the backward (16 B x 33.5 M pairs); algorithmic minimum 19 MB
-                         "traffic": 534751488 if a.batch == PER_GPU_BATCH else None,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
-                         "launch_ms": fwd_ms,
-                         "secondary_bound": {"what": "instruction issue of the bias gather: 1036 thread-instructions per (query,key) "
-                                                     "pair, issue slots 78 % / FMA pipe 58 % busy (ncu, DESIGN.md 4.1)",
-                                             "gevals_per_s": evals / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None}},
+            "roofline": {"kernel": "dt3::rpe_dtables_kernel (adjoint of the Vertex-RPE bias gather: the dominant kernel, "
+                                   f"{tot[2] / timed_eager_steps:.1f} ms of the step)",
+                         "bound": "hbm", "achieved": dt_gbs, "peak": peak_bw, "unit": "GB/s", "frac": dt_gbs / peak_bw if peak_bw else None,
+                         "traffic": ncu.get("dtables", {}).get("dram_bytes") if full else None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6450",
+                         "launch_ms": dt_ms, "algorithmic_bytes": dt_bytes,
+                         "secondary_bound": {"what": "instruction issue, not memory: the kernel sorts the pairs of a unit by table cell "
+                                                     "and accumulates in registers (DESIGN.md 4.3)",
+                                             "warp_inst_per_pair": dt_inst / pairs if (dt_inst and full) else None,
+                                             "warp_inst_per_pair_minimum": 8.0,
+                                             "gevals_per_s": evals / (dt_ms * 1e-3) / 1e9 if dt_ms > 0 else None}},
+            "roofline_attention": {"kernel": "rpe_xattn_fwd_kernel<bias,MQA> (fused Vertex-RPE cross attention, forward: the kernel "
+                                             "north_star names)",
+                                   "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                                   "frac": achieved / peak_tf if peak_tf else None,
+                                   # the write of the per-pair bias kept for the backward (16 B x pairs) dominates; algorithmic minimum 19 MB
+                                   "traffic": ncu.get("xattn_fwd", {}).get("dram_bytes") if full else None,
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                                   "launch_ms": fwd_ms,
+                                   "secondary_bound": {"what": "instruction issue of the bias gather (8 vertices x 4 (z,y) corners x one "
+                                                               "LDS.128 + fp16->fp32 conversions + FFMA per pair), DESIGN.md 4.1",
+                                                       "gevals_per_s": evals / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None}},
             "kernel_ms_per_step": {"xattn_fwd": tot[0] / timed_eager_steps, "xattn_bwd_pass1": tot[1] / timed_eager_steps,
                                    "dtables": tot[2] / timed_eager_steps, "xattn_bwd_pass2_dkdv": tot[3] / timed_eager_steps,
                                    "launches_per_step": [int(c) // timed_eager_steps for c in cnt],

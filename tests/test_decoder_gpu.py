@@ -283,3 +283,33 @@ def test_fused_box_decode_and_grouped_heads_equal_the_plain_paths():
     for n in pb:
         if n.endswith("center_head.layers.8.weight") or n.endswith("size_head.layers.8.weight"):
             assert (pa[n] - pb[n]).abs().max().item() <= 2e-3 * (pb[n].abs().max().item() + 1e-9), n
+
+
+def test_decoder_c2_shape_vs_oracle_port_per_layer():
+    """BASELINE config C2: one ScanNet-shaped scene, 4096 keys x 1024 queries x 8 decoder layers, eval mode -- the product on
+    the GPU against the CPU oracle port, error per layer (logged to gpurun_out/parity_r2.jsonl).  Weights: the reference's
+    own initialisation (xavier_uniform, zero-initialised centre / size heads) under a fixed seed, shared through the
+    state_dict."""
+    B, nK, nq, L = 1, 4096, 1024, 8
+    torch.manual_seed(0)
+    ora = odt.OracleDecoder(num_layers=L, num_queries=nq).eval()
+    with torch.no_grad():                                   # non-trivial box refinement: the reference zero-initialises these
+        for hs in ora.mlp_heads:
+            for name in ("center_head", "size_head"):
+                hs[name].layers[-1].weight.normal_(0.0, 0.02)
+    dec = build_product_decoder(L, nq)
+    dec.load_state_dict(ora.state_dict())
+    dec = dec.cuda().eval()
+    c = recipe.decoder_case(77, B, nK)
+    with torch.no_grad():
+        want, _ = ora(torch.from_numpy(c["feat"]), torch.from_numpy(c["xyz"]), [torch.from_numpy(c["mins"]), torch.from_numpy(c["maxs"])],
+                      torch.from_numpy(c["center_normalized"]), torch.from_numpy(c["size_normalized"]))
+    got, _ = _run_product(dec, c, False)
+    worst = []
+    for li, (dg, dw) in enumerate(zip(got["aux_outputs"] + [got["outputs"]], want["aux_outputs"] + [want["outputs"]])):
+        errs = {k: float(np.abs(dg[k].float().cpu().numpy() - dw[k].numpy()).max() / (np.abs(dw[k].numpy()).max() + 1e-6)) for k in KEYS}
+        worst.append(max(errs.values()))
+        _log(f"C2 4096x1024x8 eval vs oracle port, level {li} worst of {len(KEYS)} outputs", worst[-1])
+    assert worst[0] <= 1e-5                                  # proposal stage: no attention involved
+    assert worst[1] <= 1e-3, worst                           # one decoder layer: north_star's tolerance
+    assert max(worst) <= 5e-3, worst                         # eight layers deep
