@@ -285,11 +285,14 @@ def test_fused_box_decode_and_grouped_heads_equal_the_plain_paths():
             assert (pa[n] - pb[n]).abs().max().item() <= 2e-3 * (pb[n].abs().max().item() + 1e-9), n
 
 
-def test_decoder_c2_shape_vs_oracle_port_per_layer():
+def test_decoder_c2_shape_vs_oracle_port_per_layer(monkeypatch):
     """BASELINE config C2: one ScanNet-shaped scene, 4096 keys x 1024 queries x 8 decoder layers, eval mode -- the product on
     the GPU against the CPU oracle port, error per layer (logged to gpurun_out/parity_r2.jsonl).  Weights: the reference's
     own initialisation (xavier_uniform, zero-initialised centre / size heads) under a fixed seed, shared through the
-    state_dict."""
+    state_dict.  The 1024 queries are the top-k of 4096 proposal scores: adjacent scores are ~1e-4 apart, so the 1e-6
+    difference between a CPU and a GPU fp32 GEMM swaps a few near-tied ranks and thereby permutes per-query outputs.  The
+    numeric comparison therefore runs the product on the oracle's selection, and the product's own selection is checked
+    separately (same set up to near-ties)."""
     B, nK, nq, L = 1, 4096, 1024, 8
     torch.manual_seed(0)
     ora = odt.OracleDecoder(num_layers=L, num_queries=nq).eval()
@@ -304,7 +307,22 @@ def test_decoder_c2_shape_vs_oracle_port_per_layer():
     with torch.no_grad():
         want, _ = ora(torch.from_numpy(c["feat"]), torch.from_numpy(c["xyz"]), [torch.from_numpy(c["mins"]), torch.from_numpy(c["maxs"])],
                       torch.from_numpy(c["center_normalized"]), torch.from_numpy(c["size_normalized"]))
+    want_top = torch.topk(want["aux_outputs"][0]["objectness_prob"], nq, dim=1)[1]
+    real_topk, seen = torch.topk, {}
+
+    def topk_on_oracle_selection(score, k, dim=-1, **kw):
+        vals, idx = real_topk(score, k, dim=dim, **kw)
+        if k == nq and tuple(score.shape) == (B, nK):
+            seen["own"] = idx.cpu()
+            return vals, want_top.to(idx.device)
+        return vals, idx
+    monkeypatch.setattr(torch, "topk", topk_on_oracle_selection)
     got, _ = _run_product(dec, c, False)
+    monkeypatch.setattr(torch, "topk", real_topk)
+    assert "own" in seen
+    common = len(set(seen["own"][0].tolist()) & set(want_top[0].tolist()))
+    _log("C2 top-k selection: fraction of the oracle's 1024 proposals the product selects itself", common / nq)
+    assert common >= nq - 8
     worst = []
     for li, (dg, dw) in enumerate(zip(got["aux_outputs"] + [got["outputs"]], want["aux_outputs"] + [want["outputs"]])):
         errs = {k: float(np.abs(dg[k].float().cpu().numpy() - dw[k].numpy()).max() / (np.abs(dw[k].numpy()).max() + 1e-6)) for k in KEYS}

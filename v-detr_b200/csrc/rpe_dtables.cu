@@ -58,14 +58,7 @@ struct Params {
   unsigned long long* phase_clocks;       // [8] optional (developer): cycles per phase summed over CTAs, else null
 };
 
-__device__ __forceinline__ float scale_of(unsigned bits, int dense) {
-  if (!dense) return vdetr_grad_scale(bits);
-  const float m = __uint_as_float(bits);
-  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
-  float e = floorf(log2f(16384.f / m));
-  e = fminf(fmaxf(e, -100.f), 100.f);
-  return exp2f(e);
-}
+__device__ __forceinline__ float scale_of(unsigned bits, int dense) { return vdetr_dt_scale(bits, dense); }
 
 // one axis: cell index + 1 in [0, n] (15 = both corners outside the table) and the 16-bit fraction
 __device__ __forceinline__ void axis_rec(float d, float ls, float c1, float c0, int n, unsigned& nib, unsigned& frac) {
@@ -1126,7 +1119,7 @@ extern "C" int vdetr_debug_dt_clocks(unsigned long long* out8) {
 size_t rpe_dtables_scratch_bytes(const VdetrXattnShape* s) {
   const int P3 = s->grid_n + 2;
   return vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024) + 1024 +
-         vdetr_align_up((size_t)vdetr_num_sms() * 8 * P3 * P3 * P3 * 4 * sizeof(float), 1024);
+         vdetr_align_up((size_t)vdetr_num_sms() * 8 * P3 * P3 * P3 * 4 * sizeof(float), 1024) + vdetr_align_up(rpe_dt6_priv_bytes(), 1024);
 }
 
 // dsb: scale * dS as fp16 rows [(b*nQp + q)*4 + h][nKp]; scale derives from *absmax_bits (vdetr_grad_scale, or the
@@ -1148,6 +1141,8 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   int* qperm = reinterpret_cast<int*>(w);
   int* slow_count = reinterpret_cast<int*>(w + vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024));
   float* priv = reinterpret_cast<float*>(w + vdetr_align_up((size_t)s->B * s->nQ * sizeof(int), 1024) + 1024);
+  float* priv6 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(priv) +
+                                          vdetr_align_up((size_t)vdetr_num_sms() * 8 * (n + 2) * (n + 2) * (n + 2) * 4 * sizeof(float), 1024));
 
   dt3::Params P = {};
   P.B = s->B; P.nQ = s->nQ; P.nK = s->nK; P.nQp = nQp; P.nKp = nKp; P.n = n; P.R = n + 1; P.P3 = n + 2;
@@ -1172,12 +1167,12 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   }();
   P.cost = cost;
   P.slow_count = slow_count;
-  // default: the dt3 kernel for every query; VDETR_DT_IMPL=5: dt5 (tensor-core accumulation) for axis-aligned boxes + dt3
-  // for the others (exits at once when there are none)
+  // default (6): dt6, the dense tcgen05 contraction (rpe_dtables_umma.cu), for axis-aligned boxes + dt3 for the others (it
+  // exits at once when there are none); VDETR_DT_IMPL=3: the dt3 kernel for every query; =5: dt5 (mma.sync accumulation) + dt3
   const char* impl_env = getenv("VDETR_DT_IMPL");          // read per call: tests switch it at run time
-  const int impl = (impl_env && impl_env[0] == '5') ? 5 : 3;
+  const int impl = (impl_env && impl_env[0] == '5') ? 5 : (impl_env && impl_env[0] == '3') ? 3 : 6;
   const bool use_dt5 = impl == 5;
-  P.only_slow = use_dt5 ? 1 : 0;
+  P.only_slow = impl != 3 ? 1 : 0;
   const int grid3 = P.units < vdetr_num_sms() ? P.units : vdetr_num_sms();
   dt3::Params P4 = P;
   P4.qblocks = (s->nQ + dt5::QB - 1) / dt5::QB;
@@ -1205,6 +1200,7 @@ int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4*
   const int total = 8 * n * n * n * 4;
   dt3::rpe_dtables_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(priv, copies, n, P.P3, dtables, absmax_bits, dense_scale);
   VDETR_LAUNCH_CHECK();
+  if (impl == 6) return rpe_dt6_launch(s, nQp, nKp, xyz4, geo, dsb, absmax_bits, dense_scale, dtables, 1, priv6, st);
   return 0;
 }
 

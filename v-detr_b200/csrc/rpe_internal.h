@@ -65,6 +65,21 @@ __device__ __forceinline__ float vdetr_grad_scale(unsigned absmax_bits) {
   return exp2f(e);
 }
 
+// scale of the fp16 dS rows the dTables kernels read: the backward's gradient scale, or (dense C-ABI helper) its own rule
+__device__ __forceinline__ float vdetr_dt_scale(unsigned bits, int dense) {
+  if (!dense) return vdetr_grad_scale(bits);
+  const float m = __uint_as_float(bits);
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
+  float e = floorf(log2f(16384.f / m));
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
+
+// dTables of axis-aligned boxes as a dense tcgen05 contraction (rpe_dtables_umma.cu)
+size_t rpe_dt6_priv_bytes();
+int rpe_dt6_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const __half* dsb,
+                   const unsigned* absmax_bits, int dense_scale, float* dtables, int accumulate, float* priv, cudaStream_t st);
+
 // dTables (rpe_dtables.cu)
 size_t rpe_dtables_scratch_bytes(const VdetrXattnShape* s);
 int rpe_dtables_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz4, const float4* geo, const __half* dsb,
