@@ -290,9 +290,11 @@ def main():
     from vdetr_b200 import parallel
     model = dec
     use_graph = not a.no_graph and not a.profile
-    opt = torch.optim.AdamW([p for p in dec.parameters() if p.requires_grad], lr=1e-5, weight_decay=0.1, fused=True,
-                            capturable=use_graph)
-    gsync = parallel.FlatGradAllReduce(dec.parameters())    # all .grad are views of one buffer: ONE NCCL all-reduce / step
+    # AdamW on flat buffers (parallel.FlatAdamW, csrc/optim.cu: one launch per step); its gradient views are the buffer
+    # that is all-reduced: ONE NCCL all-reduce per step, the 1 / world factor folded into the optimizer's gradient scale
+    opt = parallel.FlatAdamW(dec.named_parameters(), lr=1e-5, weight_decay=0.1)
+    opt.world_scale = 1.0 / world
+    gsync = opt.grads
     lo, hi = parallel.shard_range(a.batch * world, rank, world)     # scenes [lo, hi) of the global batch live on this rank
     assert hi - lo == a.batch
     host = synth_scene(a.batch, NK, lo, torch)
@@ -313,7 +315,7 @@ def main():
 
     def step(inp, fetch_loss):
         loss = fwd_bwd(inp)
-        gsync.sync_()          # N > 1: the single NCCL all-reduce of the flat gradient buffer
+        gsync.sync_(average=False)   # N > 1: the single NCCL all-reduce (SUM) of the flat gradient buffer
         opt.step()
         return loss.item() if fetch_loss else loss
 
@@ -373,7 +375,7 @@ def main():
 
         def graph_step():
             graph.replay()
-            gsync.sync_()
+            gsync.sync_(average=False)
             graph_opt.replay()
             return static_loss
 

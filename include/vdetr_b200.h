@@ -228,6 +228,15 @@ int vdetr_box_decode_bwd(const float* size, const float* pre_size, const float* 
 int vdetr_lsap(const float* cost, const int32_t* nactual_gt, int B, int nQ, int ngt, long long* per_prop_gt_inds,
                float* proposal_matched_mask, void* stream);
 
+/* AdamW on flat buffers (replaces the multi-tensor torch.optim.AdamW the reference builds in optimizer.py:25 and steps in
+ * engine.py:105-108): p, g, m, v are device arrays of n floats (16-byte aligned); elements [0, n_decay) are weight-decayed.
+ * lr [1], step [1] (the 1-based step count as a float, already incremented) and the optional grad_scale [1] live in DEVICE
+ * memory so that a captured CUDA graph follows a schedule; the gradient is multiplied by grad_scale_host * grad_scale[0]
+ * (1 / world size, gradient-norm clipping of engine.py:105-106).  Same update as torch.optim.AdamW. */
+int vdetr_adamw_flat(float* p, const float* g, float* m, float* v, long long n, long long n_decay, const float* lr,
+                     const float* step, const float* grad_scale, float grad_scale_host, float beta1, float beta2, float eps,
+                     float weight_decay, void* stream);
+
 /* Developer aid: with VDETR_DT_CLOCKS=1 in the environment the dTables kernel sums the SM cycles each of its phases
  * takes ([0] records, [1] zero+B0, [2] histogram, [3] scan, [4] scatter, [5] accumulate) over all CTAs; this call
  * copies the 8 counters to the host and clears them (synchronises the device). */

@@ -53,6 +53,7 @@ _SIGS = {
                                     c_void_p, c_void_p]),
     "vdetr_reduce_workspace_floats": (c_size_t, [c_int]),
     "vdetr_colsum_workspace_floats": (c_size_t, [c_int]),
+    "vdetr_adamw_flat": (c_int, [c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p, c_void_p] + [c_float] * 5 + [c_void_p]),
     "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vdetr_bn_relu_supported": (c_int, [c_int]),
     "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong,

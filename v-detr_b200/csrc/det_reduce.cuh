@@ -8,9 +8,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
-constexpr int VDETR_RED_MAX_BLOCKS = 64;       // partial sums per reduction (grids of the reducing kernels are capped to this)
+constexpr int VDETR_RED_MAX_BLOCKS = 128;      // partial sums per reduction (grids of the reducing kernels are capped to this)
 
-// workspace of one reduction over `cols` columns of two quantities: [2 * cols] results, [64][2 * cols] partials, ticket
+// workspace of one reduction over `cols` columns of two quantities: [2 * cols] results, [128][2 * cols] partials, ticket
 static inline size_t vdetr_reduce_ws_floats(int cols) { return (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols + 32; }
 
 // Called by ALL threads of every CTA after the CTA has written part[blockIdx.x * ncols + c] for all c.

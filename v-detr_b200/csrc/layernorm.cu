@@ -71,19 +71,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float4* __r
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = ag[i];
   }
-  for (int r = blockIdx.x * LN_WARPS + warp; r < rows; r += gridDim.x * LN_WARPS) {
+  // two rows per iteration: the 4 * VEC loads of both rows are issued before either is consumed (the kernel streams 3 x 8 MB
+  // per call and was latency bound with one row in flight per warp)
+  auto row = [&](int r, const float4 (&xv)[VEC], const float4 (&d)[VEC]) {
     const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
     float4 xh[VEC], g[VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 xv = x[(size_t)r * C4 + i * 32 + lane], d = dy[(size_t)r * C4 + i * 32 + lane];
-      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      xh[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
+      g[i] = make_float4(d[i].x * gm[i].x, d[i].y * gm[i].y, d[i].z * gm[i].z, d[i].w * gm[i].w);
       s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
       s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-      ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+      ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
     }
     const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
 #pragma unroll
@@ -91,6 +92,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float4* __r
       dx[(size_t)r * C4 + i * 32 + lane] =
           make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2), rs * (g[i].z - m1 - xh[i].z * m2),
                       rs * (g[i].w - m1 - xh[i].w * m2));
+  };
+  const int stride = gridDim.x * LN_WARPS;
+  int r = blockIdx.x * LN_WARPS + warp;
+  for (; r + stride < rows; r += 2 * stride) {
+    float4 xa[VEC], da[VEC], xb[VEC], db[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      xa[i] = x[(size_t)r * C4 + i * 32 + lane]; da[i] = dy[(size_t)r * C4 + i * 32 + lane];
+      xb[i] = x[(size_t)(r + stride) * C4 + i * 32 + lane]; db[i] = dy[(size_t)(r + stride) * C4 + i * 32 + lane];
+    }
+    row(r, xa, da);
+    row(r + stride, xb, db);
+  }
+  if (r < rows) {
+    float4 xa[VEC], da[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { xa[i] = x[(size_t)r * C4 + i * 32 + lane]; da[i] = dy[(size_t)r * C4 + i * 32 + lane]; }
+    row(r, xa, da);
   }
   // column sums of this CTA: warps -> shared memory -> per-CTA partial sums -> last CTA adds them in block order
 #pragma unroll
@@ -125,7 +144,7 @@ int launch_bwd(const float* dy, const float* x, const float* mean, const float* 
   // enough rows per warp to amortise the column reduction; at most 64 CTAs (= partial sums of the final reduction)
   constexpr int C = VEC * 128;
   int grid = (rows + LN_WARPS * 4 - 1) / (LN_WARPS * 4);
-  grid = max(1, min(grid, VDETR_RED_MAX_BLOCKS));
+  grid = max(1, min(grid, VDETR_RED_MAX_BLOCKS));          // (the order of the row sums depends on the grid only: deterministic)
   float* part = ws + 2 * C;
   unsigned* ticket = reinterpret_cast<unsigned*>(ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * C);
   VDETR_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
@@ -209,6 +228,62 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   for (int b = 0; b < (int)gridDim.x; ++b) s[b & 3] += __ldcg(part + (size_t)b * cols + c);
   out[c] = (s[0] + s[1]) + (s[2] + s[3]);
 }
+// cols % 4 == 0, cols <= 1024, 16-byte aligned rows: a thread owns 4 adjacent columns (one float4 per row), the cols / 4 threads
+// of a row group walk the slice 8 rows at a time with all 8 loads in flight; row groups are combined through shared memory.
+__global__ void __launch_bounds__(256) colsum4_kernel(const float4* __restrict__ x, int rows, int c4, float* __restrict__ out,
+                                                      float* __restrict__ part, unsigned* __restrict__ tickets) {
+  __shared__ float4 red[256];
+  __shared__ bool s_last;
+  const int groups = 256 / c4, grp = threadIdx.x / c4, col = threadIdx.x % c4;
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grp < groups) {
+    int r = r0 + grp;
+    for (; r + 7 * groups < r1; r += 8 * groups) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = x[(size_t)(r + j * groups) * c4 + col];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j & 3].x += v[j].x; acc[j & 3].y += v[j].y; acc[j & 3].z += v[j].z; acc[j & 3].w += v[j].w; }
+    }
+    for (; r < r1; r += groups) {
+      const float4 v = x[(size_t)r * c4 + col];
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+    }
+  }
+  red[threadIdx.x] = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                                 (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  __syncthreads();
+  if (threadIdx.x < c4) {
+    float4 s = red[threadIdx.x];
+    for (int g = 1; g < groups; ++g) {
+      const float4 t = red[g * c4 + threadIdx.x];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    reinterpret_cast<float4*>(part)[(size_t)blockIdx.x * c4 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(tickets, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < c4 * 4; c += 256) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    int b = 0;
+    for (; b + 7 < (int)gridDim.x; b += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += __ldcg(part + (size_t)(b + j) * c4 * 4 + c);
+    }
+    for (int j = 0; b < (int)gridDim.x; ++b, ++j) s[j] += __ldcg(part + (size_t)b * c4 * 4 + c);
+    out[c] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  }
+}
 }  // namespace
 
 // workspace: vdetr_colsum_workspace_floats(cols) floats
@@ -220,6 +295,15 @@ extern "C" int vdetr_colsum(const float* x, int rows, int cols, float* out, floa
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) {
     VDETR_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
+    return 0;
+  }
+  if (cols % 4 == 0 && cols <= 1024 && 256 % (cols / 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && rows >= 256) {
+    int slices4 = (rows + 127) / 128;
+    slices4 = slices4 > VDETR_RED_MAX_BLOCKS ? VDETR_RED_MAX_BLOCKS : slices4;
+    unsigned* tk = reinterpret_cast<unsigned*>(workspace + (size_t)VDETR_RED_MAX_BLOCKS * cols);
+    VDETR_CUDA_TRY(cudaMemsetAsync(tk, 0, sizeof(unsigned), st));
+    colsum4_kernel<<<slices4, 256, 0, st>>>(reinterpret_cast<const float4*>(x), rows, cols / 4, out, workspace, tk);
+    VDETR_LAUNCH_CHECK();
     return 0;
   }
   const int threads = cols >= 256 ? 256 : ((cols + 31) / 32) * 32;

@@ -85,9 +85,85 @@ class FlatGradAllReduce:
         self._attached = True
         return self.flat
 
-    def sync_(self):
+    def sync_(self, average: bool = True):
+        """SUM all-reduce of the flat buffer; average=False leaves the 1 / world factor to the optimizer (FlatAdamW folds
+        it into its gradient scale: no extra pass over the buffer)."""
         self.gather_()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+            if average:
+                self.flat.div_(dist.get_world_size())
         return self.flat
+
+
+class FlatAdamW:
+    """torch.optim.AdamW semantics (the reference: optimizer.py:4-26, stepped after clip_grad_norm_ in engine.py:105-108) on
+    FLAT buffers: parameters are re-homed as views of one fp32 buffer, gradients are the views of FlatGradAllReduce, the two
+    moments are flat, and a step is ONE kernel launch (csrc/optim.cu) instead of ~22 multi-tensor launches over ~1000 small
+    tensors.  lr, the step count and the gradient scale live on the device, so the step can sit inside a captured CUDA graph
+    and still follow a learning-rate schedule (set_lr) or a clipped gradient norm.
+
+    no_decay(name, param) -> True puts a parameter into the group without weight decay (--filter_biases_wd)."""
+
+    def __init__(self, named_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, no_decay=None):
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        if not named:
+            raise ValueError("FlatAdamW: no trainable parameters")
+        dec = [(n, p) for n, p in named if not (no_decay and no_decay(n, p))]
+        nod = [(n, p) for n, p in named if no_decay and no_decay(n, p)]
+        self.names = [n for n, _ in dec + nod]
+        self.params = [p for _, p in dec + nod]
+        ref = self.params[0]
+        if not ref.is_cuda or any(p.dtype != torch.float32 or p.device != ref.device for p in self.params):
+            raise RuntimeError("FlatAdamW needs fp32 CUDA parameters on one device (there is no CPU path)")
+        self.n = sum(p.numel() for p in self.params)
+        self.n_decay = sum(p.numel() for _, p in dec)
+        self.flat_p = torch.empty(self.n, dtype=torch.float32, device=ref.device)
+        o = 0
+        with torch.no_grad():
+            for p in self.params:                      # parameters become views of the flat buffer (same values)
+                v = self.flat_p[o:o + p.numel()].view_as(p)
+                v.copy_(p)
+                p.data = v
+                o += p.numel()
+        self.grads = FlatGradAllReduce(self.params)    # same order: flat_g[i] is the gradient of flat_p[i]
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.lr = torch.tensor([lr], dtype=torch.float32, device=ref.device)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=ref.device)
+        self.grad_scale = torch.ones(1, dtype=torch.float32, device=ref.device)
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.world_scale = 1.0                         # 1 / world size when the all-reduce is a plain SUM
+
+    def set_lr(self, lr: float):
+        self.lr.fill_(lr)
+
+    def clip_grad_norm_(self, max_norm: float):
+        """torch.nn.utils.clip_grad_norm_ (engine.py:105-106) as a device-side scale of the flat gradient; returns the norm."""
+        norm = torch.linalg.vector_norm(self.grads.gather_()) * self.world_scale
+        torch.clamp(max_norm / (norm + 1e-6), max=1.0, out=self.grad_scale[0])
+        return norm
+
+    @torch.no_grad()
+    def step(self):
+        from . import _C
+        self.grads.gather_()
+        self.step_t += 1.0
+        with torch.cuda.device(self.flat_p.device):
+            _C.check(_C.lib().vdetr_adamw_flat(_C.ptr(self.flat_p), _C.ptr(self.grads.flat), _C.ptr(self.exp_avg),
+                                               _C.ptr(self.exp_avg_sq), self.n, self.n_decay, _C.ptr(self.lr), _C.ptr(self.step_t),
+                                               _C.ptr(self.grad_scale), float(self.world_scale), float(self.betas[0]),
+                                               float(self.betas[1]), float(self.eps), float(self.weight_decay), _C.stream_ptr()))
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.grads.zero_()
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_t.clone(),
+                "lr": self.lr.clone(), "names": list(self.names)}
+
+    def load_state_dict(self, sd):
+        if list(sd["names"]) != self.names:
+            raise ValueError("FlatAdamW.load_state_dict: parameter order differs")
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_t.copy_(sd["step"]); self.lr.copy_(sd["lr"])
