@@ -12,14 +12,19 @@
 // columns x 128 lanes) stay in tensor memory for the whole launch: no atomics, no flushes; every CTA leaves one private
 // copy and a second kernel sums the copies in a fixed order (bit-reproducible).
 //
-//   stage   = 64 pairs (one query x 64 consecutive keys): four A tiles [104 rows x 64 pairs] + one B tile [88 x 64], fp16,
-//             K-major rows of 128 B with the 128-byte swizzle (the layout TMA would write).  Rows >= 100 of A / >= 80 of B
-//             are dump rows for corners outside the table (zero padding of grid_sample), never read as results: the MMA
-//             (M = 128) reads 24 rows past each A tile, which only feeds accumulator lanes 104..127 that nobody reads.
-//   warps   : 3 stages x 4 producer warps (lane = pair; a warp owns 32 pairs and the z sign `vh`: it writes A_{vh,+},
-//             A_{vh,-} and the x^{vh} half of B), four MMA warps (one lane each issues the 4 K-steps of its variant per stage:
-//             tcgen05.mma M = 128, N = 80, K = 16).  A producer computes the next item while the MMAs of its stage run,
-//             then zeroes the 16 entries it wrote last time and writes the new ones.
+//   stage   = 64 pairs (one query x 64 consecutive keys): four A tiles [104 rows x 64 pairs], fp16, K-major rows of 128 B with
+//             the 128-byte swizzle (the layout TMA would write), and one B tile stored MN-MAJOR ([64 pairs][128 columns] in two
+//             64-column blocks, 128-byte swizzle): the 4 heads of one x table point are 8 contiguous bytes of a pair's row, so
+//             a producer writes them with ONE 64-bit store.  Rows >= 100 of A / columns >= 80 of B are dump slots for corners
+//             outside the table (zero padding of grid_sample), never read as results: the MMA (M = 128) reads 24 rows past
+//             each A tile, which only feeds accumulator lanes 104..127 that nobody reads.
+//   warps   : 3 stages x 6 producer warps (lane = pair; a warp owns 32 pairs and one role: the A tiles of y+, the A tiles of
+//             y-, or the B tile -- see produce<>), four MMA warps (one lane each issues the 4 K-steps of its variant per
+//             stage: tcgen05.mma M = 128, N = 80, K = 16).  A producer computes the next item while the MMAs of its stage
+//             run, then zeroes the entries it wrote last time and writes the new ones.  The producers are bound by
+//             instruction issue, so the roles are cut to minimise instructions per pair (6 + 2 axis evaluations, 16 + 4
+//             stores); the first version (4 warps per stage, 8 + 8 axes, 32 16-bit stores per pair) kept the MMA warps
+//             waiting 40 % of the time.
 //   bound   : 40 cycles per MMA (128 x 80 x 16 MACs) x 16 = 640 cycles per 64 pairs and SM.
 #include "rpe_internal.h"
 #include "rpe_fast.cuh"
@@ -32,10 +37,11 @@ using namespace tc;
 constexpr int STAGES = 3, KS = 64;
 constexpr int TP = 10;                                  // table points per axis the tiles are laid out for (n <= TP)
 constexpr int A_ROWS = 104, A_BYTES = A_ROWS * 128;     // rows 100..103: dump
-constexpr int B_ROWS = 88, B_BYTES = B_ROWS * 128;      // rows 80..87: dump
+constexpr int B_BYTES = 2 * KS * 128;                   // MN-major: two 64-column blocks of [64 pairs][128 B]; columns 80..87: dump
 constexpr int NCOL = 2 * TP * 4;                        // 80 accumulator columns: (x sign, x point, head)
 constexpr int STAGE_BYTES = 4 * A_BYTES + B_BYTES;      // 64512
-constexpr int PROD_WARPS = STAGES * 4;
+constexpr int WPS = 6;                                  // producer warps per stage
+constexpr int PROD_WARPS = STAGES * WPS;
 constexpr int MMA_WARPS = 4;                            // one per (z sign, y sign) variant: issuing an MMA costs ~100 cycles
 constexpr int THREADS = (PROD_WARPS + MMA_WARPS) * 32;
 constexpr int COPY_FLOATS = 4 * TP * TP * NCOL;         // one private copy: [variant][z * 10 + y][80]
@@ -71,12 +77,152 @@ __device__ __forceinline__ void axis_pt(float d, float ls, float c1, float c0, i
   n0 = __float_as_int(r) - rpe::MAGIC_BITS;
 }
 
-struct Raw {                    // what a producer lane loads for one pair
-  float4 kx;                    // key xyz
-  float zq, yp, ym, xq;         // the query's z^{vh}, y+, y-, x^{vh} box faces
-  int fast;                     // axis-aligned box
-  unsigned short d[4];          // scaled fp16 dS of the 4 heads
-};
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+
+// One producer warp: 32 pairs (lane = pair) of every STAGES-th item of the CTA, for one role:
+//   ROLE 0 / 1 : the y sign ys = ROLE; writes the 4 entries of A_{z+,ys} and of A_{z-,ys}   (3 axes: z+, z-, y^{ys})
+//   ROLE 2     : the B tile: for x+ and x-, the two x table points times the 4 heads of dS = four 64-bit stores (2 axes)
+// Per step: compute the entries of the next item from registers loaded two rounds ago, wait until the MMAs that read the
+// stage are done, zero the entries written last time, write the new ones, hand the stage over, reload the register set.
+template <int ROLE>
+__device__ __forceinline__ void produce(const Params& P, uint8_t* smem, uint64_t* bar_full, uint64_t* bar_empty, int stage, int khalf,
+                                        int lane, long long i_begin, int my_items, long long tk0, long long tk1) {
+  constexpr int NA = (ROLE == 2) ? 4 : 8;               // stores per step (16-bit for A, 64-bit for B)
+  const uint32_t kloc = (uint32_t)(khalf * 32 + lane);
+  const uint32_t lanec = ((kloc >> 3) << 4) | ((kloc & 7u) << 1);
+  const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
+  const uint32_t tA0 = sbase + (uint32_t)ROLE * A_BYTES, tA1 = tA0 + 2 * A_BYTES;          // (z+, ys), (z-, ys)
+  // MN-major B: this pair's 128-byte row of column block 0; the 4 heads of column group c (a multiple of 4) are 8 bytes
+  const uint32_t brow = sbase + 4 * A_BYTES + kloc * 128u, bsw = kloc & 7u;
+  auto b_off = [&](uint32_t c) { return brow + (c >> 6) * (uint32_t)(KS * 128) + ((((c & 63u) >> 3) ^ bsw) << 4) + ((c & 4u) << 1); };
+  const int n = P.n;
+
+  struct Raw {                    // what a lane loads for one pair
+    float4 kx;                    // key xyz
+    float f0, f1, f2;             // box faces: ROLE 0/1: z+, z-, y^{ys};  ROLE 2: x+, x-
+    int fast;                     // axis-aligned box
+    unsigned short d[4];          // ROLE 2: scaled fp16 dS of the 4 heads
+  };
+  // decode the first item of this stage
+  long long g0 = i_begin + stage;
+  int kt = (int)(g0 % P.KT);
+  long long r = g0 / P.KT;
+  int q = (int)(r % P.nQ), b = (int)(r / P.nQ);
+
+  auto load = [&](Raw& w, int b_, int q_, int kt_) {
+    const int k = kt_ * KS + (int)kloc;
+    const float* g = reinterpret_cast<const float*>(P.geo + ((size_t)b_ * P.nQp + q_) * 9);
+    if (ROLE < 2) { w.f0 = __ldg(g + 2); w.f1 = __ldg(g + 6); w.f2 = __ldg(g + ROLE * 4 + 1); }
+    else { w.f0 = __ldg(g); w.f1 = __ldg(g + 4); }
+    w.fast = __float_as_int(__ldg(g + 3));
+    w.kx = __ldg(P.xyz4 + (size_t)b_ * P.nKp + k);
+    if (ROLE == 2) {
+      const unsigned short* dp = reinterpret_cast<const unsigned short*>(P.dsb) + ((size_t)b_ * P.nQp + q_) * 4 * P.nKp + k;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) w.d[h] = __ldg(dp + (size_t)h * P.nKp);
+    }
+  };
+  // Two register sets in ping-pong: the set an item was computed from is reloaded (after the stage has been handed to the
+  // MMA warp) with the item two rounds ahead, so a load has a whole round to land, no register is copied while its load
+  // is in flight, and the MEMBAR inside fence.proxy.async never waits for a young load.  The addresses written by one
+  // step are the ones the next step clears: two address sets in ping-pong as well.
+  auto advance = [&]() {
+    kt += STAGES;
+    while (kt >= P.KT) { kt -= P.KT; if (++q == P.nQ) { q = 0; ++b; } }
+  };
+  Raw r0, r1;
+  int kt0 = kt, kt1 = 0;
+  if (stage < my_items) load(r0, b, q, kt);
+  advance();
+  if (stage + STAGES < my_items) { load(r1, b, q, kt); kt1 = kt; }
+  uint32_t adr0[NA], adr1[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) adr0[i] = adr1[i] = (ROLE == 2) ? b_off(80u) : tA0 + sw_off(100, lanec);
+
+  long long c_comp = 0, c_wait = 0, c_store = 0, c_load = 0;
+  auto step = [&](Raw& cur, int& ckt, int it, uint32_t (&adr)[NA], const uint32_t (&old)[NA]) {
+    const long long t0 = P.clk ? clock64() : 0;
+    const bool active = (ckt * KS + (int)kloc) < P.nK && cur.fast != 0;   // inside nK, axis-aligned box
+    const float act = active ? 1.f : 0.f;
+    uint32_t val[NA], hi2[4];                           // hi2: heads 2, 3 of the 64-bit B stores
+    if (ROLE < 2) {
+      int nz[2], ny;
+      float fz[2], fy;
+      axis_pt(cur.f0 - cur.kx.z, P.log_scale, P.c1, P.c0, n, nz[0], fz[0]);
+      axis_pt(cur.f1 - cur.kx.z, P.log_scale, P.c1, P.c0, n, nz[1], fz[1]);
+      axis_pt(cur.f2 - cur.kx.y, P.log_scale, P.c1, P.c0, n, ny, fy);
+      const bool vy0 = (unsigned)ny < (unsigned)n, vy1 = (unsigned)(ny + 1) < (unsigned)n;
+      const float wy0 = (1.f - fy) * act, wy1 = fy * act;
+#pragma unroll
+      for (int zs = 0; zs < 2; ++zs) {
+        const uint32_t tile = zs ? tA1 : tA0;
+        const bool vz0 = (unsigned)nz[zs] < (unsigned)n, vz1 = (unsigned)(nz[zs] + 1) < (unsigned)n;
+        const float wz1 = fz[zs], wz0 = 1.f - wz1;
+        const int r00 = nz[zs] * TP + ny;
+        const uint32_t p0 = pack_f16x2(wz0 * wy0, wz0 * wy1), p1 = pack_f16x2(wz1 * wy0, wz1 * wy1);
+        adr[zs * 4 + 0] = tile + sw_off((vz0 && vy0) ? (uint32_t)r00 : 100u, lanec);
+        adr[zs * 4 + 1] = tile + sw_off((vz0 && vy1) ? (uint32_t)(r00 + 1) : 101u, lanec);
+        adr[zs * 4 + 2] = tile + sw_off((vz1 && vy0) ? (uint32_t)(r00 + TP) : 102u, lanec);
+        adr[zs * 4 + 3] = tile + sw_off((vz1 && vy1) ? (uint32_t)(r00 + TP + 1) : 103u, lanec);
+        val[zs * 4 + 0] = p0; val[zs * 4 + 1] = p0 >> 16; val[zs * 4 + 2] = p1; val[zs * 4 + 3] = p1 >> 16;
+      }
+    } else {
+      // hx[x] * dS[h]: fp32 products rounded once to fp16 (dS arrives as scaled fp16)
+      const float2 d01 = __half22float2(__halves2half2(__ushort_as_half(cur.d[0]), __ushort_as_half(cur.d[1])));
+      const float2 d23 = __half22float2(__halves2half2(__ushort_as_half(cur.d[2]), __ushort_as_half(cur.d[3])));
+#pragma unroll
+      for (int xs = 0; xs < 2; ++xs) {
+        int nx;
+        float fx;
+        axis_pt((xs ? cur.f1 : cur.f0) - cur.kx.x, P.log_scale, P.c1, P.c0, n, nx, fx);
+        const float w0 = (1.f - fx) * act, w1 = fx * act;
+        const bool vx0 = (unsigned)nx < (unsigned)n, vx1 = (unsigned)(nx + 1) < (unsigned)n;
+        adr[xs * 2 + 0] = b_off(vx0 ? (uint32_t)((xs * TP + nx) * 4) : 80u);
+        adr[xs * 2 + 1] = b_off(vx1 ? (uint32_t)((xs * TP + nx + 1) * 4) : 84u);
+        val[xs * 2 + 0] = pack_f16x2(w0 * d01.x, w0 * d01.y); val[xs * 2 + 1] = pack_f16x2(w1 * d01.x, w1 * d01.y);
+        hi2[xs * 2 + 0] = pack_f16x2(w0 * d23.x, w0 * d23.y); hi2[xs * 2 + 1] = pack_f16x2(w1 * d23.x, w1 * d23.y);
+      }
+    }
+
+    const int round = it / STAGES;
+    // (the stores depend on everything computed above, so t1 is taken after the compute phase has retired)
+    const long long t1 = P.clk ? clock64() + (long long)((adr[0] & 0) + (adr[NA - 1] & 0) + (val[NA - 1] & 0)) : 0;
+    if (round > 0) mbar_wait(bar_empty + stage, (round - 1) & 1);        // the MMAs that read this stage are done
+    const long long t2 = P.clk ? clock64() : 0;
+    if (!(P.dbg & 2)) {
+      if (ROLE < 2) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) sts16(old[i], 0u);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) sts16(adr[i], val[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) sts64(old[i], 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) sts64(adr[i], val[i], hi2[i]);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_full + stage);
+    const long long t3 = P.clk ? clock64() : 0;
+    // reload this register set with the item two rounds ahead
+    advance();
+    if (it + 2 * STAGES < my_items && !(P.dbg & 4)) { load(cur, b, q, kt); ckt = kt; }
+    if (P.clk) { const long long t4 = clock64(); c_comp += t1 - t0; c_wait += t2 - t1; c_store += t3 - t2; c_load += t4 - t3; }
+  };
+  for (int it = stage; it < my_items; it += 2 * STAGES) {
+    step(r0, kt0, it, adr0, adr1);
+    if (it + STAGES < my_items) step(r1, kt1, it + STAGES, adr1, adr0);
+  }
+  if (P.clk && threadIdx.x == 0) { atomicAdd(P.clk + 6, (unsigned long long)(tk1 - tk0)); atomicAdd(P.clk + 7, (unsigned long long)(clock64() - tk1)); }
+  if (P.clk && lane == 0) {
+    atomicAdd(P.clk + 0, (unsigned long long)c_comp); atomicAdd(P.clk + 1, (unsigned long long)c_wait);
+    atomicAdd(P.clk + 2, (unsigned long long)c_store); atomicAdd(P.clk + 3, (unsigned long long)c_load);
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -95,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
   }
   if (warp == PROD_WARPS) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s, 128); mbar_init(bar_empty + s, MMA_WARPS); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s, WPS); mbar_init(bar_empty + s, MMA_WARPS); }
       mbar_init(bar_done, MMA_WARPS);
       fence_barrier_init();
     }
@@ -115,134 +261,24 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
 
   if (warp < PROD_WARPS) {
     // ------------------------------------------------------------------------------------------ producers
-    const int stage = warp >> 2, pw = warp & 3, khalf = pw & 1, vh = pw >> 1;
-    const uint32_t kloc = (uint32_t)(khalf * 32 + lane);
-    const uint32_t lanec = ((kloc >> 3) << 4) | ((kloc & 7u) << 1);
-    const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
-    const uint32_t tA0 = sbase + (uint32_t)(vh * 2) * A_BYTES, tA1 = tA0 + A_BYTES, tB = sbase + 4 * A_BYTES;
-    const int n = P.n;
-    uint32_t clr[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) clr[i] = tA0 + sw_off(100, lanec);
-
-    // decode the first item of this stage
-    long long g0 = i_begin + stage;
-    int kt = (int)(g0 % P.KT);
-    long long r = g0 / P.KT;
-    int q = (int)(r % P.nQ), b = (int)(r / P.nQ);
-
-    auto load = [&](Raw& w, int b_, int q_, int kt_) {
-      const int k = kt_ * KS + (int)kloc;
-      const float* g = reinterpret_cast<const float*>(P.geo + ((size_t)b_ * P.nQp + q_) * 9);
-      w.zq = __ldg(g + vh * 4 + 2); w.yp = __ldg(g + 1); w.ym = __ldg(g + 5); w.xq = __ldg(g + vh * 4);
-      w.fast = __float_as_int(__ldg(g + 3));
-      w.kx = __ldg(P.xyz4 + (size_t)b_ * P.nKp + k);
-      const unsigned short* dp = reinterpret_cast<const unsigned short*>(P.dsb) + ((size_t)b_ * P.nQp + q_) * 4 * P.nKp + k;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) w.d[h] = __ldg(dp + (size_t)h * P.nKp);
-    };
-    // Two register sets in ping-pong: the set an item was computed from is reloaded (after the stage has been handed to the
-    // MMA warp) with the item two rounds ahead, so a load has a whole round (~2000 cycles) to land, no register is copied
-    // while its load is in flight, and the MEMBAR inside fence.proxy.async never waits for a young load.
-    auto advance = [&]() {
-      kt += STAGES;
-      while (kt >= P.KT) { kt -= P.KT; if (++q == P.nQ) { q = 0; ++b; } }
-    };
-    Raw r0, r1;
-    int kt0 = kt, kt1 = 0;
-    if (stage < my_items) load(r0, b, q, kt);
-    advance();
-    if (stage + STAGES < my_items) { load(r1, b, q, kt); kt1 = kt; }
-
-    long long c_comp = 0, c_wait = 0, c_store = 0, c_load = 0;
-    auto step = [&](Raw& cur, int& ckt, int it) {
-      const long long t0 = P.clk ? clock64() : 0;
-      const bool active = (ckt * KS + (int)kloc) < P.nK && cur.fast != 0;   // inside nK, axis-aligned box
-      const float act = active ? 1.f : 0.f;
-      int nz, nyp, nym, nx;
-      float fz, fyp, fym, fx;
-      axis_pt(cur.zq - cur.kx.z, P.log_scale, P.c1, P.c0, n, nz, fz);
-      axis_pt(cur.yp - cur.kx.y, P.log_scale, P.c1, P.c0, n, nyp, fyp);
-      axis_pt(cur.ym - cur.kx.y, P.log_scale, P.c1, P.c0, n, nym, fym);
-      axis_pt(cur.xq - cur.kx.x, P.log_scale, P.c1, P.c0, n, nx, fx);
-
-      uint32_t adr[16], val[16];
-      const float wz0 = (1.f - fz) * act, wz1 = fz * act;
-      const bool vz0 = (unsigned)nz < (unsigned)n, vz1 = (unsigned)(nz + 1) < (unsigned)n;
-#pragma unroll
-      for (int ys = 0; ys < 2; ++ys) {
-        const int ny = ys ? nym : nyp;
-        const float fy = ys ? fym : fyp;
-        const bool vy0 = (unsigned)ny < (unsigned)n, vy1 = (unsigned)(ny + 1) < (unsigned)n;
-        const uint32_t tile = ys ? tA1 : tA0;
-        const int r00 = nz * TP + ny;
-        const uint32_t p0 = pack_f16x2(wz0 * (1.f - fy), wz0 * fy), p1 = pack_f16x2(wz1 * (1.f - fy), wz1 * fy);
-        adr[ys * 4 + 0] = tile + sw_off((vz0 && vy0) ? (uint32_t)r00 : 100u, lanec);
-        adr[ys * 4 + 1] = tile + sw_off((vz0 && vy1) ? (uint32_t)(r00 + 1) : 101u, lanec);
-        adr[ys * 4 + 2] = tile + sw_off((vz1 && vy0) ? (uint32_t)(r00 + TP) : 102u, lanec);
-        adr[ys * 4 + 3] = tile + sw_off((vz1 && vy1) ? (uint32_t)(r00 + TP + 1) : 103u, lanec);
-        val[ys * 4 + 0] = p0; val[ys * 4 + 1] = p0 >> 16; val[ys * 4 + 2] = p1; val[ys * 4 + 3] = p1 >> 16;
-      }
-      {
-        // hx[x] * dS[h]: fp32 products rounded once to fp16 (dS arrives as scaled fp16)
-        const float2 d01 = __half22float2(__halves2half2(__ushort_as_half(cur.d[0]), __ushort_as_half(cur.d[1])));
-        const float2 d23 = __half22float2(__halves2half2(__ushort_as_half(cur.d[2]), __ushort_as_half(cur.d[3])));
-        const float w0 = (1.f - fx) * act, w1 = fx * act;
-        const bool vx0 = (unsigned)nx < (unsigned)n, vx1 = (unsigned)(nx + 1) < (unsigned)n;
-        const uint32_t c0 = vx0 ? (uint32_t)((vh * TP + nx) * 4) : 80u, c1 = vx1 ? (uint32_t)((vh * TP + nx + 1) * 4) : 84u;
-        const uint32_t ua01 = pack_f16x2(w0 * d01.x, w0 * d01.y), ua23 = pack_f16x2(w0 * d23.x, w0 * d23.y);
-        const uint32_t ub01 = pack_f16x2(w1 * d01.x, w1 * d01.y), ub23 = pack_f16x2(w1 * d23.x, w1 * d23.y);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          adr[8 + h] = tB + sw_off(c0 + h, lanec);
-          adr[12 + h] = tB + sw_off(c1 + h, lanec);
-        }
-        val[8] = ua01; val[9] = ua01 >> 16; val[10] = ua23; val[11] = ua23 >> 16;
-        val[12] = ub01; val[13] = ub01 >> 16; val[14] = ub23; val[15] = ub23 >> 16;
-      }
-
-      const int round = it / STAGES;
-      // (the stores depend on everything computed above, so t1 is taken after the compute phase has retired)
-      const long long t1 = P.clk ? clock64() + (long long)(__float_as_int(fz + fx + fyp + fym) & 0) + (adr[0] & 0) + (adr[15] & 0) + (val[15] & 0) : 0;
-      if (round > 0) mbar_wait(bar_empty + stage, (round - 1) & 1);        // the MMAs that read this stage are done
-      const long long t2 = P.clk ? clock64() : 0;
-      if (!(P.dbg & 2)) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sts16(clr[i], 0u);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { sts16(adr[i], val[i]); clr[i] = adr[i]; }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(bar_full + stage);
-      const long long t3 = P.clk ? clock64() : 0;
-      // reload this register set with the item two rounds ahead
-      advance();
-      if (it + 2 * STAGES < my_items && !(P.dbg & 4)) { load(cur, b, q, kt); ckt = kt; }
-      if (P.clk) { const long long t4 = clock64(); c_comp += t1 - t0; c_wait += t2 - t1; c_store += t3 - t2; c_load += t4 - t3; }
-    };
-    for (int it = stage; it < my_items; it += 2 * STAGES) {
-      step(r0, kt0, it);
-      if (it + STAGES < my_items) step(r1, kt1, it + STAGES);
-    }
-    if (P.clk && tid == 0) { atomicAdd(P.clk + 6, (unsigned long long)(tk1 - tk0)); atomicAdd(P.clk + 7, (unsigned long long)(clock64() - tk1)); }
-    if (P.clk && lane == 0) {
-      atomicAdd(P.clk + 0, (unsigned long long)c_comp); atomicAdd(P.clk + 1, (unsigned long long)c_wait);
-      atomicAdd(P.clk + 2, (unsigned long long)c_store); atomicAdd(P.clk + 3, (unsigned long long)c_load);
-    }
+    const int stage = warp / WPS, pw = warp % WPS;
+    if (pw < 2) produce<0>(P, smem, bar_full, bar_empty, stage, pw & 1, lane, i_begin, my_items, tk0, tk1);
+    else if (pw < 4) produce<1>(P, smem, bar_full, bar_empty, stage, pw & 1, lane, i_begin, my_items, tk0, tk1);
+    else produce<2>(P, smem, bar_full, bar_empty, stage, pw & 1, lane, i_begin, my_items, tk0, tk1);
   } else {
     // ------------------------------------------------------------------------------------------ MMA issuers
     // Warp PROD_WARPS + v issues the 4 K-steps of variant v of every stage.  (One lane issuing all 16 MMAs of a stage was
     // the bottleneck of the first version: ~95 cycles of descriptor moves and issue per MMA against 40 cycles of execution.)
     if (lane == 0) {
       const int v = warp - PROD_WARPS;
-      const uint32_t idesc = umma_idesc_f16((P.dbg & 16) ? 64 : 128, (P.dbg & 8) ? 48 : ((P.dbg & 32) ? 160 : NCOL));   // (developer timing experiments)
+      const uint32_t idesc = umma_idesc_f16_major(128, NCOL, false, true);   // A K-major, B MN-major
       const uint32_t td = tmem_base + v * NCOL;
       uint64_t da[STAGES], db[STAGES];
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) {
         const uint32_t sbase = smem_u32(smem + s * STAGE_BYTES);
         da[s] = umma_desc_sw128(sbase + v * A_BYTES);
-        db[s] = umma_desc_sw128(sbase + 4 * A_BYTES);
+        db[s] = umma_desc_sw128_mn(sbase + 4 * A_BYTES, KS * 128, 1024);   // column blocks 8192 B apart, 8-pair groups 1024 B
       }
       long long m_wait = 0, m_issue = 0;
       for (int it0 = 0; it0 < my_items; it0 += STAGES) {
@@ -257,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
             if (!(P.dbg & 1)) {
 #pragma unroll
               for (int kk = 0; kk < KS / 16; ++kk)
-                umma_bf16(td, da[s] + (uint64_t)(kk * 2), db[s] + (uint64_t)(kk * 2), idesc, (it0 + s) > 0 || kk > 0);
+                umma_bf16(td, da[s] + (uint64_t)(kk * 2), db[s] + (uint64_t)(kk * 128), idesc, (it0 + s) > 0 || kk > 0);   // 16 pairs: +32 B of an A row, +16 rows of B
             }
             umma_commit(bar_empty + s);
             if (P.clk) { m_wait += t1 - t0; m_issue += clock64() - t1; }
