@@ -220,6 +220,10 @@ def main():
     ap.add_argument("--mlp-dropout", type=float, default=0.3, help="--mlp_dropout of the reference (main.py:92)")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of one step to this file and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying a captured CUDA graph")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange fused with AdamW over peer memory (csrc/peer.cu) or one NCCL all-reduce + AdamW")
+    ap.add_argument("--no-sync-bn", action="store_true",
+                    help="N > 1: keep BatchNorm statistics per GPU (default: SyncBatchNorm over peer memory, as main.py:512-514)")
     ap.add_argument("--max-seconds", type=int, default=480, help="hard watchdog: abort instead of hanging")
     ap.add_argument("--reference-budget", type=int, default=200, help="--impl reference: stop sampling after this many seconds")
     a = ap.parse_args()
@@ -236,7 +240,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     config = {"workload": f"C3/C4: {a.batch} scenes per GPU x {NK} keys x {NQ} queries x {NLAYERS} decoder layers, "
-                          f"fwd+bwd+AdamW, train mode (BN batch stats per GPU, dec_dropout {a.dropout} incl. attention dropout "
+                          f"fwd+bwd+AdamW, train mode (BatchNorm batch statistics{" synchronised over the GPUs" if (world > 1 and not a.no_sync_bn and a.exchange == "peer") else ""}, dec_dropout {a.dropout} incl. attention dropout "
                           f"inside the fused kernels, mlp_dropout {a.mlp_dropout}), TF32 Linear/Conv layers",
               "global_batch": a.batch * world, "parallelism": f"dp{world}",
               "l2": "per-step working set (> 6 GB of attention scratch, saved bias and activations) >> 126 MB L2; no explicit flush",
@@ -292,9 +296,25 @@ def main():
     use_graph = not a.no_graph and not a.profile
     # AdamW on flat buffers (parallel.FlatAdamW, csrc/optim.cu: one launch per step); its gradient views are the buffer
     # that is all-reduced: ONE NCCL all-reduce per step, the 1 / world factor folded into the optimizer's gradient scale
-    opt = parallel.FlatAdamW(dec.named_parameters(), lr=1e-5, weight_decay=0.1)
+    peer, exchange, sync_bn = None, "none (1 GPU)", False
+    if ddp and a.exchange == "peer":
+        try:
+            peer = parallel.PeerGroup(dev)
+            exchange = "fused reduce-scatter + AdamW + all-gather over peer memory (csrc/peer.cu), no NCCL call in the step"
+        except Exception as e:      # e.g. no P2P access between the GPUs of this box: the NCCL form of the same step
+            sys.stderr.write(f"bench.py: peer memory unavailable ({e!r}); using the NCCL all-reduce\n")
+            peer = None
+    if ddp and peer is None:
+        exchange = "one NCCL all-reduce of the flat gradient buffer + flat AdamW"
+    opt = parallel.FlatAdamW(dec.named_parameters(), lr=1e-5, weight_decay=0.1, peer=peer)
     opt.world_scale = 1.0 / world
     gsync = opt.grads
+    if peer is not None and not a.no_sync_bn:
+        peer.enable_sync_batchnorm()
+        sync_bn = True
+    # (how this arm ran: kept out of `config`, which both arms print identically)
+    run_info = {"exchange": exchange,
+                "batchnorm": "SyncBatchNorm statistics over peer memory" if sync_bn else "batch statistics per GPU"}
     lo, hi = parallel.shard_range(a.batch * world, rank, world)     # scenes [lo, hi) of the global batch live on this rank
     assert hi - lo == a.batch
     host = synth_scene(a.batch, NK, lo, torch)
@@ -315,8 +335,9 @@ def main():
 
     def step(inp, fetch_loss):
         loss = fwd_bwd(inp)
-        gsync.sync_(average=False)   # N > 1: the single NCCL all-reduce (SUM) of the flat gradient buffer
-        opt.step()
+        if peer is None:
+            gsync.sync_(average=False)   # N > 1: the single NCCL all-reduce (SUM) of the flat gradient buffer
+        opt.step()                       # peer form: the exchange is inside the optimizer kernels
         return loss.item() if fetch_loss else loss
 
     def e2e_step():
@@ -364,7 +385,8 @@ def main():
                 step(static_in, False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # two graphs with the (eager, one launch) NCCL all-reduce between them: forward+backward | optimizer
+        # NCCL form: two graphs with the (eager, one launch) all-reduce between them: forward+backward | optimizer.
+        # Peer form: the cross-GPU barriers and P2P kernels are ordinary graph nodes, the whole step is two replays back to back.
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_loss = fwd_bwd(static_in)
@@ -375,7 +397,8 @@ def main():
 
         def graph_step():
             graph.replay()
-            gsync.sync_(average=False)
+            if peer is None:
+                gsync.sync_(average=False)
             graph_opt.replay()
             return static_loss
 
@@ -421,8 +444,9 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     # fused forward kernel: algorithmic FLOPs = 4*H*nQ*nK*hd per layer-scene (QK^T + PV), BASELINE.md section 3
     flops_fwd = 4.0 * 4 * NQ * NK * 64 * a.batch
-    config["launch"] = ("CUDA graph replay (fwd+bwd graph, eager NCCL all-reduce, optimizer graph)" if graph is not None
-                        else "eager launches")
+    run_info["launch"] = ("CUDA graph replay (fwd+bwd graph, optimizer graph" +
+                          (", eager NCCL all-reduce between them)" if (ddp and peer is None) else ")")) if graph is not None \
+        else "eager launches"
     fwd_ms = tot[0] / max(cnt[0], 1)
     dt_ms = tot[2] / max(cnt[2], 1)
     achieved = flops_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
@@ -454,7 +478,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 tensor-core operands (QK^T from hi/lo fp16 splits of fp32 q and k; P, V, dO, dS as (scaled) fp16), "
                      "fp32 bias / softmax / accumulators; TF32 for the nn.Linear GEMMs",
-            "data": "synthetic", "config": config,
+            "data": "synthetic", "config": config, "run": run_info,
             "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": own_launches_per_step * a.steps,
             "clocks": sampler.summary(),

@@ -228,6 +228,57 @@ int vdetr_box_decode_bwd(const float* size, const float* pre_size, const float* 
 int vdetr_lsap(const float* cost, const int32_t* nactual_gt, int B, int nQ, int ngt, long long* per_prop_gt_inds,
                float* proposal_matched_mask, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Peer memory over NVLink (one process per GPU; csrc/peer.cu).  Replaces, for the data-parallel step of the reference,
+ * DistributedDataParallel's NCCL gradient all-reduce + clip_grad_norm_ + AdamW (main.py:515-517, engine.py:105-108) and
+ * nn.SyncBatchNorm's per-layer collectives (main.py:512-514).
+ * Buffers are cudaMalloc allocations shared as 64-byte CUDA IPC handles; `*_ptrs` arguments are HOST arrays of `world`
+ * device pointers, entry [rank] being this process's own allocation.  flags: VDETR_PEER_CHANNELS * VDETR_PEER_MAX_WORLD
+ * uint32 per rank (zero-initialised by vdetr_peer_alloc); epoch: this rank's private device array of VDETR_PEER_CHANNELS
+ * uint32 (zero-initialised).  Every rank must issue the same sequence of exchanging calls. */
+#define VDETR_PEER_MAX_WORLD 8
+#define VDETR_PEER_CHANNELS 4
+int vdetr_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int vdetr_peer_open(const unsigned char* handle64, void** ptr);
+int vdetr_peer_close(void* ptr);
+int vdetr_peer_free(void* ptr);
+/* 1 if a barrier ever timed out (20 s) waiting for a peer: the results of this process are then invalid */
+int vdetr_peer_error(int* out);
+int vdetr_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t* epoch, int channel, void* stream);
+/* bytes of the per-rank partial-norm exchange buffer of vdetr_adamw_flat_peer */
+size_t vdetr_peer_norm_bytes(void);
+/* Gradient exchange fused with the optimizer: rank `rank` owns elements [lo, hi) of the flat vectors (lo % 4 == 0, hi % 4 == 0
+ * or hi == n; the shards of all ranks tile [0, n)).  Sums the gradients of the shard over all ranks (P2P loads, rank order),
+ * computes the global gradient norm, scales by grad_scale_host (1 / world) and -- if max_norm > 0 -- by
+ * min(1, max_norm / (norm + 1e-6)) like clip_grad_norm_, applies AdamW (see vdetr_adamw_flat) to the shard with the LOCAL
+ * shard-sized moments m, v and scratch `reduced`, and stores the new parameters into every rank's parameter vector (P2P
+ * stores).  Three flag barriers (channels 0-2) order it against the peers; norm_out [1] (optional) gets the norm. */
+int vdetr_adamw_flat_peer(void* const* p_ptrs, void* const* g_ptrs, void* const* flag_ptrs, void* const* norm_ptrs, int rank, int world,
+                          uint32_t* epoch, float* reduced, float* m, float* v, long long n, long long n_decay, long long lo,
+                          long long hi, const float* lr, const float* step, float grad_scale_host, float max_norm, float* norm_out,
+                          float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* SyncBatchNorm: floats of the per-rank statistics exchange buffer for up to `cap` channels (all groups of a launch together) */
+size_t vdetr_peer_bn_slot_floats(int cap);
+/* Merge BatchNorm statistics over all ranks (channel 3).  fwd: sum / sumsq are this rank's shifted sums of `groups` x `cols`
+ * channels over `rows` rows (pivot = row 0 of x, group g at x + g * group_stride) and are rewritten in place so that they
+ * describe the statistics of all ranks; bwd: gsum_g / gsum_b = sums of dgamma / dbeta over all ranks.  total_rows_out [1]. */
+int vdetr_peer_bn_fwd(void* const* flag_ptrs, void* const* slot_ptrs, int rank, int world, uint32_t* epoch, int cap, float* sum,
+                      float* sumsq, const float* x, int cols, int groups, long long group_stride, int rows, float* total_rows_out,
+                      void* stream);
+int vdetr_peer_bn_bwd(void* const* flag_ptrs, void* const* slot_ptrs, int rank, int world, uint32_t* epoch, int cap,
+                      const float* dgamma, const float* dbeta, int cols_total, int rows, float* gsum_g, float* gsum_b,
+                      float* total_rows_out, void* stream);
+/* Library-wide SyncBatchNorm switch (the equivalent of nn.SyncBatchNorm.convert_sync_batchnorm, main.py:512-514): with a
+ * context of world > 1, vdetr_bn_relu_train_fwd / _bwd exchange their statistics through vdetr_peer_bn_*; NULL switches off. */
+typedef struct VdetrPeerCtx {
+  void* flags[VDETR_PEER_MAX_WORLD];
+  void* slots[VDETR_PEER_MAX_WORLD];
+  int rank, world;
+  uint32_t* epoch;
+  int cap;
+} VdetrPeerCtx;
+int vdetr_bn_sync_set(const VdetrPeerCtx* ctx);
+
 /* AdamW on flat buffers (replaces the multi-tensor torch.optim.AdamW the reference builds in optimizer.py:25 and steps in
  * engine.py:105-108): p, g, m, v are device arrays of n floats (16-byte aligned); elements [0, n_decay) are weight-decayed.
  * lr [1], step [1] (the 1-based step count as a float, already incremented) and the optional grad_scale [1] live in DEVICE

@@ -24,6 +24,14 @@ class XattnShape(ctypes.Structure):
                 ("has_bias", c_int)]
 
 
+PEER_MAX_WORLD, PEER_CHANNELS = 8, 4
+
+
+class PeerCtx(ctypes.Structure):
+    _fields_ = [("flags", c_void_p * PEER_MAX_WORLD), ("slots", c_void_p * PEER_MAX_WORLD), ("rank", c_int), ("world", c_int),
+                ("epoch", c_void_p), ("cap", c_int)]
+
+
 _SIGS = {
     "vdetr_version": (ctypes.c_char_p, []),
     "vdetr_error_string": (ctypes.c_char_p, [c_int]),
@@ -54,6 +62,21 @@ _SIGS = {
     "vdetr_reduce_workspace_floats": (c_size_t, [c_int]),
     "vdetr_colsum_workspace_floats": (c_size_t, [c_int]),
     "vdetr_adamw_flat": (c_int, [c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p, c_void_p] + [c_float] * 5 + [c_void_p]),
+    "vdetr_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    "vdetr_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "vdetr_peer_close": (c_int, [c_void_p]),
+    "vdetr_peer_free": (c_int, [c_void_p]),
+    "vdetr_peer_error": (c_int, [ctypes.POINTER(c_int)]),
+    "vdetr_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "vdetr_peer_norm_bytes": (c_size_t, []),
+    "vdetr_adamw_flat_peer": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 4 + [ctypes.c_longlong] * 4 + [c_void_p, c_void_p] +
+                              [c_float, c_float, c_void_p] + [c_float] * 4 + [c_void_p]),
+    "vdetr_peer_bn_slot_floats": (c_size_t, [c_int]),
+    "vdetr_peer_bn_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  ctypes.c_longlong, c_int, c_void_p, c_void_p]),
+    "vdetr_peer_bn_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "vdetr_bn_sync_set": (c_int, [c_void_p]),
     "vdetr_colsum": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vdetr_bn_relu_supported": (c_int, [c_int]),
     "vdetr_bn_relu_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong,

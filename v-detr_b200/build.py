@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvdetr_b200.so")
-SOURCES = ["api.cu", "pointnet2.cu", "rpe_simt.cu", "rpe_xattn_fwd.cu", "rpe_xattn_bwd.cu", "rpe_dtables.cu", "rpe_dtables_umma.cu", "layernorm.cu", "batchnorm.cu", "boxdecode.cu", "matcher.cu", "optim.cu"]
+SOURCES = ["api.cu", "pointnet2.cu", "rpe_simt.cu", "rpe_xattn_fwd.cu", "rpe_xattn_bwd.cu", "rpe_dtables.cu", "rpe_dtables_umma.cu", "layernorm.cu", "batchnorm.cu", "boxdecode.cu", "matcher.cu", "optim.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # developer knob: VDETR_EXTRA_NVCC="-DVDETR_DT_THREADS=768 -DVDETR_DT_QB=15" (tuning experiments)

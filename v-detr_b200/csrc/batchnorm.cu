@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const floa
                                                                       float* __restrict__ mean, float* __restrict__ rstd,
                                                                       float* running_mean, float* running_var, int ld4, size_t gs4,
                                                                       uint32_t drop_thresh, float inv_keep,
-                                                                      const unsigned long long* __restrict__ drop_seed) {
+                                                                      const unsigned long long* __restrict__ drop_seed,
+                                                                      const float* __restrict__ total_rows) {
   constexpr int C4 = VEC * 32, C = C4 * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint2 dkey = make_uint2(0u, 0u);
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_apply_relu_kernel(const floa
         mean[c0 + e] = m[e];
         rstd[c0 + e] = rs[e];
         if (running_mean) {
-          const float unbiased = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+          const float nt = total_rows ? __ldg(total_rows) : (float)rows;      // SyncBatchNorm: rows of all ranks
+          const float unbiased = nt > 1.f ? var * (nt / (nt - 1.f)) : var;
           running_mean[c0 + e] = (1.f - momentum) * running_mean[c0 + e] + momentum * m[e];
           running_var[c0 + e] = (1.f - momentum) * running_var[c0 + e] + momentum * unbiased;
         }
@@ -186,12 +188,12 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* 
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float4* __restrict__ gamma, const float* __restrict__ dgamma,
                                                                   const float* __restrict__ dbeta, float4* __restrict__ dx, int ld4,
-                                                                  size_t gs4, float inv_keep) {
+                                                                  size_t gs4, float inv_keep, const float* __restrict__ total_rows) {
   constexpr int C4 = VEC * 32, C = VEC * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   dy += blockIdx.y * gs4; y += blockIdx.y * gs4; x += blockIdx.y * gs4; dx += blockIdx.y * gs4; gamma += blockIdx.y * C4;
   mean += blockIdx.y * C; rstd += blockIdx.y * C; dgamma += blockIdx.y * C; dbeta += blockIdx.y * C;
-  const float inv_n = 1.0f / (float)rows;
+  const float inv_n = 1.0f / (total_rows ? __ldg(total_rows) : (float)rows);      // SyncBatchNorm: sums and rows of all ranks
   float4 mu[VEC], rs[VEC], k1[VEC], k2[VEC], k3[VEC];      // dx = k1 * g - k2 - xhat * k3
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -219,6 +221,10 @@ __global__ void __launch_bounds__(BN_WARPS * 32) bn_bwd_dx_kernel(const float4* 
   }
 }
 
+// SyncBatchNorm context (vdetr_bn_sync_set): world > 1 makes every training BatchNorm of this process exchange its statistics
+// with the other ranks -- the library-wide equivalent of nn.SyncBatchNorm.convert_sync_batchnorm(model), main.py:512-514.
+VdetrPeerCtx g_bn_sync = {};
+
 inline int bn_grid(int rows, int rows_per_warp) {
   int g = (rows + BN_WARPS * rows_per_warp - 1) / (BN_WARPS * rows_per_warp);
   return g < 1 ? 1 : (g > vdetr_num_sms() * 4 ? vdetr_num_sms() * 4 : g);
@@ -245,10 +251,18 @@ int fwd_t(const float* x, const float* gamma, const float* beta, int rows, const
   bn_stats_kernel<VEC><<<dim3(bn_red_grid(rows), L.groups), BN_WARPS * 32, 0, st>>>(reinterpret_cast<const float4*>(x), rows, ws,
                                                                                     ws + cols, part, tickets, ld4, gs4);
   VDETR_LAUNCH_CHECK();
+  float* misc = ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols + 32;       // [0]: rows of all ranks
+  const float* total_rows = nullptr;
+  if (g_bn_sync.world > 1) {      // SyncBatchNorm: merge the statistics of all ranks over peer memory (peer.cu)
+    const int rc = vdetr_peer_bn_fwd(g_bn_sync.flags, g_bn_sync.slots, g_bn_sync.rank, g_bn_sync.world, g_bn_sync.epoch, g_bn_sync.cap,
+                                     ws, ws + cols, x, VEC * 128, L.groups, (long long)L.group_stride, rows, misc, st);
+    if (rc) return rc;
+    total_rows = misc;
+  }
   bn_apply_relu_kernel<VEC><<<dim3(bn_grid(rows, 2), L.groups), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(x), rows, ws, ws + cols, reinterpret_cast<const float4*>(gamma),
       reinterpret_cast<const float4*>(beta), eps, momentum, reinterpret_cast<float4*>(y), mean, rstd, running_mean, running_var, ld4, gs4,
-      drop_p > 0.f ? philox::thresh_of(drop_p) : 0u, 1.0f / (1.0f - drop_p), drop_seed);
+      drop_p > 0.f ? philox::thresh_of(drop_p) : 0u, 1.0f / (1.0f - drop_p), drop_seed, total_rows);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
@@ -265,9 +279,17 @@ int bwd_t(const float* dy, const float* y, const float* x, const float* mean, co
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
       dgamma, dbeta, part, tickets, ld4, gs4, inv_keep);
   VDETR_LAUNCH_CHECK();
+  float* misc = ws + (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols + 32;       // [0]: rows of all ranks, [32 ...): sums of all ranks
+  const float *sum_g = dgamma, *sum_b = dbeta, *total_rows = nullptr;
+  if (g_bn_sync.world > 1) {      // SyncBatchNorm: dx needs the two sums over ALL ranks; dgamma / dbeta stay this rank's
+    const int rc = vdetr_peer_bn_bwd(g_bn_sync.flags, g_bn_sync.slots, g_bn_sync.rank, g_bn_sync.world, g_bn_sync.epoch, g_bn_sync.cap,
+                                     dgamma, dbeta, cols, rows, misc + 32, misc + 32 + cols, misc, st);
+    if (rc) return rc;
+    sum_g = misc + 32; sum_b = misc + 32 + cols; total_rows = misc;
+  }
   bn_bwd_dx_kernel<VEC><<<dim3(bn_grid(rows, 2), L.groups), BN_WARPS * 32, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x), rows, mean, rstd,
-      reinterpret_cast<const float4*>(gamma), dgamma, dbeta, reinterpret_cast<float4*>(dx), ld4, gs4, inv_keep);
+      reinterpret_cast<const float4*>(gamma), sum_g, sum_b, reinterpret_cast<float4*>(dx), ld4, gs4, inv_keep, total_rows);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
@@ -280,6 +302,14 @@ bool layout_ok(int cols, int groups, long long group_stride, long long row_strid
 }  // namespace
 
 extern "C" {
+
+int vdetr_bn_sync_set(const VdetrPeerCtx* ctx) {
+  if (!ctx) { g_bn_sync = VdetrPeerCtx{}; return 0; }
+  if (ctx->world < 1 || ctx->world > VDETR_PEER_MAX_WORLD || ctx->rank < 0 || ctx->rank >= ctx->world || !ctx->epoch || ctx->cap < 1)
+    return VDETR_ERR_BAD_ARG;
+  g_bn_sync = *ctx;
+  return 0;
+}
 
 int vdetr_bn_relu_supported(int cols) { return cols == 128 || cols == 256 || cols == 384 || cols == 512; }
 

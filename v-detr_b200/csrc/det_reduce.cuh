@@ -10,8 +10,9 @@
 
 constexpr int VDETR_RED_MAX_BLOCKS = 128;      // partial sums per reduction (grids of the reducing kernels are capped to this)
 
-// workspace of one reduction over `cols` columns of two quantities: [2 * cols] results, [128][2 * cols] partials, ticket
-static inline size_t vdetr_reduce_ws_floats(int cols) { return (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols + 32; }
+// workspace of one reduction over `cols` columns of two quantities: [2 * cols] results, [128][2 * cols] partials, 32 tickets,
+// then (SyncBatchNorm only) [32] scalars and [2 * cols] sums over all ranks
+static inline size_t vdetr_reduce_ws_floats(int cols) { return (size_t)(VDETR_RED_MAX_BLOCKS + 1) * 2 * cols + 32 + 32 + 2 * (size_t)cols; }
 
 // Called by ALL threads of every CTA after the CTA has written part[blockIdx.x * ncols + c] for all c.
 // ncols columns; results go to out_a[c] (c < split) or out_b[c - split].  *ticket must be 0 before the launch.

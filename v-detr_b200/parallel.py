@@ -45,11 +45,12 @@ class FlatGradAllReduce:
     ~100 ms step, so overlapping it with backward (what DistributedDataParallel's buckets do) buys nothing here.
     """
 
-    def __init__(self, params):
+    def __init__(self, params, flat=None):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device) if flat is None else flat   # (peer memory: PeerGroup.alloc)
+        assert self.flat.numel() == n and self.flat.dtype == ref.dtype
         self.views, o = [], 0
         for p in self.params:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
@@ -96,6 +97,111 @@ class FlatGradAllReduce:
         return self.flat
 
 
+class _RawCuda:
+    """A cudaMalloc allocation owned by libvdetr_b200 (peer memory) exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerBuffer:
+    """One allocation per rank, every rank's mapped into this process: `local` is this rank's memory as a uint8 tensor,
+    `ptrs` a ctypes array of `world` device pointers (entry [rank] = local) in the form the C ABI takes."""
+
+    def __init__(self, local, ptrs, raw):
+        self.local, self.ptrs, self._raw = local, ptrs, raw
+
+    def view(self, dtype, numel=None):
+        t = self.local.view(dtype)
+        return t if numel is None else t[:numel]
+
+
+class PeerGroup:
+    """Peer memory over NVLink for the ranks of one node (csrc/peer.cu): cudaMalloc allocations exchanged as CUDA IPC handles
+    through torch.distributed, a flag array for cross-GPU barriers and this rank's epoch counters.  world == 1 works without
+    torch.distributed (the exchanges degenerate to local copies), which is how the single-GPU tests cover the kernels."""
+
+    def __init__(self, device):
+        from . import _C
+        self.device = torch.device(device)
+        self.dist = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.rank = dist.get_rank() if self.dist else 0
+        self.world = dist.get_world_size() if self.dist else 1
+        if self.world > _C.PEER_MAX_WORLD:
+            raise RuntimeError(f"PeerGroup: at most {_C.PEER_MAX_WORLD} ranks (one NVSwitch node)")
+        self._bufs = []
+        self.flags = self.alloc(_C.PEER_CHANNELS * _C.PEER_MAX_WORLD * 4)
+        self.epoch = torch.zeros(_C.PEER_CHANNELS, dtype=torch.int32, device=self.device)
+        self._bn_ctx = None
+
+    def alloc(self, nbytes: int) -> PeerBuffer:
+        import ctypes
+        from . import _C
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _C.check(_C.lib().vdetr_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+            handles = [None] * self.world
+            if self.dist:
+                dist.all_gather_object(handles, bytes(handle.raw))
+            ptrs = (ctypes.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs[r] = ptr.value
+                else:
+                    q = ctypes.c_void_p()
+                    _C.check(_C.lib().vdetr_peer_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q)))
+                    ptrs[r] = q.value
+            local = torch.as_tensor(_RawCuda(ptr.value, nbytes), device=self.device)
+        buf = PeerBuffer(local, ptrs, ptr.value)
+        self._bufs.append(buf)
+        if self.dist:
+            dist.barrier()           # every rank has mapped every allocation before anyone uses it
+        return buf
+
+    def barrier(self, channel: int = 0):
+        """Cross-GPU barrier on the current stream (a one-warp kernel; capturable in a CUDA graph)."""
+        from . import _C
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().vdetr_peer_barrier(self.flags.ptrs, self.rank, self.world, _C.ptr(self.epoch), channel, _C.stream_ptr()))
+
+    def check(self):
+        """Raises if a barrier of this process ever timed out waiting for a peer."""
+        import ctypes
+        from . import _C
+        e = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().vdetr_peer_error(ctypes.byref(e)))
+        if e.value:
+            raise RuntimeError("PeerGroup: a cross-GPU barrier timed out (a peer rank died or fell out of step)")
+
+    def enable_sync_batchnorm(self, max_channels: int = 4096):
+        """The reference converts every BatchNorm to SyncBatchNorm (main.py:512-514).  Here: from now on every training-mode
+        BatchNorm+ReLU launch of this process (ops.bn_relu_train*) merges its statistics with the other ranks through peer
+        memory -- one small kernel per exchange (csrc/peer.cu), no NCCL call.  Every rank must run the same layers."""
+        from . import _C
+        slots = self.alloc(_C.lib().vdetr_peer_bn_slot_floats(max_channels) * 4)
+        ctx = _C.PeerCtx()
+        for r in range(self.world):
+            ctx.flags[r] = self.flags.ptrs[r]
+            ctx.slots[r] = slots.ptrs[r]
+        ctx.rank, ctx.world, ctx.epoch, ctx.cap = self.rank, self.world, _C.ptr(self.epoch), max_channels
+        import ctypes
+        _C.check(_C.lib().vdetr_bn_sync_set(ctypes.byref(ctx)))
+        self._bn_ctx = ctx
+
+    def disable_sync_batchnorm(self):
+        from . import _C
+        _C.check(_C.lib().vdetr_bn_sync_set(None))
+        self._bn_ctx = None
+
+
+def _peer_norm_bytes():
+    from . import _C
+    return int(_C.lib().vdetr_peer_norm_bytes())
+
+
 class FlatAdamW:
     """torch.optim.AdamW semantics (the reference: optimizer.py:4-26, stepped after clip_grad_norm_ in engine.py:105-108) on
     FLAT buffers: parameters are re-homed as views of one fp32 buffer, gradients are the views of FlatGradAllReduce, the two
@@ -103,9 +209,14 @@ class FlatAdamW:
     tensors.  lr, the step count and the gradient scale live on the device, so the step can sit inside a captured CUDA graph
     and still follow a learning-rate schedule (set_lr) or a clipped gradient norm.
 
-    no_decay(name, param) -> True puts a parameter into the group without weight decay (--filter_biases_wd)."""
+    no_decay(name, param) -> True puts a parameter into the group without weight decay (--filter_biases_wd).
 
-    def __init__(self, named_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, no_decay=None):
+    peer = PeerGroup: the data-parallel form.  Parameters and gradients live in peer memory, every rank owns a contiguous
+    shard of the flat vector, and step() is the fused exchange of csrc/peer.cu: reduce-scatter of the gradients by P2P loads,
+    global gradient norm (max_norm > 0 clips like engine.py:105-106), AdamW on the shard with shard-sized moments, all-gather
+    of the parameters by P2P stores -- no NCCL call, no separate all-reduce (FlatGradAllReduce.sync_ is not used)."""
+
+    def __init__(self, named_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, no_decay=None, peer=None):
         named = [(n, p) for n, p in named_params if p.requires_grad]
         if not named:
             raise ValueError("FlatAdamW: no trainable parameters")
@@ -118,7 +229,13 @@ class FlatAdamW:
             raise RuntimeError("FlatAdamW needs fp32 CUDA parameters on one device (there is no CPU path)")
         self.n = sum(p.numel() for p in self.params)
         self.n_decay = sum(p.numel() for _, p in dec)
-        self.flat_p = torch.empty(self.n, dtype=torch.float32, device=ref.device)
+        self.peer = peer
+        if peer is None:
+            self.flat_p = torch.empty(self.n, dtype=torch.float32, device=ref.device)
+        else:
+            self._p_buf = peer.alloc(self.n * 4)
+            self._g_buf = peer.alloc(self.n * 4)
+            self.flat_p = self._p_buf.view(torch.float32, self.n)
         o = 0
         with torch.no_grad():
             for p in self.params:                      # parameters become views of the flat buffer (same values)
@@ -126,9 +243,23 @@ class FlatAdamW:
                 v.copy_(p)
                 p.data = v
                 o += p.numel()
-        self.grads = FlatGradAllReduce(self.params)    # same order: flat_g[i] is the gradient of flat_p[i]
-        self.exp_avg = torch.zeros_like(self.flat_p)
-        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.max_norm = 0.0                            # peer form: > 0 clips the global gradient norm inside step()
+        if peer is None:
+            self.grads = FlatGradAllReduce(self.params)    # same order: flat_g[i] is the gradient of flat_p[i]
+            self.lo, self.hi = 0, self.n
+        else:
+            if peer.dist:
+                dist.broadcast(self.flat_p, 0)         # every rank starts from rank 0's parameters (what DDP does)
+            self.grads = FlatGradAllReduce(self.params, flat=self._g_buf.view(torch.float32, self.n))
+            n4 = self.n // 4
+            self.lo = (n4 * peer.rank // peer.world) * 4
+            self.hi = self.n if peer.rank == peer.world - 1 else (n4 * (peer.rank + 1) // peer.world) * 4
+            self._norm_buf = peer.alloc(_peer_norm_bytes())
+            self._reduced = torch.zeros(max(self.hi - self.lo, 4), dtype=torch.float32, device=ref.device)
+            self.last_norm = torch.zeros(1, dtype=torch.float32, device=ref.device)
+        # moments: the whole vector, or (peer form) this rank's shard only
+        self.exp_avg = torch.zeros(max(self.hi - self.lo, 4), dtype=torch.float32, device=ref.device)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
         self.lr = torch.tensor([lr], dtype=torch.float32, device=ref.device)
         self.step_t = torch.zeros(1, dtype=torch.float32, device=ref.device)
         self.grad_scale = torch.ones(1, dtype=torch.float32, device=ref.device)
@@ -139,7 +270,12 @@ class FlatAdamW:
         self.lr.fill_(lr)
 
     def clip_grad_norm_(self, max_norm: float):
-        """torch.nn.utils.clip_grad_norm_ (engine.py:105-106) as a device-side scale of the flat gradient; returns the norm."""
+        """torch.nn.utils.clip_grad_norm_ (engine.py:105-106) as a device-side scale of the flat gradient; returns the norm.
+        Peer form: the norm of the summed gradient only exists inside step(); this sets max_norm for it and returns the
+        device tensor step() writes the norm to."""
+        if self.peer is not None:
+            self.max_norm = float(max_norm)
+            return self.last_norm
         norm = torch.linalg.vector_norm(self.grads.gather_()) * self.world_scale
         torch.clamp(max_norm / (norm + 1e-6), max=1.0, out=self.grad_scale[0])
         return norm
@@ -149,6 +285,16 @@ class FlatAdamW:
         from . import _C
         self.grads.gather_()
         self.step_t += 1.0
+        if self.peer is not None:
+            pg = self.peer
+            with torch.cuda.device(self.flat_p.device):
+                _C.check(_C.lib().vdetr_adamw_flat_peer(self._p_buf.ptrs, self._g_buf.ptrs, pg.flags.ptrs, self._norm_buf.ptrs, pg.rank,
+                                                        pg.world, _C.ptr(pg.epoch), _C.ptr(self._reduced), _C.ptr(self.exp_avg),
+                                                        _C.ptr(self.exp_avg_sq), self.n, self.n_decay, self.lo, self.hi, _C.ptr(self.lr),
+                                                        _C.ptr(self.step_t), float(self.world_scale), float(self.max_norm),
+                                                        _C.ptr(self.last_norm), float(self.betas[0]), float(self.betas[1]),
+                                                        float(self.eps), float(self.weight_decay), _C.stream_ptr()))
+            return
         with torch.cuda.device(self.flat_p.device):
             _C.check(_C.lib().vdetr_adamw_flat(_C.ptr(self.flat_p), _C.ptr(self.grads.flat), _C.ptr(self.exp_avg),
                                                _C.ptr(self.exp_avg_sq), self.n, self.n_decay, _C.ptr(self.lr), _C.ptr(self.step_t),
@@ -158,12 +304,25 @@ class FlatAdamW:
     def zero_grad(self, set_to_none: bool = True):
         self.grads.zero_()
 
+    def _full_moment(self, shard):
+        """Peer form: assemble a whole-vector moment from the shards of all ranks (checkpointing only)."""
+        n = self.hi - self.lo
+        if self.peer is None or not self.peer.dist:
+            return shard[:n].clone()
+        parts = [None] * self.peer.world
+        dist.all_gather_object(parts, (self.lo, shard[:n].cpu()))
+        full = torch.empty(self.n, dtype=torch.float32)
+        for lo, t in parts:
+            full[lo:lo + t.numel()] = t
+        return full.to(shard.device)
+
     def state_dict(self):
-        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_t.clone(),
-                "lr": self.lr.clone(), "names": list(self.names)}
+        return {"exp_avg": self._full_moment(self.exp_avg), "exp_avg_sq": self._full_moment(self.exp_avg_sq),
+                "step": self.step_t.clone(), "lr": self.lr.clone(), "names": list(self.names)}
 
     def load_state_dict(self, sd):
         if list(sd["names"]) != self.names:
             raise ValueError("FlatAdamW.load_state_dict: parameter order differs")
-        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        n = self.hi - self.lo
+        self.exp_avg[:n].copy_(sd["exp_avg"][self.lo:self.hi]); self.exp_avg_sq[:n].copy_(sd["exp_avg_sq"][self.lo:self.hi])
         self.step_t.copy_(sd["step"]); self.lr.copy_(sd["lr"])
