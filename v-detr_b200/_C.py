@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvdetr_b200.so")
+LIB_PATH = os.environ.get("VDETR_B200_LIB") or os.path.join(_HERE, "lib", "libvdetr_b200.so")   # (override: developer experiments)
 _lib = None
 
 c_int, c_size_t, c_void_p, c_float = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_float

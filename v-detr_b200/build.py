@@ -11,7 +11,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# developer knob: VDETR_LIB_SUFFIX=_x builds lib_x/libvdetr_b200.so (an experimental variant next to the product library;
+# load it with VDETR_B200_LIB=<path>, see _C.py)
+LIBDIR = os.path.join(HERE, "lib" + os.environ.get("VDETR_LIB_SUFFIX", ""))
 LIB = os.path.join(LIBDIR, "libvdetr_b200.so")
 SOURCES = ["api.cu", "pointnet2.cu", "rpe_simt.cu", "rpe_xattn_fwd.cu", "rpe_xattn_bwd.cu", "rpe_dtables.cu", "rpe_dtables_umma.cu", "layernorm.cu", "batchnorm.cu", "boxdecode.cu", "matcher.cu", "optim.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -27,6 +27,9 @@ constexpr int NCOMPUTE = NCOMPUTE_WARPS * 32;
 constexpr int NTHREADS = NCOMPUTE + 32;
 constexpr int BM = 128, BN = 64, HD = 64, QT = 32, BIAS_STRIDE_F4 = BN + 1;
 constexpr float LOG2E = 1.4426950408889634f;
+#ifndef VDETR_BWD_EVENT_LOOP
+#define VDETR_BWD_EVENT_LOOP 0      // measured: the polling loop costs more than the reordering buys (0.41 vs 0.36 ms)
+#endif
 constexpr int TMEM_COLS = 512;                     // S0 [0,64) S1 [64,128) dP0 [128,192) dP1 [192,256) dQ [256,320)
 
 struct BwdParams {
@@ -50,13 +53,14 @@ struct SmemLayout {
   uint32_t q, ql, dO, stage, ds, bias, rowbuf, bars, total;
 };
 constexpr uint32_t STAGE_BYTES = 3 * BN * 128;     // K hi, K lo, V
+constexpr int NSTAGE = 3;                          // K / V ring: a tile's K / V is requested two tiles ahead
 __host__ __device__ inline SmemLayout smem_layout(bool has_bias) {
   SmemLayout L;
   uint32_t o = 0;
   L.q = o;      o += BM * 128;
   L.ql = o;     o += BM * 128;
   L.dO = o;     o += BM * 128;
-  L.stage = o;  o += 2 * STAGE_BYTES;
+  L.stage = o;  o += NSTAGE * STAGE_BYTES;
   L.ds = o;     o += 2 * BM * 128;
   L.bias = o;   o += has_bias ? 2 * QT * BIAS_STRIDE_F4 * 16 : 0;
   L.rowbuf = o; o += BM * 4 * 4;
@@ -82,12 +86,16 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* sRow = reinterpret_cast<float*>(smem + L.rowbuf);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_full = bars + 1;    // [2] K / V (/ bias) of a tile have landed in stage s
+  uint64_t* bar_full = bars + 17;   // [NSTAGE] K / V of a tile have landed in stage gj % NSTAGE
   uint64_t* bar_s = bars + 3;       // [2] S and dP of a tile are in TMEM buffer s
   uint64_t* bar_tfree = bars + 5;   // [2] every compute thread has read TMEM buffer s
-  uint64_t* bar_ds = bars + 7;      // [2] the dS tile is in sdS[s] (and the bias tile of stage s has been read)
-  uint64_t* bar_dq = bars + 9;      // [2] the dQ MMAs of a tile are done: sdS[s] and stage s are free
+  uint64_t* bar_ds = bars + 7;      // [2] the dS tile is in sdS[s]
+  uint64_t* bar_dq = bars + 9;      // [2] the dQ MMAs of a tile are done: sdS[s] and the tile's K / V stage are free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_bfull = bars + 13;  // [2] the bias tile of a key tile has landed in bias buffer s
+  uint64_t* bar_bfree = bars + 15;  // [2] every compute thread has copied its bias values out of buffer s
+  uint64_t* bar_kfree = bars + 20;  // [NSTAGE] the dQ MMAs that read K / V stage gj % NSTAGE are done (same event as bar_dq, but a
+                                    // ring of NSTAGE: a parity wait may only ask for the LATEST completed phase of a barrier)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_control = warp == NCOMPUTE_WARPS;
@@ -95,9 +103,11 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (is_control) {
     if (lane == 0) {
       mbar_init(bar_q, 1);
+      for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_kfree + s, 1); }
       for (int s = 0; s < 2; ++s) {
-        mbar_init(bar_full + s, 1); mbar_init(bar_s + s, 1); mbar_init(bar_tfree + s, NCOMPUTE);
+        mbar_init(bar_s + s, 1); mbar_init(bar_tfree + s, NCOMPUTE);
         mbar_init(bar_ds + s, NCOMPUTE); mbar_init(bar_dq + s, 1);
+        mbar_init(bar_bfull + s, 1); mbar_init(bar_bfree + s, NCOMPUTE);
       }
       fence_barrier_init();
       prefetch_tmap(&tmQ); prefetch_tmap(&tmQl); prefetch_tmap(&tmdO); prefetch_tmap(&tmK); prefetch_tmap(&tmKl); prefetch_tmap(&tmV);
@@ -141,49 +151,54 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_2d(sQ, &tmQ, 0, qrow0, bar_q);
         tma_load_2d(sQl, &tmQl, 0, qrow0, bar_q);
         tma_load_2d(sdO, &tmdO, 0, qrow0, bar_q);
-        const uint32_t kbytes = STAGE_BYTES + (HAS_BIAS ? QT * BN * 16 : 0);
-        auto load_tile = [&](int j) {
+        auto load_kv = [&](int j) {
           const uint32_t gj = g + j;
-          const int s = gj & 1;
-          // stage s, sdS[s] and bias[s] were last used by tile gj - 2: its dQ MMAs (issued after every compute thread
-          // had arrived on bar_ds) must have completed
-          if (gj >= 2) mbar_wait(bar_dq + s, ((gj - 2) >> 1) & 1);
+          const int s = gj % NSTAGE;
+          // stage s was last used by tile gj - NSTAGE: its dQ MMAs (which read K hi) must have completed
+          if (gj >= NSTAGE) mbar_wait(bar_kfree + s, (gj / NSTAGE - 1) & 1);
           uint8_t* st = sStage + s * STAGE_BYTES;
           uint64_t* bk = bar_full + s;
-          mbar_arrive_expect_tx(bk, kbytes);
+          mbar_arrive_expect_tx(bk, STAGE_BYTES);
           const int kr = krow0 + (tile_begin + j) * BN;
           tma_load_2d(st, &tmK, 0, kr, bk);
           tma_load_2d(st + BN * 128, &tmKl, 0, kr, bk);
           tma_load_2d(st + 2 * BN * 128, &tmV, 0, kr, bk);
-          if (HAS_BIAS) {
-            const float4* src = P.bias_in + ((size_t)b * P.nQp + q0) * P.nKp + (tile_begin + j) * BN;
-            float4* dstb = sBias + s * (QT * BIAS_STRIDE_F4);
-            for (int qq = 0; qq < QT; ++qq) bulk_load_1d(dstb + qq * BIAS_STRIDE_F4, src + (size_t)qq * P.nKp, BN * 16, bk);
-          }
+        };
+        // The bias tile (32 KB, more than half of a tile's bytes) has its own ring: the compute threads copy their 16 values
+        // into registers as soon as the tile has landed and release the buffer at the START of the tile's compute phase, so
+        // the bias of tile j + 2 is requested a whole tile earlier than the K / V stage allows -- two bias tiles in flight.
+        auto load_bias = [&](int j) {
+          if (!HAS_BIAS) return;
+          const uint32_t gj = g + j;
+          const int s = gj & 1;
+          if (gj >= 2) mbar_wait(bar_bfree + s, ((gj - 2) >> 1) & 1);
+          uint64_t* bk = bar_bfull + s;
+          mbar_arrive_expect_tx(bk, QT * BN * 16);
+          const float4* src = P.bias_in + ((size_t)b * P.nQp + q0) * P.nKp + (tile_begin + j) * BN;
+          float4* dstb = sBias + s * (QT * BIAS_STRIDE_F4);
+          for (int qq = 0; qq < QT; ++qq) bulk_load_1d(dstb + qq * BIAS_STRIDE_F4, src + (size_t)qq * P.nKp, BN * 16, bk);
         };
         auto issue_dq = [&](int j) {
           const uint32_t gj = g + j;
           const int s = gj & 1;
           mbar_wait_relaxed(bar_ds + s, (gj >> 1) & 1);      // a tile of compute work away
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sdS + s * (BM * 128)), b0 = smem_u32(sStage + s * STAGE_BYTES);
+          const uint32_t a0 = smem_u32(sdS + s * (BM * 128)), b0 = smem_u32(sStage + (gj % NSTAGE) * STAGE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk)
             umma_bf16(tdQ, umma_desc_sw128(a0) + (uint64_t)(kk * 2), umma_desc_sw128_mn(b0 + kk * 2048, 8192, 1024), idesc_q,
                       (j > 0) || (kk > 0));
           umma_commit(bar_dq + s);
+          umma_commit(bar_kfree + gj % NSTAGE);
         };
-        load_tile(0);
-        if (T > 1) load_tile(1);
-        mbar_wait(bar_q, it & 1);
-        for (int j = 0; j < T; ++j) {
+        auto issue_s = [&](int j) {
           const uint32_t gj = g + j;
           const int s = gj & 1;
-          mbar_wait(bar_full + s, (gj >> 1) & 1);
+          mbar_wait(bar_full + gj % NSTAGE, (gj / NSTAGE) & 1);
           if (gj >= 2) mbar_wait(bar_tfree + s, ((gj - 2) >> 1) & 1);      // TMEM buffer s has been read
           tc_fence_after();
           {
-            const uint8_t* st = sStage + s * STAGE_BYTES;
+            const uint8_t* st = sStage + (gj % NSTAGE) * STAGE_BYTES;
             const uint64_t dqh = umma_desc_sw128(smem_u32(sQ)), dql = umma_desc_sw128(smem_u32(sQl));
             const uint64_t dkh = umma_desc_sw128(smem_u32(st)), dkl = umma_desc_sw128(smem_u32(st + BN * 128));
             const uint64_t ddo = umma_desc_sw128(smem_u32(sdO)), dv = umma_desc_sw128(smem_u32(st + 2 * BN * 128));
@@ -197,12 +212,44 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int kk = 0; kk < HD / 16; ++kk) umma_bf16(tdP0 + s * BN, ddo + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_s, kk > 0);
             umma_commit(bar_s + s);
           }
+        };
+#if VDETR_BWD_EVENT_LOOP
+        // The control lane serves four queues (bias loads, K / V loads, S / dP MMAs, dQ MMAs); each entry has its own
+        // readiness condition on an mbarrier.  Polling them round-robin issues whatever is ready first: a late K / V tile no
+        // longer delays the dQ MMAs of the tile before it (which the compute warps of the NEXT tile wait for), and loads go
+        // out the moment their buffer is released.
+        {
+          auto ready = [&](uint64_t* bar, uint32_t gj_done) { return mbar_try_wait(bar + (gj_done & 1), (gj_done >> 1) & 1); };
+          int nb = 0, nk = 0, ns = 0, nd = 0;
+          load_kv(0); load_bias(0); nb = nk = 1;
+          mbar_wait(bar_q, it & 1);
+          while (nd < T) {
+            bool progress = false;
+            if (HAS_BIAS && nb < T && (g + nb < 2 || ready(bar_bfree, g + nb - 2))) { load_bias(nb++); progress = true; }
+            if (nk < T && (g + nk < NSTAGE || mbar_try_wait(bar_kfree + (g + nk) % NSTAGE, ((g + nk) / NSTAGE - 1) & 1))) { load_kv(nk++); progress = true; }
+            if (ns < nk && (!HAS_BIAS || ns < nb) && mbar_try_wait(bar_full + (g + ns) % NSTAGE, ((g + ns) / NSTAGE) & 1) &&
+                (g + ns < 2 || ready(bar_tfree, g + ns - 2))) {
+              issue_s(ns++); progress = true;
+            }
+            if (nd < ns && ready(bar_ds, g + nd)) { issue_dq(nd++); progress = true; }
+            if (!progress) __nanosleep(64);
+          }
+        }
+#else
+        load_kv(0); load_bias(0);
+        if (T > 1) { load_kv(1); load_bias(1); }
+        if (T > 2) load_kv(2);
+        mbar_wait(bar_q, it & 1);
+        for (int j = 0; j < T; ++j) {
+          if (j > 0 && j + 1 < T) load_bias(j + 1);           // buffer of tile j - 1: released when its compute phase began
+          issue_s(j);
           if (j > 0) {
             issue_dq(j - 1);
-            if (j + 1 < T) load_tile(j + 1);                // into the stage tile j - 1 just released
+            if (j + 2 < T) load_kv(j + 2);                  // into the stage tile j - 1 just released
           }
         }
         issue_dq(T - 1);
+#endif
         // sQ / sQl / sdO / the stages may only be overwritten (next item) after the last MMAs have finished
         mbar_wait(bar_dq + ((g + T - 1) & 1), ((g + T - 1) >> 1) & 1);
       }
@@ -231,11 +278,34 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float lse2 = (q < P.nQ) ? __ldg(P.lse + ((size_t)b * 4 + h) * P.nQ + q) * LOG2E : INFINITY;
       const size_t grow = (size_t)(qrow0 + row) * P.nKp;
 
+      uint32_t pk[8], dk_[8];                                               // Pd / g dS of the previous tile, stored one tile late
+      int key0_prev = -1;
+      auto store_prev = [&]() {
+        if (key0_prev < 0) return;
+        uint4* dstp = reinterpret_cast<uint4*>(P.pb + grow + key0_prev + slice * 16);
+        uint4* dstd = reinterpret_cast<uint4*>(P.dsb + grow + key0_prev + slice * 16);
+        dstp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dstp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
+      };
       for (int j = 0; j < T; ++j) {
         const uint32_t gj = g + j;
         const int s = gj & 1;
         const int key0 = (tile_begin + j) * BN;
-        if (HAS_BIAS) mbar_wait(bar_full + s, (gj >> 1) & 1);               // the bias tile has landed
+        float bz[16];
+        if (HAS_BIAS) {
+          mbar_wait(bar_bfull + s, (gj >> 1) & 1);                          // the bias tile has landed
+          const float* brow =
+              reinterpret_cast<const float*>(sBias + s * (QT * BIAS_STRIDE_F4) + (row >> 2) * BIAS_STRIDE_F4 + slice * 16) + (row & 3);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) bz[c] = brow[c * 4];
+          // generic-proxy reads of the buffer are ordered before the bulk copies (async proxy) that refill it
+          fence_proxy_async_smem();
+          mbar_arrive(bar_bfree + s);
+        }
+        // Pd and g dS of the previous tile go to global memory here: a proxy fence waits for the thread's outstanding stores,
+        // so stores issued right before one sat on the tile's critical path (12 % of the stall samples); issued here they
+        // drain during this tile's compute phase.
+        store_prev();
         mbar_wait(bar_s + s, (gj >> 1) & 1);
         tc_fence_after();
         uint32_t sr[16], dr[16];
@@ -244,9 +314,6 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_tfree + s);                                         // TMEM buffer s may be overwritten
-        const float* brow = nullptr;
-        if (HAS_BIAS)
-          brow = reinterpret_cast<const float*>(sBias + s * (QT * BIAS_STRIDE_F4) + (row >> 2) * BIAS_STRIDE_F4 + slice * 16) + (row & 3);
         const bool tail_tile = key0 + BN > P.nK;
         uint32_t keep = 0xFFFFu;
         float dscale = 1.f;
@@ -254,14 +321,13 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           keep = philox::keep_mask16(drop, (uint32_t)(qrow0 + row), (uint32_t)((key0 >> 4) + slice));
           dscale = drop.inv_keep;
         }
-        uint32_t pk[8], dk_[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
           float pv[2], dv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             float sv = __uint_as_float(sr[c + e]);
-            if (HAS_BIAS) sv += brow[(c + e) * 4];
+            if (HAS_BIAS) sv += bz[c + e];
             float p = ex2_approx(sv * LOG2E - lse2);
             if (tail_tile && key0 + slice * 16 + c + e >= P.nK) p = 0.f;       // only the last key tile is ragged
             const float m = ((keep >> (c + e)) & 1u) ? dscale : 0.f;
@@ -271,12 +337,6 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[c >> 1] = pack_f16x2(pv[0], pv[1]);
           dk_[c >> 1] = pack_f16x2(dv[0], dv[1]);
         }
-        {
-          uint4* dstp = reinterpret_cast<uint4*>(P.pb + grow + key0 + slice * 16);
-          uint4* dstd = reinterpret_cast<uint4*>(P.dsb + grow + key0 + slice * 16);
-          dstp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dstp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          dstd[0] = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]); dstd[1] = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
-        }
         // dS tile -> sdS[s] as the A operand of dQ += dS K (K-major rows of 128 B, 128-byte swizzle: chunk ^= row % 8)
         if (gj >= 2) mbar_wait(bar_dq + s, ((gj - 2) >> 1) & 1);             // the dQ MMAs of tile gj - 2 have read sdS[s]
         {
@@ -285,11 +345,12 @@ rpe_xattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           *reinterpret_cast<uint4*>(prow + ((ch0 ^ (row & 7)) << 4)) = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]);
           *reinterpret_cast<uint4*>(prow + ((ch1 ^ (row & 7)) << 4)) = make_uint4(dk_[4], dk_[5], dk_[6], dk_[7]);
         }
-        // generic-proxy accesses of this tile (sdS writes, bias reads) are ordered before the async-proxy accesses that
-        // follow the arrive (the dQ MMAs reading sdS, the bulk copies rewriting the bias buffer two tiles later)
+        // generic-proxy writes of sdS are ordered before the async-proxy reads that follow the arrive (the dQ MMAs)
         fence_proxy_async_smem();
         mbar_arrive(bar_ds + s);
+        key0_prev = key0;
       }
+      store_prev();
       // ------------------------------------------------------------------ item epilogue: dQ partial sums of this split
       {
         const uint32_t gl = g + T - 1;
