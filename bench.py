@@ -464,10 +464,10 @@ def main():
     # dTables (adjoint of the bias gather) is the dominant kernel of the step: dt6, a dense tcgen05 contraction.
     # Algorithmic work per pair: 8 vertices x 8 corners x 4 heads = 256 multiply-adds = 512 FLOP; mandatory HBM traffic: the
     # scaled fp16 dS of the 4 heads (8 B per pair) + key xyz + query geometry + one 128 KB table copy per CTA.
-    # What the kernel EXECUTES on the tensor pipe is the dense form of that contraction: per 64 pairs 16 MMAs of 128 x 80 x 16,
-    # i.e. 81 920 FLOP per pair of which 512 touch non-zero weights.
+    # What the kernel EXECUTES on the tensor pipe is the dense form of that contraction: per 64 pairs 4 K-steps of
+    # 128 x (256 + 144) x 16, i.e. 102 400 FLOP per pair of which 512 touch non-zero weights.
     dt_flops = pairs * 512.0
-    dt_dense_flops = pairs * (16 * 128 * 80 * 16 * 2) / 64.0
+    dt_dense_flops = pairs * (4 * 128 * 400 * 16 * 2) / 64.0
     dt_bytes = pairs * 8 + a.batch * (NK * 16 + NQ * 144) + 148 * 4 * 100 * 80 * 4
     dt_tf = dt_flops / (dt_ms * 1e-3) / 1e12 if dt_ms > 0 else 0.0
     dt_dense_tf = dt_dense_flops / (dt_ms * 1e-3) / 1e12 if dt_ms > 0 else 0.0
@@ -489,10 +489,10 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                          "launch_ms": dt_ms, "algorithmic_flops": dt_flops, "algorithmic_bytes": dt_bytes,
                          "note": "achieved counts the 512 useful FLOP per (query, key) pair only; the kernel reaches them by executing the "
-                                 "dense 128 x 80 MMAs of the factored weights (96 % zeros) because that costs 13x fewer issue slots than "
+                                 "dense 128 x 400 MMAs of the factored weights (96 % zeros) because that costs 13x fewer issue slots than "
                                  "sorting + register accumulation (dt3: 3.7 ms) -- see executed_dense_mma for how busy the tensor pipe is",
                          "executed_dense_mma": {"tflops": dt_dense_tf, "frac_of_peak": dt_dense_tf / peak_tf if peak_tf else None,
-                                                "flops_per_pair": 81920, "mma_floor_ms": dt_dense_flops / (2 * 4096.0 * 148 * 1.965e9) * 1e3,
+                                                "flops_per_pair": 102400, "mma_floor_ms": dt_dense_flops / (2 * 4096.0 * 148 * 1.965e9) * 1e3,
                                                 "tensor_pipe_active_pct_ncu": ncu.get("dtables", {}).get("tensor_pipe_pct") if full else None},
                          "hbm_view": {"achieved_gbs": dt_gbs, "peak_gbs": peak_bw, "frac": dt_gbs / peak_bw if peak_bw else None},
                          "warp_inst_per_pair": dt_inst / pairs if (dt_inst and full) else None},

@@ -58,7 +58,7 @@ if os.environ.get("VDETR_DT_CLOCKS") == "1":
     torch.cuda.synchronize()
     _C.check(_C.lib().vdetr_debug_dt6_clocks(buf))
     items = B * 1024 * 64 * 4
-    v = [buf[i] / items / (6 if i < 4 else 4) for i in range(6)]
+    v = [buf[i] / items / (6 if i < 4 else 2) for i in range(6)]
     print("dt6 cycles per producer step: compute %.0f wait-empty %.0f store+fence+arrive %.0f load-issue %.0f | per item in an MMA warp: wait-full %.0f issue+commit %.0f"
           % tuple(v))
     print("per CTA and call: prologue %.0f cycles, producer loop of warp 0 %.0f cycles" % (buf[6] / 148 / 4, buf[7] / 148 / 4))

@@ -4,28 +4,31 @@
 // For an axis-aligned box the trilinear weight of vertex (sx, sy, sz) in {+,-}^3 factors per axis,
 //     w(q, k; z, y, x) = hz^{sz}(q,k)[z] * hy^{sy}(q,k)[y] * hx^{sx}(q,k)[x],
 // every h a "hat" with (at most) two non-zero entries among the n <= 10 table points of that axis, so
-//     dT_{sx,sy,sz}[z][y][x][h] = sum_pairs ( hz^{sz}[z] hy^{sy}[y] ) * ( hx^{sx}[x] dS[h] )
-// is a GEMM over the pair index:  D_{sz,sy} [100 (z,y) x 80 (sx, x, h)]  +=  A_{sz,sy} [100 x pairs] * B [pairs x 80].
+//     dT_{sx,sy,sz}[z][y][x][h] = sum_pairs ( hz^{sz}[z] dS[h] ) * ( hy^{sy}[y] hx^{sx}[x] )
+// is ONE GEMM over the pair index:  D [80 (sz, z, h) x 400 (sy, y, sx, x)]  +=  A [80 x pairs] * B [pairs x 400].
 // The operands are 96 % zeros -- but scattering the 16 + 16 non-zero fp16 values of a pair into shared-memory tiles costs
-// ~20 instructions per vertex evaluation, where sorting the pairs by table cell and accumulating them in registers (dt3)
-// costs ~300, and the tensor pipe is otherwise idle in this phase of the step.  The four accumulators (4 x 80 fp32 TMEM
-// columns x 128 lanes) stay in tensor memory for the whole launch: no atomics, no flushes; every CTA leaves one private
-// copy and a second kernel sums the copies in a fixed order (bit-reproducible).
+// ~25 instructions per pair and axis pair, where sorting the pairs by table cell and accumulating them in registers (dt3)
+// costs hundreds, and the tensor pipe is otherwise idle in this phase of the step.  The accumulator (400 fp32 TMEM columns
+// x 128 lanes) stays in tensor memory for the whole launch: no atomics, no flushes; every CTA leaves one private copy and a
+// second kernel sums the copies in a fixed order (bit-reproducible).
 //
-//   stage   = 64 pairs (one query x 64 consecutive keys): four A tiles [104 rows x 64 pairs], fp16, K-major rows of 128 B with
-//             the 128-byte swizzle (the layout TMA would write), and one B tile stored MN-MAJOR ([64 pairs][128 columns] in two
-//             64-column blocks, 128-byte swizzle): the 4 heads of one x table point are 8 contiguous bytes of a pair's row, so
-//             a producer writes them with ONE 64-bit store.  Rows >= 100 of A / columns >= 80 of B are dump slots for corners
-//             outside the table (zero padding of grid_sample), never read as results: the MMA (M = 128) reads 24 rows past
-//             each A tile, which only feeds accumulator lanes 104..127 that nobody reads.
-//   warps   : 3 stages x 6 producer warps (lane = pair; a warp owns 32 pairs and one role: the A tiles of y+, the A tiles of
-//             y-, or the B tile -- see produce<>), four MMA warps (one lane each issues the 4 K-steps of its variant per
-//             stage: tcgen05.mma M = 128, N = 80, K = 16).  A producer computes the next item while the MMAs of its stage
-//             run, then zeroes the entries it wrote last time and writes the new ones.  The producers are bound by
-//             instruction issue, so the roles are cut to minimise instructions per pair (6 + 2 axis evaluations, 16 + 4
-//             stores); the first version (4 warps per stage, 8 + 8 axes, 32 16-bit stores per pair) kept the MMA warps
-//             waiting 40 % of the time.
-//   bound   : 40 cycles per MMA (128 x 80 x 16 MACs) x 16 = 640 cycles per 64 pairs and SM.
+//   stage   = 64 pairs (one query x 64 consecutive keys):
+//             B tile [408 rows x 64 pairs] fp16, K-major rows of 128 B with the 128-byte swizzle (the layout TMA would write);
+//               row = ((sy * 10 + y) * 2 + sx) * 10 + x, rows 400..407 = dump rows for corners outside the table (the zero
+//               padding of grid_sample);
+//             A tile stored MN-MAJOR ([64 pairs][128 rows] in two 64-row blocks, 128-byte swizzle): row = (sz * 10 + z) * 4 + h,
+//               so the 4 heads of a z point are 8 contiguous bytes of a pair's line -> ONE 64-bit store; rows 80..87 = dump.
+//   warps   : 3 stages x 6 producer warps (lane = pair; a warp owns 32 pairs and one role: the B rows of y+, the B rows of
+//             y-, or the A tile -- see produce<>), two MMA warps (one lane each: columns [0, 256) and [256, 400) of D,
+//             4 K-steps per stage: tcgen05.mma M = 128, N = 256 / 144, K = 16).  A producer computes the next item while
+//             the MMAs of its stage run, then zeroes the entries it wrote last time and writes the new ones.
+//   bound   : (128 + 72) cycles per K-step x 4 = 800 cycles of tensor pipe per 64 pairs and SM; operand reads from shared
+//             memory 21 KB per K-step = 96 ... 120 B/clk.
+//   history : the first layout had (z, y) on the M side (four 100-row A tiles, one per (sz, sy)) and N = 80 (sx, x, h):
+//             640 tensor cycles per item, but an M = 128, N = 80 MMA reads 6.5 KB of operands for 40 cycles of math -- 162 B/clk
+//             against the 128 B/clk shared memory delivers -- and the producers' scattered stores compete for the same port:
+//             2.0 ms per launch, MMA warps idle a third of the time.  Operand bytes per MAC fall with N, and this is the one
+//             factorisation of the contraction with a large N.
 #include "rpe_internal.h"
 #include "rpe_fast.cuh"
 #include <stdlib.h>
@@ -36,17 +39,19 @@ using namespace tc;
 
 constexpr int STAGES = 3, KS = 64;
 constexpr int TP = 10;                                  // table points per axis the tiles are laid out for (n <= TP)
-constexpr int A_ROWS = 104, A_BYTES = A_ROWS * 128;     // rows 100..103: dump
-constexpr int B_BYTES = 2 * KS * 128;                   // MN-major: two 64-column blocks of [64 pairs][128 B]; columns 80..87: dump
-constexpr int NCOL = 2 * TP * 4;                        // 80 accumulator columns: (x sign, x point, head)
-constexpr int STAGE_BYTES = 4 * A_BYTES + B_BYTES;      // 64512
+constexpr int NB = 2 * TP * 2 * TP;                     // 400 accumulator columns: (y sign, y point, x sign, x point)
+constexpr int B_ROWS = NB + 8, B_BYTES = B_ROWS * 128;  // rows 400..407: dump
+constexpr int MA = 2 * TP * 4;                          // 80 accumulator rows: (z sign, z point, head)
+constexpr int A_BYTES = 2 * KS * 128;                   // MN-major: two 64-row blocks of [64 pairs][128 B]; rows 80..87: dump
+constexpr int N0 = 256, N1 = NB - N0;                   // the two MMAs of a K-step
+constexpr int STAGE_BYTES = B_BYTES + A_BYTES;          // 68608
 constexpr int WPS = 6;                                  // producer warps per stage
 constexpr int PROD_WARPS = STAGES * WPS;
-constexpr int MMA_WARPS = 4;                            // one per (z sign, y sign) variant: issuing an MMA costs ~100 cycles
+constexpr int MMA_WARPS = 2;                            // one per column chunk of D
 constexpr int THREADS = (PROD_WARPS + MMA_WARPS) * 32;
-constexpr int COPY_FLOATS = 4 * TP * TP * NCOL;         // one private copy: [variant][z * 10 + y][80]
-static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "tiles start on 1024-byte swizzle atoms");
-static_assert(3 * 1024 <= B_BYTES, "the MMA over-read of the last A tile stays inside the stage");
+constexpr int COPY_FLOATS = MA * NB;                    // one private copy: [(sz, z, h)][(sy, y, sx, x)]
+static_assert(B_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && (N0 * 128) % 1024 == 0, "tiles start on 1024-byte swizzle atoms");
+static_assert(N1 % 16 == 0 && N0 % 16 == 0 && NB <= 512, "MMA shapes / TMEM columns");
 
 struct Params {
   int B, nQ, nK, nQp, nKp, n, KT;
@@ -82,26 +87,26 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
 }
 
 // One producer warp: 32 pairs (lane = pair) of every STAGES-th item of the CTA, for one role:
-//   ROLE 0 / 1 : the y sign ys = ROLE; writes the 4 entries of A_{z+,ys} and of A_{z-,ys}   (3 axes: z+, z-, y^{ys})
-//   ROLE 2     : the B tile: for x+ and x-, the two x table points times the 4 heads of dS = four 64-bit stores (2 axes)
+//   ROLE 0 / 1 : the y sign sy = ROLE; writes, for x+ and x-, the 4 entries hy^{sy}[y] hx^{sx}[x] of B   (3 axes: x+, x-, y^{sy})
+//   ROLE 2     : the A tile: for z+ and z-, the two z table points times the 4 heads of dS = four 64-bit stores (2 axes)
 // Per step: compute the entries of the next item from registers loaded two rounds ago, wait until the MMAs that read the
 // stage are done, zero the entries written last time, write the new ones, hand the stage over, reload the register set.
 template <int ROLE>
 __device__ __forceinline__ void produce(const Params& P, uint8_t* smem, uint64_t* bar_full, uint64_t* bar_empty, int stage, int khalf,
                                         int lane, long long i_begin, int my_items, long long tk0, long long tk1) {
-  constexpr int NA = (ROLE == 2) ? 4 : 8;               // stores per step (16-bit for A, 64-bit for B)
+  constexpr int NA = (ROLE == 2) ? 4 : 8;               // stores per step (16-bit for B, 64-bit for A)
   const uint32_t kloc = (uint32_t)(khalf * 32 + lane);
   const uint32_t lanec = ((kloc >> 3) << 4) | ((kloc & 7u) << 1);
   const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
-  const uint32_t tA0 = sbase + (uint32_t)ROLE * A_BYTES, tA1 = tA0 + 2 * A_BYTES;          // (z+, ys), (z-, ys)
-  // MN-major B: this pair's 128-byte row of column block 0; the 4 heads of column group c (a multiple of 4) are 8 bytes
-  const uint32_t brow = sbase + 4 * A_BYTES + kloc * 128u, bsw = kloc & 7u;
-  auto b_off = [&](uint32_t c) { return brow + (c >> 6) * (uint32_t)(KS * 128) + ((((c & 63u) >> 3) ^ bsw) << 4) + ((c & 4u) << 1); };
+  const uint32_t tB = sbase;
+  // MN-major A: this pair's 128-byte line of row block 0; the 4 heads of row group m (a multiple of 4) are 8 bytes
+  const uint32_t arow = sbase + B_BYTES + kloc * 128u, asw = kloc & 7u;
+  auto a_off = [&](uint32_t m) { return arow + (m >> 6) * (uint32_t)(KS * 128) + ((((m & 63u) >> 3) ^ asw) << 4) + ((m & 4u) << 1); };
   const int n = P.n;
 
   struct Raw {                    // what a lane loads for one pair
     float4 kx;                    // key xyz
-    float f0, f1, f2;             // box faces: ROLE 0/1: z+, z-, y^{ys};  ROLE 2: x+, x-
+    float f0, f1, f2;             // box faces: ROLE 0/1: x+, x-, y^{sy};  ROLE 2: z+, z-
     int fast;                     // axis-aligned box
     unsigned short d[4];          // ROLE 2: scaled fp16 dS of the 4 heads
   };
@@ -114,8 +119,8 @@ __device__ __forceinline__ void produce(const Params& P, uint8_t* smem, uint64_t
   auto load = [&](Raw& w, int b_, int q_, int kt_) {
     const int k = kt_ * KS + (int)kloc;
     const float* g = reinterpret_cast<const float*>(P.geo + ((size_t)b_ * P.nQp + q_) * 9);
-    if (ROLE < 2) { w.f0 = __ldg(g + 2); w.f1 = __ldg(g + 6); w.f2 = __ldg(g + ROLE * 4 + 1); }
-    else { w.f0 = __ldg(g); w.f1 = __ldg(g + 4); }
+    if (ROLE < 2) { w.f0 = __ldg(g); w.f1 = __ldg(g + 4); w.f2 = __ldg(g + ROLE * 4 + 1); }
+    else { w.f0 = __ldg(g + 2); w.f1 = __ldg(g + 6); }
     w.fast = __float_as_int(__ldg(g + 3));
     w.kx = __ldg(P.xyz4 + (size_t)b_ * P.nKp + k);
     if (ROLE == 2) {
@@ -139,50 +144,49 @@ __device__ __forceinline__ void produce(const Params& P, uint8_t* smem, uint64_t
   if (stage + STAGES < my_items) { load(r1, b, q, kt); kt1 = kt; }
   uint32_t adr0[NA], adr1[NA];
 #pragma unroll
-  for (int i = 0; i < NA; ++i) adr0[i] = adr1[i] = (ROLE == 2) ? b_off(80u) : tA0 + sw_off(100, lanec);
+  for (int i = 0; i < NA; ++i) adr0[i] = adr1[i] = (ROLE == 2) ? a_off((uint32_t)MA) : tB + sw_off((uint32_t)NB, lanec);
 
   long long c_comp = 0, c_wait = 0, c_store = 0, c_load = 0;
   auto step = [&](Raw& cur, int& ckt, int it, uint32_t (&adr)[NA], const uint32_t (&old)[NA]) {
     const long long t0 = P.clk ? clock64() : 0;
     const bool active = (ckt * KS + (int)kloc) < P.nK && cur.fast != 0;   // inside nK, axis-aligned box
     const float act = active ? 1.f : 0.f;
-    uint32_t val[NA], hi2[4];                           // hi2: heads 2, 3 of the 64-bit B stores
+    uint32_t val[NA], hi2[4];                           // hi2: heads 2, 3 of the 64-bit A stores
     if (ROLE < 2) {
-      int nz[2], ny;
-      float fz[2], fy;
-      axis_pt(cur.f0 - cur.kx.z, P.log_scale, P.c1, P.c0, n, nz[0], fz[0]);
-      axis_pt(cur.f1 - cur.kx.z, P.log_scale, P.c1, P.c0, n, nz[1], fz[1]);
+      int nx[2], ny;
+      float fx[2], fy;
+      axis_pt(cur.f0 - cur.kx.x, P.log_scale, P.c1, P.c0, n, nx[0], fx[0]);
+      axis_pt(cur.f1 - cur.kx.x, P.log_scale, P.c1, P.c0, n, nx[1], fx[1]);
       axis_pt(cur.f2 - cur.kx.y, P.log_scale, P.c1, P.c0, n, ny, fy);
       const bool vy0 = (unsigned)ny < (unsigned)n, vy1 = (unsigned)(ny + 1) < (unsigned)n;
       const float wy0 = (1.f - fy) * act, wy1 = fy * act;
 #pragma unroll
-      for (int zs = 0; zs < 2; ++zs) {
-        const uint32_t tile = zs ? tA1 : tA0;
-        const bool vz0 = (unsigned)nz[zs] < (unsigned)n, vz1 = (unsigned)(nz[zs] + 1) < (unsigned)n;
-        const float wz1 = fz[zs], wz0 = 1.f - wz1;
-        const int r00 = nz[zs] * TP + ny;
-        const uint32_t p0 = pack_f16x2(wz0 * wy0, wz0 * wy1), p1 = pack_f16x2(wz1 * wy0, wz1 * wy1);
-        adr[zs * 4 + 0] = tile + sw_off((vz0 && vy0) ? (uint32_t)r00 : 100u, lanec);
-        adr[zs * 4 + 1] = tile + sw_off((vz0 && vy1) ? (uint32_t)(r00 + 1) : 101u, lanec);
-        adr[zs * 4 + 2] = tile + sw_off((vz1 && vy0) ? (uint32_t)(r00 + TP) : 102u, lanec);
-        adr[zs * 4 + 3] = tile + sw_off((vz1 && vy1) ? (uint32_t)(r00 + TP + 1) : 103u, lanec);
-        val[zs * 4 + 0] = p0; val[zs * 4 + 1] = p0 >> 16; val[zs * 4 + 2] = p1; val[zs * 4 + 3] = p1 >> 16;
+      for (int xs = 0; xs < 2; ++xs) {
+        const bool vx0 = (unsigned)nx[xs] < (unsigned)n, vx1 = (unsigned)(nx[xs] + 1) < (unsigned)n;
+        const float wx1 = fx[xs], wx0 = 1.f - wx1;
+        const int r00 = ((ROLE * TP + ny) * 2 + xs) * TP + nx[xs];          // row of (y0, x0); y + 1: + 2 * TP, x + 1: + 1
+        const uint32_t p0 = pack_f16x2(wy0 * wx0, wy0 * wx1), p1 = pack_f16x2(wy1 * wx0, wy1 * wx1);
+        adr[xs * 4 + 0] = tB + sw_off((vy0 && vx0) ? (uint32_t)r00 : (uint32_t)NB, lanec);
+        adr[xs * 4 + 1] = tB + sw_off((vy0 && vx1) ? (uint32_t)(r00 + 1) : (uint32_t)(NB + 1), lanec);
+        adr[xs * 4 + 2] = tB + sw_off((vy1 && vx0) ? (uint32_t)(r00 + 2 * TP) : (uint32_t)(NB + 2), lanec);
+        adr[xs * 4 + 3] = tB + sw_off((vy1 && vx1) ? (uint32_t)(r00 + 2 * TP + 1) : (uint32_t)(NB + 3), lanec);
+        val[xs * 4 + 0] = p0; val[xs * 4 + 1] = p0 >> 16; val[xs * 4 + 2] = p1; val[xs * 4 + 3] = p1 >> 16;
       }
     } else {
-      // hx[x] * dS[h]: fp32 products rounded once to fp16 (dS arrives as scaled fp16)
+      // hz[z] * dS[h]: fp32 products rounded once to fp16 (dS arrives as scaled fp16)
       const float2 d01 = __half22float2(__halves2half2(__ushort_as_half(cur.d[0]), __ushort_as_half(cur.d[1])));
       const float2 d23 = __half22float2(__halves2half2(__ushort_as_half(cur.d[2]), __ushort_as_half(cur.d[3])));
 #pragma unroll
-      for (int xs = 0; xs < 2; ++xs) {
-        int nx;
-        float fx;
-        axis_pt((xs ? cur.f1 : cur.f0) - cur.kx.x, P.log_scale, P.c1, P.c0, n, nx, fx);
-        const float w0 = (1.f - fx) * act, w1 = fx * act;
-        const bool vx0 = (unsigned)nx < (unsigned)n, vx1 = (unsigned)(nx + 1) < (unsigned)n;
-        adr[xs * 2 + 0] = b_off(vx0 ? (uint32_t)((xs * TP + nx) * 4) : 80u);
-        adr[xs * 2 + 1] = b_off(vx1 ? (uint32_t)((xs * TP + nx + 1) * 4) : 84u);
-        val[xs * 2 + 0] = pack_f16x2(w0 * d01.x, w0 * d01.y); val[xs * 2 + 1] = pack_f16x2(w1 * d01.x, w1 * d01.y);
-        hi2[xs * 2 + 0] = pack_f16x2(w0 * d23.x, w0 * d23.y); hi2[xs * 2 + 1] = pack_f16x2(w1 * d23.x, w1 * d23.y);
+      for (int zs = 0; zs < 2; ++zs) {
+        int nz;
+        float fz;
+        axis_pt((zs ? cur.f1 : cur.f0) - cur.kx.z, P.log_scale, P.c1, P.c0, n, nz, fz);
+        const float w0 = (1.f - fz) * act, w1 = fz * act;
+        const bool vz0 = (unsigned)nz < (unsigned)n, vz1 = (unsigned)(nz + 1) < (unsigned)n;
+        adr[zs * 2 + 0] = a_off(vz0 ? (uint32_t)((zs * TP + nz) * 4) : (uint32_t)MA);
+        adr[zs * 2 + 1] = a_off(vz1 ? (uint32_t)((zs * TP + nz + 1) * 4) : (uint32_t)(MA + 4));
+        val[zs * 2 + 0] = pack_f16x2(w0 * d01.x, w0 * d01.y); val[zs * 2 + 1] = pack_f16x2(w1 * d01.x, w1 * d01.y);
+        hi2[zs * 2 + 0] = pack_f16x2(w0 * d23.x, w0 * d23.y); hi2[zs * 2 + 1] = pack_f16x2(w1 * d23.x, w1 * d23.y);
       }
     }
 
@@ -267,18 +271,17 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
     else produce<2>(P, smem, bar_full, bar_empty, stage, pw & 1, lane, i_begin, my_items, tk0, tk1);
   } else {
     // ------------------------------------------------------------------------------------------ MMA issuers
-    // Warp PROD_WARPS + v issues the 4 K-steps of variant v of every stage.  (One lane issuing all 16 MMAs of a stage was
-    // the bottleneck of the first version: ~95 cycles of descriptor moves and issue per MMA against 40 cycles of execution.)
+    // Warp PROD_WARPS + c issues the 4 K-steps of column chunk c of every stage.
     if (lane == 0) {
-      const int v = warp - PROD_WARPS;
-      const uint32_t idesc = umma_idesc_f16_major(128, NCOL, false, true);   // A K-major, B MN-major
-      const uint32_t td = tmem_base + v * NCOL;
+      const int c = warp - PROD_WARPS;
+      const uint32_t idesc = umma_idesc_f16_major(128, c ? N1 : N0, true, false);   // A MN-major, B K-major
+      const uint32_t td = tmem_base + c * N0;
       uint64_t da[STAGES], db[STAGES];
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) {
         const uint32_t sbase = smem_u32(smem + s * STAGE_BYTES);
-        da[s] = umma_desc_sw128(sbase + v * A_BYTES);
-        db[s] = umma_desc_sw128_mn(sbase + 4 * A_BYTES, KS * 128, 1024);   // column blocks 8192 B apart, 8-pair groups 1024 B
+        da[s] = umma_desc_sw128_mn(sbase + B_BYTES, KS * 128, 1024);    // row blocks 8192 B apart, 8-pair groups 1024 B
+        db[s] = umma_desc_sw128(sbase + c * N0 * 128);
       }
       long long m_wait = 0, m_issue = 0;
       for (int it0 = 0; it0 < my_items; it0 += STAGES) {
@@ -292,8 +295,8 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
             tc_fence_after();
             if (!(P.dbg & 1)) {
 #pragma unroll
-              for (int kk = 0; kk < KS / 16; ++kk)
-                umma_bf16(td, da[s] + (uint64_t)(kk * 2), db[s] + (uint64_t)(kk * 128), idesc, (it0 + s) > 0 || kk > 0);   // 16 pairs: +32 B of an A row, +16 rows of B
+              for (int kk = 0; kk < KS / 16; ++kk)     // 16 pairs: +16 lines of A, +32 B of a B row
+                umma_bf16(td, da[s] + (uint64_t)(kk * 128), db[s] + (uint64_t)(kk * 2), idesc, (it0 + s) > 0 || kk > 0);
             }
             umma_commit(bar_empty + s);
             if (P.clk) { m_wait += t1 - t0; m_issue += clock64() - t1; }
@@ -307,25 +310,21 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
   }
 
   // -------------------------------------------------------------------------------------------- epilogue: TMEM -> private copy
-  if (warp < 8) {
+  if (warp < 12) {                             // 3 column groups x 4 lane quarters; rows >= 80 of D are never read
     mbar_wait_relaxed(bar_done, 0);
     tc_fence_after();
     const int quad = warp & 3, row = quad * 32 + lane;
     float* dst = P.priv + (size_t)blockIdx.x * COPY_FLOATS;
 #pragma unroll 1
-    for (int vv = 0; vv < 2; ++vv) {
-      const int v = (warp >> 2) * 2 + vv;
-#pragma unroll 1
-      for (int c = 0; c < NCOL / 16; ++c) {
-        uint32_t rr[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(v * NCOL + c * 16), rr);
-        tmem_ld_wait();
-        if (row < TP * TP) {
-          float4* o = reinterpret_cast<float4*>(dst + ((size_t)v * TP * TP + row) * NCOL + c * 16);
+    for (int c = warp >> 2; c < NB / 16; c += 3) {
+      uint32_t rr[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16), rr);
+      tmem_ld_wait();
+      if (row < MA) {
+        float4* o = reinterpret_cast<float4*>(dst + (size_t)row * NB + c * 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
-        }
+        for (int j = 0; j < 4; ++j)
+          o[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
       }
     }
   }
@@ -335,43 +334,40 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
 }
 
 // out[vertex][z][y][x][h] (+)= (1 / scale) * sum over the private copies, in a fixed order.  A CTA owns 32 consecutive
-// outputs; its 8 warps split the copies.
+// elements of a copy (coalesced reads); its 8 warps split the copies; every element maps to one output.
 __global__ void __launch_bounds__(256) rpe_dtables_umma_reduce_kernel(const float* __restrict__ priv, int copies, int n,
                                                                       float* __restrict__ out, const unsigned* absmax_bits, int dense,
                                                                       int accumulate) {
   __shared__ float part[8][32];
   const float inv = 1.0f / vdetr_dt_scale(*absmax_bits, dense);
-  const int total = 8 * n * n * n * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i0 = blockIdx.x * 32; i0 < total; i0 += gridDim.x * 32) {
-    const int i = i0 + lane;
-    float s = 0.f;
-    if (i < total) {
-      const int h = i & 3;
-      int r = i >> 2;
-      const int x = r % n; r /= n;
-      const int y = r % n; r /= n;
-      const int z = r % n;
-      const int v = r / n;
-      // vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4..7: the same with z +
-      const int xs = ((v & 3) >= 2) ? 1 : 0, ys = ((v & 3) == 1 || (v & 3) == 2) ? 1 : 0, zs = (v < 4) ? 1 : 0;
-      const size_t src = ((size_t)(zs * 2 + ys) * TP * TP + z * TP + y) * NCOL + (xs * TP + x) * 4 + h;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int i0 = blockIdx.x * 32; i0 < COPY_FLOATS; i0 += gridDim.x * 32) {
+    const int src = i0 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (src < COPY_FLOATS) {
       int c = warp;
       for (; c + 24 < copies; c += 32) {
         s0 += priv[(size_t)c * COPY_FLOATS + src]; s1 += priv[(size_t)(c + 8) * COPY_FLOATS + src];
         s2 += priv[(size_t)(c + 16) * COPY_FLOATS + src]; s3 += priv[(size_t)(c + 24) * COPY_FLOATS + src];
       }
       for (; c < copies; c += 8) s0 += priv[(size_t)c * COPY_FLOATS + src];
-      s = (s0 + s1) + (s2 + s3);
     }
-    part[warp][lane] = s;
+    part[warp][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (warp == 0 && i < total) {
+    if (warp == 0 && src < COPY_FLOATS) {
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += part[w][lane];
-      out[i] = (accumulate ? out[i] : 0.f) + t * inv;
+      // src = m * 400 + col, m = (sz * 10 + z) * 4 + h, col = ((sy * 10 + y) * 2 + sx) * 10 + x
+      const int m = src / NB, col = src - m * NB;
+      const int h = m & 3, z = (m >> 2) % TP, zs = (m >> 2) / TP;
+      const int x = col % TP, xs = (col / TP) & 1, y = (col / (2 * TP)) % TP, ys = col / (2 * TP * TP);
+      if (z < n && y < n && x < n) {
+        // vertex sign table: 0:(+,+,-) 1:(+,-,-) 2:(-,-,-) 3:(-,+,-) 4..7: the same with z +
+        const int v = (zs ? 0 : 4) + (xs ? (ys ? 2 : 3) : (ys ? 1 : 0));
+        const size_t o = ((((size_t)v * n + z) * n + y) * n + x) * 4 + h;
+        out[o] = (accumulate ? out[o] : 0.f) + t * inv;
+      }
     }
     __syncthreads();
   }
@@ -414,8 +410,7 @@ int rpe_dt6_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz
   VDETR_CUDA_TRY(cudaFuncSetAttribute(dt6::rpe_dtables_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dt6::rpe_dtables_umma_kernel<<<grid, dt6::THREADS, smem, st>>>(P);
   VDETR_LAUNCH_CHECK();
-  const int total = 8 * n * n * n * 4;
-  dt6::rpe_dtables_umma_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(priv, grid, n, dtables, absmax_bits, dense_scale, accumulate);
+  dt6::rpe_dtables_umma_reduce_kernel<<<(dt6::COPY_FLOATS + 31) / 32, 256, 0, st>>>(priv, grid, n, dtables, absmax_bits, dense_scale, accumulate);
   VDETR_LAUNCH_CHECK();
   return 0;
 }
