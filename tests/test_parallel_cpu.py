@@ -75,6 +75,19 @@ def test_shard_range_is_a_partition():
 
 
 @pytest.mark.timeout(300)
+def test_flat_shard_range_tiles_the_vector_on_float4_boundaries():
+    """The shards of the peer-memory optimizer (parallel.FlatAdamW(peer=...), csrc/peer.cu) partition [0, n) for any n and
+    world size, with float4-aligned interior boundaries."""
+    from vdetr_b200.parallel import flat_shard_range
+    for n in (0, 1, 3, 4, 5, 17, 1000, 11_634_563, 11_634_564):
+        for world in (1, 2, 3, 8):
+            edges = [flat_shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+                assert hi == lo2 and lo <= hi and hi % 4 == 0
+            assert all(lo % 4 == 0 for lo, _ in edges)
+
+
 def test_ddp_gloo_world2_gradients_and_timing():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

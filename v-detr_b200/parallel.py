@@ -27,6 +27,15 @@ def wrap_data_parallel(module: torch.nn.Module, device=None, find_unused_paramet
     return torch.nn.parallel.DistributedDataParallel(module, device_ids=ids, find_unused_parameters=find_unused_parameters)
 
 
+def flat_shard_range(n: int, rank: int, world: int):
+    """[lo, hi) of a flat vector of n floats owned by `rank` in the peer-memory optimizer (csrc/peer.cu): shards tile [0, n),
+    every boundary except n itself is a multiple of 4 (the kernels move float4), the last rank takes the tail."""
+    n4 = n // 4
+    lo = (n4 * rank // world) * 4
+    hi = n if rank == world - 1 else (n4 * (rank + 1) // world) * 4
+    return lo, hi
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Every multi-GPU time is reported as the maximum over ranks (never wall clock)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -251,9 +260,7 @@ class FlatAdamW:
             if peer.dist:
                 dist.broadcast(self.flat_p, 0)         # every rank starts from rank 0's parameters (what DDP does)
             self.grads = FlatGradAllReduce(self.params, flat=self._g_buf.view(torch.float32, self.n))
-            n4 = self.n // 4
-            self.lo = (n4 * peer.rank // peer.world) * 4
-            self.hi = self.n if peer.rank == peer.world - 1 else (n4 * (peer.rank + 1) // peer.world) * 4
+            self.lo, self.hi = flat_shard_range(self.n, peer.rank, peer.world)
             self._norm_buf = peer.alloc(_peer_norm_bytes())
             self._reduced = torch.zeros(max(self.hi - self.lo, 4), dtype=torch.float32, device=ref.device)
             self.last_norm = torch.zeros(1, dtype=torch.float32, device=ref.device)
