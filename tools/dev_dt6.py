@@ -32,6 +32,26 @@ for (b, nq, nk) in ((1, 5, 64), (1, 33, 130), (2, 100, 1000), (1, 1024, 4096)):
           f"finite {bool(torch.isfinite(c).all())}  run-to-run identical {bool(torch.equal(c, c2))}", flush=True)
 
 xyz, ref, ds = case(B, 1024, 4096, 1)
+splits = os.environ.get("DT6_SPLITS", "")
+if splits:      # developer: time the kernel for several column splits of the two MMAs of a K-step
+    for n0 in splits.split(","):
+        os.environ["VDETR_DT_IMPL"] = "6"; os.environ["VDETR_DT6_DBG"] = "0"; os.environ["VDETR_DT6_N0"] = n0
+        for _ in range(2):
+            c = ops.rpe_bias_grad_tables(xyz, ref, None, t0, ds)
+        torch.cuda.synchronize()
+        import ctypes
+        from vdetr_b200 import _C
+        _C.lib().vdetr_timing_enable(1)
+        for _ in range(5):
+            c = ops.rpe_bias_grad_tables(xyz, ref, None, t0, ds)
+        torch.cuda.synchronize()
+        tot = (ctypes.c_float * 4)(); cnt = (ctypes.c_int * 4)()
+        _C.lib().vdetr_timing_read(tot, cnt)
+        _C.lib().vdetr_timing_enable(0)
+        os.environ["VDETR_DT_IMPL"] = "3"
+        a = ops.rpe_bias_grad_tables(xyz, ref, None, t0, ds)
+        print(f"N0 = {n0}: {tot[2] / max(cnt[2], 1):.4f} ms per call; max|dt6 - dt3| / max {((c - a).abs().max() / a.abs().max()).item():.3e}", flush=True)
+    sys.exit(0)
 for impl, dbg in (("3", "0"), ("6", "0"), ("6", "1"), ("6", "2"), ("6", "3")):
     os.environ["VDETR_DT_IMPL"] = impl
     os.environ["VDETR_DT6_DBG"] = dbg

@@ -63,6 +63,7 @@ struct Params {
   float* priv;                                          // [gridDim.x][COPY_FLOATS]
   unsigned long long* clk;                              // developer: [8] phase cycle sums (VDETR_DT_CLOCKS=1), else null
   int dbg;                                              // developer: 1 = no MMAs, 2 = no producer work, 4 = no loads
+  int n0;                                               // columns of the first MMA of a K-step (the second takes NB - n0)
 };
 
 __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
@@ -274,14 +275,14 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_dtables_umma_kernel(const Para
     // Warp PROD_WARPS + c issues the 4 K-steps of column chunk c of every stage.
     if (lane == 0) {
       const int c = warp - PROD_WARPS;
-      const uint32_t idesc = umma_idesc_f16_major(128, c ? N1 : N0, true, false);   // A MN-major, B K-major
-      const uint32_t td = tmem_base + c * N0;
+      const uint32_t idesc = umma_idesc_f16_major(128, c ? NB - P.n0 : P.n0, true, false);   // A MN-major, B K-major
+      const uint32_t td = tmem_base + c * P.n0;
       uint64_t da[STAGES], db[STAGES];
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) {
         const uint32_t sbase = smem_u32(smem + s * STAGE_BYTES);
         da[s] = umma_desc_sw128_mn(sbase + B_BYTES, KS * 128, 1024);    // row blocks 8192 B apart, 8-pair groups 1024 B
-        db[s] = umma_desc_sw128(sbase + c * N0 * 128);
+        db[s] = umma_desc_sw128(sbase + c * P.n0 * 128);
       }
       long long m_wait = 0, m_issue = 0;
       for (int it0 = 0; it0 < my_items; it0 += STAGES) {
@@ -399,6 +400,8 @@ int rpe_dt6_launch(const VdetrXattnShape* s, int nQp, int nKp, const float4* xyz
   P.c0 = 0.5f * (float)(n - 1);
   P.xyz4 = xyz4; P.geo = geo; P.dsb = dsb; P.priv = priv;
   { const char* e = getenv("VDETR_DT6_DBG"); P.dbg = e ? atoi(e) : 0; }
+  P.n0 = dt6::N0;
+  { const char* e = getenv("VDETR_DT6_N0"); if (e && atoi(e) >= 144 && atoi(e) <= 256 && atoi(e) % 16 == 0) P.n0 = atoi(e); }   // developer
   static const bool want_clocks = []() { const char* e = getenv("VDETR_DT_CLOCKS"); return e && e[0] == '1'; }();
   if (want_clocks && !g_dt6_clocks) {
     VDETR_CUDA_TRY(cudaMalloc(&g_dt6_clocks, 8 * sizeof(unsigned long long)));
