@@ -162,6 +162,19 @@ def test_grouped_heads_equal_head_by_head():
         for n in dec.HEAD_NAMES:
             assert a[n].shape == b[n].shape
             assert (a[n] - b[n]).abs().max().item() <= 1e-4 * (b[n].abs().max().item() + 1.0), n
+        if train:
+            # gradients through the grouped stack (incl. the _PadStack / _SplitHeadOutputs nodes) equal the head-by-head ones
+            w = {n: torch.randn(a[n].shape, generator=g) for n in dec.HEAD_NAMES if n != "angle_cls_head"}   # one head unused
+            pa = [p for n in dec.HEAD_NAMES for p in heads[n].parameters()]
+            pb = [p for n in dec.HEAD_NAMES for p in twin[n].parameters()]
+            ga = torch.autograd.grad(sum((a[n] * w[n]).sum() for n in w), pa, allow_unused=True)
+            gb = torch.autograd.grad(sum((b[n] * w[n]).sum() for n in w), pb, allow_unused=True)
+            for x1, x2, p_ in zip(ga, gb, pa):
+                if x2 is None:
+                    assert x1 is None or float(x1.abs().max()) == 0.0
+                    continue
+                assert x1 is not None and x1.shape == p_.shape
+                assert (x1 - x2).abs().max().item() <= 2e-4 * (x2.abs().max().item() + 1e-6)
         for n in dec.HEAD_NAMES:
             for m1, m2 in zip(heads[n].modules(), twin[n].modules()):
                 if isinstance(m1, torch.nn.BatchNorm1d):
@@ -169,3 +182,30 @@ def test_grouped_heads_equal_head_by_head():
                     assert torch.allclose(m1.running_var, m2.running_var, atol=1e-5)
                     assert int(m1.num_batches_tracked) == int(m2.num_batches_tracked)
     _ = vt
+
+
+def test_batched_token_linear_gradients_equal_bmm_autograd():
+    """ops._BatchedTokenLinear (dW in the parameter layout, split-K over 512-token slices) against torch.baddbmm's autograd,
+    for a contiguous [G, T, in] input and for the [T, G, in] -> transpose view the grouped heads feed into layer 2."""
+    from vdetr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    G, T, I, O = 3, 2048, 32, 24
+    for strided in (False, True):
+        base = torch.randn((T, G, I) if strided else (G, T, I), generator=g)
+        w = torch.randn(G, O, I, generator=g, requires_grad=True)
+        b = torch.randn(G, O, generator=g, requires_grad=True)
+        dy = torch.randn(G, T, O, generator=g)
+        xa = base.clone().requires_grad_(True)
+        xb = base.clone().requires_grad_(True)
+        va = xa.transpose(0, 1) if strided else xa
+        vb = xb.transpose(0, 1) if strided else xb
+        want = torch.baddbmm(b.unsqueeze(1), va, w.transpose(1, 2))
+        gw = torch.autograd.grad(want, (xa, w, b), dy)
+        got = ops._BatchedTokenLinear.apply(vb, w, b)
+        gg = torch.autograd.grad(got, (xb, w, b), dy)
+        assert torch.allclose(got, want, atol=1e-5)
+        for a_, r_ in zip(gg, gw):
+            assert a_.shape == r_.shape and (a_ - r_).abs().max().item() <= 1e-4 * r_.abs().max().item()
+        assert gg[1].is_contiguous()
+        got2 = ops._BatchedTokenLinear.apply(vb, w, None)
+        assert torch.allclose(got2, torch.bmm(va, w.transpose(1, 2)), atol=1e-5)

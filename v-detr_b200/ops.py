@@ -379,6 +379,51 @@ class _TokenLinear(Function):
         return dx, dw, db
 
 
+class _BatchedTokenLinear(Function):
+    """y[g] = x[g] @ W[g]^T (+ b[g]) for G independent layers on token-major activations: x [G, T, in] (any strides a batched
+    GEMM takes), W [G, out, in], b [G, out] or None -> [G, T, out].  What torch.bmm / baddbmm with W.transpose(1, 2) compute, but
+    the backward produces dW directly in the parameters' [G, out, in] layout (autograd's BmmBackward returns the transpose:
+    one strided copy per head in AccumulateGrad) and as a split-K batched GEMM over 512-token slices + one fixed-order sum
+    (the contraction runs over T = 8192 ... 32768 tokens for a 256 x 256 result: G x 4 output tiles otherwise)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        if bias is None:
+            return torch.bmm(x, weight.transpose(1, 2))
+        return torch.baddbmm(bias.unsqueeze(1), x, weight.transpose(1, 2))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        G, T, O = dy.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.bmm(dy, weight)
+        if ctx.needs_input_grad[1]:
+            S = min(T // 512, 64)
+            while S > 1 and T % S:
+                S -= 1
+            if S >= 4 and dy.is_contiguous() and x.is_contiguous():
+                part = torch.bmm(dy.view(G * S, T // S, O).transpose(1, 2), x.view(G * S, T // S, -1))      # [G*S, out, in]
+                dw = part.view(G, S, O, -1).sum(1)
+            else:
+                dw = torch.bmm(dy.transpose(1, 2), x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(1)
+        return dx, dw, db
+
+
+def batched_linear(x, weight, bias=None):
+    """y[g] = x[g] @ weight[g]^T + bias[g] for x [G, T, in], weight [G, out, in], bias [G, out] (see _BatchedTokenLinear)."""
+    if x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        return _BatchedTokenLinear.apply(x, weight, bias)
+    if bias is None:
+        return torch.bmm(x, weight.transpose(1, 2))
+    return torch.baddbmm(bias.unsqueeze(1), x, weight.transpose(1, 2))
+
+
 def linear(x, weight, bias=None):
     """torch.nn.functional.linear; on fp32 CUDA tensors that require grad the backward uses the library's column-sum
     kernel for the bias gradient."""

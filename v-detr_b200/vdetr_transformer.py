@@ -152,6 +152,45 @@ def _head_streams(device, n):
     return _HEAD_STREAMS[key][:n]
 
 
+class _PadStack(torch.autograd.Function):
+    """torch.stack([F.pad(t, (..., 0, omax - t.shape[0])) for t in ts]) for tensors that differ in their first dimension:
+    one zero fill + one copy per tensor forward (F.pad + stack: two launches per tensor + one), slices of the incoming gradient
+    backward (no kernel)."""
+
+    @staticmethod
+    def forward(ctx, omax, *ts):
+        ctx.sizes = [t.shape[0] for t in ts]
+        out = ts[0].new_zeros((len(ts), omax) + tuple(ts[0].shape[1:]))
+        for g, t in enumerate(ts):
+            out[g, :t.shape[0]].copy_(t)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        return (None,) + tuple(go[g, :n] for g, n in enumerate(ctx.sizes))
+
+
+class _SplitHeadOutputs(torch.autograd.Function):
+    """o [G, T = nQ*B, omax] (token t = q*B + b) -> G tensors [B, nQ, outs[g]].  The backward writes the G gradients into one
+    zero-filled [G, T, omax] buffer with one strided copy each; the equivalent chain of select / slice / view / transpose nodes
+    costs ~5 launches per head and direction (45 head outputs per decoder pass)."""
+
+    @staticmethod
+    def forward(ctx, o, nQ, B, outs):
+        ctx.meta = (o.shape, nQ, B, tuple(outs))
+        return tuple(o[g, :, :w].reshape(nQ, B, w).transpose(0, 1).contiguous() for g, w in enumerate(outs))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        shape, nQ, B, outs = ctx.meta
+        ref = next(g for g in grads if g is not None)
+        go = ref.new_zeros(shape)
+        for g, w in enumerate(outs):
+            if grads[g] is not None:
+                go[g, :, :w].view(nQ, B, w).copy_(grads[g].transpose(0, 1))
+        return go, None, None, None
+
+
 class BoxProcessor(object):
     """Turns MLP head outputs into boxes (:20-90)."""
 
@@ -339,8 +378,9 @@ class GlobalShareCrossAttention(nn.Module):
         w1 = torch.stack([m[0].weight for m in mlps])                                  # [8, hid, 3]
         b1 = torch.stack([m[0].bias for m in mlps])                                    # [8, hid]
         w2 = torch.stack([m[2].weight for m in mlps])                                  # [8, H, hid]
-        hid = torch.relu(torch.baddbmm(b1.unsqueeze(1), pts.unsqueeze(0).expand(len(mlps), -1, -1), w1.transpose(1, 2)))
-        return torch.bmm(hid, w2.transpose(1, 2)).view(len(mlps), n, n, n, -1)
+        # (ops.batched_linear: bmm / baddbmm whose weight gradients come out in the parameters' layout)
+        hid = torch.relu(ops.batched_linear(pts.unsqueeze(0).expand(len(mlps), -1, -1), w1, b1))
+        return ops.batched_linear(hid, w2).view(len(mlps), n, n, n, -1)
 
     def forward(self, query, key, reference_point, reference_angle, xyz, attn_mask=None, key_padding_mask=None,
                 need_weights=False):
@@ -613,16 +653,15 @@ class TransformerDecoder(nn.Module):
         h = ops.linear(feats, W1, b1)                                                               # [T, G*C]
         h = self._bn_relu_group(h, [st[1] for st in stacks], "cl", stacks[0][3])
         W2 = torch.stack([st[4].weight.squeeze(-1) for st in stacks])                               # [G, C, C]
-        h = torch.bmm(h.view(T, G, C).transpose(0, 1), W2.transpose(1, 2))                          # [G, T, C]
-        if stacks[0][4].bias is not None:
-            h = h + torch.stack([st[4].bias for st in stacks]).unsqueeze(1)
+        b2 = torch.stack([st[4].bias for st in stacks]) if stacks[0][4].bias is not None else None
+        h = ops.batched_linear(h.view(T, G, C).transpose(0, 1), W2, b2)                             # [G, T, C]
         h = self._bn_relu_group(h, [st[5] for st in stacks], "gm", stacks[0][7])
         outs = [st[8].out_channels for st in stacks]
         omax = (max(outs) + 7) // 8 * 8        # multiple of 8: cuBLAS otherwise falls back to its unaligned legacy kernels (140 us per call)
-        W3 = torch.stack([F.pad(st[8].weight.squeeze(-1), (0, 0, 0, omax - o)) for st, o in zip(stacks, outs)])   # [G, omax, C]
-        b3 = torch.stack([F.pad(st[8].bias, (0, omax - o)) for st, o in zip(stacks, outs)])                        # [G, omax]
-        o = torch.baddbmm(b3.unsqueeze(1), h, W3.transpose(1, 2))                                   # [G, T, omax]
-        return {n: o[g, :, :outs[g]].view(nQ, B, outs[g]).transpose(0, 1) for g, n in enumerate(self.HEAD_NAMES)}
+        W3 = _PadStack.apply(omax, *[st[8].weight.squeeze(-1) for st in stacks])                    # [G, omax, C]
+        b3 = _PadStack.apply(omax, *[st[8].bias for st in stacks])                                  # [G, omax]
+        o = ops.batched_linear(h, W3, b3)                                                           # [G, T, omax]
+        return dict(zip(self.HEAD_NAMES, _SplitHeadOutputs.apply(o, nQ, B, outs)))
 
     def _run_heads(self, heads, box_features):
         """box_features [nQ,B,C] -> {head: [B,nQ,out]} (:256-300).  The heads are evaluated token-major (GEMMs on the
