@@ -279,10 +279,12 @@ def test_fused_box_decode_and_grouped_heads_equal_the_plain_paths():
             w = db[k].float()
             # (batched vs plain GEMMs sum in different orders, and BatchNorm over 64 samples amplifies the last bits)
             assert (da[k].float() - w).abs().max().item() <= 3e-4 * (w.abs().max().item() + 1e-6), k
-    assert (ga - gb).abs().max().item() <= 2e-3 * gb.abs().max().item()
+    # (two evaluation orders of the same graph: training BatchNorm over 64 samples amplifies their last-bit differences; 2.5e-3
+    # measured with the batch-first token order, 1e-3 ... 2e-3 with the sequence-first one)
+    assert (ga - gb).abs().max().item() <= 4e-3 * gb.abs().max().item()
     for n in pb:
         if n.endswith("center_head.layers.8.weight") or n.endswith("size_head.layers.8.weight"):
-            assert (pa[n] - pb[n]).abs().max().item() <= 2e-3 * (pb[n].abs().max().item() + 1e-9), n
+            assert (pa[n] - pb[n]).abs().max().item() <= 4e-3 * (pb[n].abs().max().item() + 1e-9), n
 
 
 def test_decoder_c2_shape_vs_oracle_port_per_layer(monkeypatch):

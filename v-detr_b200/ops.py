@@ -231,8 +231,18 @@ def layer_norm_supported(x, weight, bias) -> bool:
             and weight.dtype == torch.float32 and x.shape[-1] == weight.shape[0] and x.shape[-1] in (128, 256, 384, 512))
 
 
+def batch_first_backed(x) -> bool:
+    """x is a [L, B, D] (sequence-first, the reference's convention) VIEW of contiguous batch-first memory [B, L, D].
+    The decoder keeps its token activations that way: per-token ops (linear, layer norm, dropout, residual adds) run on the
+    memory order and hand on the same kind of view, and the attention kernels -- which want [B, L, H, hd] -- get their
+    operands without the transposing copies a sequence-first memory order costs (4 per attention call and direction)."""
+    return x.dim() == 3 and not x.is_contiguous() and x.transpose(0, 1).is_contiguous()
+
+
 def layer_norm(x, weight, bias, eps=1e-5):
     """nn.LayerNorm over the last dimension (fp32, CUDA) through the library's warp-per-row kernels."""
+    if batch_first_backed(x):
+        return layer_norm(x.transpose(0, 1), weight, bias, eps).transpose(0, 1)
     return _LayerNorm.apply(x.contiguous(), weight.contiguous(), bias.contiguous(), eps)
 
 
@@ -427,6 +437,8 @@ def batched_linear(x, weight, bias=None):
 def linear(x, weight, bias=None):
     """torch.nn.functional.linear; on fp32 CUDA tensors that require grad the backward uses the library's column-sum
     kernel for the bias gradient."""
+    if batch_first_backed(x):
+        return linear(x.transpose(0, 1), weight, bias).transpose(0, 1)
     if (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and torch.is_grad_enabled()
             and (x.requires_grad or weight.requires_grad) and x.shape[-1] == weight.shape[1]):
         return _TokenLinear.apply(x, weight, bias)

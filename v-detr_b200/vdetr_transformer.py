@@ -176,19 +176,25 @@ class _SplitHeadOutputs(torch.autograd.Function):
     costs ~5 launches per head and direction (45 head outputs per decoder pass)."""
 
     @staticmethod
-    def forward(ctx, o, nQ, B, outs):
-        ctx.meta = (o.shape, nQ, B, tuple(outs))
+    def forward(ctx, o, nQ, B, outs, batch_first=False):
+        # batch_first: token t = b*nQ + q (the features came as a [nQ, B, C] view of batch-first memory)
+        ctx.meta = (o.shape, nQ, B, tuple(outs), batch_first)
+        if batch_first:
+            return tuple(o[g, :, :w].reshape(B, nQ, w) for g, w in enumerate(outs))
         return tuple(o[g, :, :w].reshape(nQ, B, w).transpose(0, 1).contiguous() for g, w in enumerate(outs))
 
     @staticmethod
     def backward(ctx, *grads):
-        shape, nQ, B, outs = ctx.meta
+        shape, nQ, B, outs, batch_first = ctx.meta
         ref = next(g for g in grads if g is not None)
         go = ref.new_zeros(shape)
         for g, w in enumerate(outs):
             if grads[g] is not None:
-                go[g, :, :w].view(nQ, B, w).copy_(grads[g].transpose(0, 1))
-        return go, None, None, None
+                if batch_first:
+                    go[g, :, :w].view(B, nQ, w).copy_(grads[g])
+                else:
+                    go[g, :, :w].view(nQ, B, w).copy_(grads[g].transpose(0, 1))
+        return go, None, None, None, None
 
 
 class BoxProcessor(object):
@@ -564,6 +570,7 @@ class TransformerDecoder(nn.Module):
         self.sort_keys = True       # Morton-order the key tokens once per forward (see module docstring)
         self.parallel_heads = os.environ.get("VDETR_B200_PARALLEL_HEADS", "1") != "0"
         self.group_heads = os.environ.get("VDETR_B200_GROUP_HEADS", "1") != "0"
+        self.batch_first_memory = os.environ.get("VDETR_B200_BATCH_FIRST", "1") != "0"   # see ops.batch_first_backed
         self.fuse_box_decode = os.environ.get("VDETR_B200_FUSE_BOX_DECODE", "1") != "0"
         # the fused box decode hard-codes utils/box_util.py:294-358 (what both dataset configs of the reference use)
         self.standard_corners = type(dataset_config).__name__ in ("ScanNetBoxConfig", "ScannetDatasetConfig", "SunrgbdDatasetConfig")
@@ -642,7 +649,7 @@ class TransformerDecoder(nn.Module):
             return F.relu(x * scale.reshape(1, -1) + shift.reshape(1, -1))
         return F.relu(x * scale.unsqueeze(1) + shift.unsqueeze(1))
 
-    def _run_heads_grouped(self, stacks, feats, nQ, B):
+    def _run_heads_grouped(self, stacks, feats, nQ, B, batch_first=False):
         """feats [T = nQ*B, C] -> {head: [B,nQ,out]}: layer 1 of all heads is ONE GEMM against the concatenated weights
         ([T, G*C], channels last), layers 2 and 3 are batched GEMMs over the heads ([G, T, C]); each BatchNorm+ReLU level
         is one grouped kernel pair.  ~4x fewer launches than head-by-head evaluation, same parameters and results."""
@@ -661,7 +668,7 @@ class TransformerDecoder(nn.Module):
         W3 = _PadStack.apply(omax, *[st[8].weight.squeeze(-1) for st in stacks])                    # [G, omax, C]
         b3 = _PadStack.apply(omax, *[st[8].bias for st in stacks])                                  # [G, omax]
         o = ops.batched_linear(h, W3, b3)                                                           # [G, T, omax]
-        return dict(zip(self.HEAD_NAMES, _SplitHeadOutputs.apply(o, nQ, B, outs)))
+        return dict(zip(self.HEAD_NAMES, _SplitHeadOutputs.apply(o, nQ, B, outs, batch_first)))
 
     def _run_heads(self, heads, box_features):
         """box_features [nQ,B,C] -> {head: [B,nQ,out]} (:256-300).  The heads are evaluated token-major (GEMMs on the
@@ -670,13 +677,20 @@ class TransformerDecoder(nn.Module):
         which read the same features and are independent, are issued on 5 forked streams and joined."""
         nQ, B, C = box_features.shape
         tokens = all(heads[n].supports_tokens for n in self.HEAD_NAMES)
+        bf = tokens and ops.batch_first_backed(box_features)       # tokens in memory order (b, q): no transposing copy
         if tokens and self.group_heads and box_features.is_cuda:
             stacks = self._grouped_plan(heads)
             if stacks is not None:
-                return self._run_heads_grouped(stacks, box_features.reshape(nQ * B, C), nQ, B)
-        feats = box_features.reshape(nQ * B, C) if tokens else box_features.permute(1, 2, 0)
+                feats = box_features.transpose(0, 1).reshape(B * nQ, C) if bf else box_features.reshape(nQ * B, C)
+                return self._run_heads_grouped(stacks, feats, nQ, B, bf)
+        if bf:
+            feats = box_features.transpose(0, 1).reshape(B * nQ, C)
+        else:
+            feats = box_features.reshape(nQ * B, C) if tokens else box_features.permute(1, 2, 0)
 
         def run(n):
+            if bf:
+                return heads[n].forward_tokens(feats).view(B, nQ, -1)
             if tokens:
                 return heads[n].forward_tokens(feats).view(nQ, B, -1).transpose(0, 1)
             return heads[n](feats).transpose(1, 2)
@@ -783,7 +797,12 @@ class TransformerDecoder(nn.Module):
         if self.sort_keys and memory_mask is None and not return_attn_weights and not self.pos_for_key:
             perm = morton_order(enc_xyz.detach())
             xyz_l = torch.gather(enc_xyz, 1, perm.unsqueeze(-1).expand(-1, -1, 3))
-            mem_l = torch.gather(memory, 0, perm.t().unsqueeze(-1).expand(-1, -1, memory.shape[-1]))
+            # gathered straight into batch-first memory and handed on as a [nK, B, C] view of it (ops.batch_first_backed)
+            mem_l = torch.gather(memory.transpose(0, 1), 1, perm.unsqueeze(-1).expand(-1, -1, memory.shape[-1])).transpose(0, 1)
+        if self.batch_first_memory:
+            # token activations live in batch-first memory behind the reference's [nQ, B, C] shapes: the attention kernels
+            # want [B, nQ, H, hd], and a sequence-first memory order costs them 4 transposing copies per call and direction
+            output = output.transpose(0, 1).contiguous().transpose(0, 1)
 
         for idx, layer in enumerate(self.layers):
             if idx > 0:
