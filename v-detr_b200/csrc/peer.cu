@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) peer_adamw_kernel(const PeerAdam A) {
 // pushes (rows, mean, M2) per channel to all peers, barrier, merge in rank order (Chan et al.), and rewrites sum / sumsq IN
 // PLACE so that bn_apply_relu_kernel -- which reads "shifted sums over `rows` local rows" -- reproduces the GLOBAL mean and
 // biased variance; total_rows_out gets the global row count (for the unbiased running variance).
-__global__ void __launch_bounds__(256) peer_bn_fwd_kernel(Peers flags, Peers slots, int rank, int world, unsigned* epoch, int channel,
+__global__ void __launch_bounds__(1024) peer_bn_fwd_kernel(Peers flags, Peers slots, int rank, int world, unsigned* epoch, int channel,
                                                           int cap, float* sum, float* sumsq, const float* x, int C, int G,
                                                           long long group_stride, int rows, float* total_rows_out) {
   const int cols = C * G;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) peer_bn_fwd_kernel(Peers flags, Peers slo
 // Backward.  dgamma / dbeta hold this rank's sums (they stay local: they are parameter gradients and go through the gradient
 // all-reduce like every other); gsum_g / gsum_b receive the sums over ALL ranks, which the input gradient needs, and
 // total_rows_out the global row count.
-__global__ void __launch_bounds__(256) peer_bn_bwd_kernel(Peers flags, Peers slots, int rank, int world, unsigned* epoch, int channel,
+__global__ void __launch_bounds__(1024) peer_bn_bwd_kernel(Peers flags, Peers slots, int rank, int world, unsigned* epoch, int channel,
                                                           int cap, const float* dgamma, const float* dbeta, int cols, int rows,
                                                           float* gsum_g, float* gsum_b, float* total_rows_out) {
   const size_t per = 1 + 2 * (size_t)cap;
@@ -354,7 +354,7 @@ int vdetr_peer_bn_fwd(void* const* flag_ptrs, void* const* slot_ptrs, int rank, 
   if (!flag_ptrs || !slot_ptrs || !epoch || !sum || !sumsq || !x || cols < 1 || groups < 1 || rows < 1) return VDETR_ERR_BAD_ARG;
   if ((long long)cols * groups > cap) return VDETR_ERR_WORKSPACE;
   if (world < 1 || world > MAXW || rank < 0 || rank >= world) return VDETR_ERR_BAD_ARG;
-  peer_bn_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(make_peers(flag_ptrs, world), make_peers(slot_ptrs, world), rank, world, epoch,
+  peer_bn_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(make_peers(flag_ptrs, world), make_peers(slot_ptrs, world), rank, world, epoch,
                                                            3, cap, sum, sumsq, x, cols, groups, group_stride, rows, total_rows_out);
   VDETR_LAUNCH_CHECK();
   return 0;
@@ -365,7 +365,7 @@ int vdetr_peer_bn_bwd(void* const* flag_ptrs, void* const* slot_ptrs, int rank, 
   if (!flag_ptrs || !slot_ptrs || !epoch || !dgamma || !dbeta || !gsum_g || !gsum_b || cols_total < 1 || rows < 1) return VDETR_ERR_BAD_ARG;
   if (cols_total > cap) return VDETR_ERR_WORKSPACE;
   if (world < 1 || world > MAXW || rank < 0 || rank >= world) return VDETR_ERR_BAD_ARG;
-  peer_bn_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(make_peers(flag_ptrs, world), make_peers(slot_ptrs, world), rank, world, epoch,
+  peer_bn_bwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(make_peers(flag_ptrs, world), make_peers(slot_ptrs, world), rank, world, epoch,
                                                            3, cap, dgamma, dbeta, cols_total, rows, gsum_g, gsum_b, total_rows_out);
   VDETR_LAUNCH_CHECK();
   return 0;
