@@ -1,5 +1,5 @@
 """Developer measurement of the BASELINE configs that are not the headline bench line (C2 forward-only, C5 dense
-stress); writes JSON lines.  Usage: python tests/dev_extra_configs.py > gpurun_out/extra.json"""
+stress); writes JSON lines.  Usage: python tools/dev_extra_configs.py > gpurun_out/extra.json"""
 import json, os, sys, types
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

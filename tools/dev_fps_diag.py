@@ -1,7 +1,7 @@
 """Developer diagnostic (not a test): where do FPS results diverge?  Run on the GPU box."""
 import os, sys, importlib.util
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pn2_util as U
 import vdetr_b200.pointnet2_utils as pu

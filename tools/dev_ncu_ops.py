@@ -1,5 +1,5 @@
 """Developer script for ncu: one fused forward (+ optional backward) at the C3 shape.  Usage under ncu:
-   ncu --set full -k regex:rpe_xattn_fwd -c 1 -o gpurun_out/fwd python tests/dev_ncu_ops.py fwd"""
+   ncu --set full -k regex:rpe_xattn_fwd -c 1 -o gpurun_out/fwd python tools/dev_ncu_ops.py fwd"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vdetr_b200 import ops

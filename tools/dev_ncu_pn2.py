@@ -1,5 +1,5 @@
 """Developer script for ncu: the pointnet2 seed ops at the SURVEY 8(d) sizes (FPS N=50 000 -> M=4096; ball query
-N=20 000, M=2048, nsample 64; gather / group).  ncu --set full -k regex:"fps|ball|gather|group" python tests/dev_ncu_pn2.py"""
+N=20 000, M=2048, nsample 64; gather / group).  ncu --set full -k regex:"fps|ball|gather|group" python tools/dev_ncu_pn2.py"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vdetr_b200.pointnet2_utils as pu
