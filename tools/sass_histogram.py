@@ -35,7 +35,7 @@ print("# whole library: " + ", ".join(f"{k}={v}" for k, v in total.items()))
 print()
 for fn, (n, c) in per.items():
     label = fn[:40]
-    for m in re.finditer(r"\d{1,3}", fn):             # Itanium mangling: <length><identifier>; take the identifier that names a kernel
+    for m in re.finditer(r"\d+", fn):             # Itanium mangling: <length><identifier>; take the identifier that names a kernel
         for k in range(len(m.group(0))):
             L = int(m.group(0)[k:])
             ident = fn[m.end():m.end() + L]
