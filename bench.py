@@ -433,6 +433,8 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
+    if peer is not None:
+        peer.check()                 # raises if a cross-GPU barrier of this rank ever timed out: the numbers would be invalid
     scenes = a.batch * world * a.steps
     value = scenes / (ms_total / 1000.0)
     e2e = scenes / (ms_e2e / 1000.0)

@@ -209,3 +209,39 @@ def test_batched_token_linear_gradients_equal_bmm_autograd():
         assert gg[1].is_contiguous()
         got2 = ops._BatchedTokenLinear.apply(vb, w, None)
         assert torch.allclose(got2, torch.bmm(va, w.transpose(1, 2)), atol=1e-5)
+
+
+def test_batch_first_backed_tokens_give_the_same_heads_and_gradients():
+    """The decoder keeps token activations in batch-first memory behind [nQ, B, C] views (ops.batch_first_backed): the grouped
+    heads on tokens in (b, q) order, incl. the _SplitHeadOutputs backward, against the sequence-first evaluation; and the
+    layout-preserving wrappers of ops.linear."""
+    import copy
+    from vdetr_b200 import ops
+    dec = _build(1, 16, False).train()
+    heads = dec.mlp_heads[1]
+    g = torch.Generator().manual_seed(11)
+    for n in dec.HEAD_NAMES:
+        heads[n].layers[-1].weight.data.normal_(generator=g); heads[n].layers[-1].bias.data.normal_(generator=g)
+        for m in heads[n].modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    nQ, B, C = 16, 3, 256
+    x = torch.randn(nQ, B, C, generator=g)
+    xa = x.clone().requires_grad_(True)
+    xb = x.transpose(0, 1).contiguous().requires_grad_(True)          # batch-first memory
+    vb = xb.transpose(0, 1)                                           # the [nQ, B, C] view the decoder hands on
+    assert ops.batch_first_backed(vb) and not ops.batch_first_backed(xa)
+    twin = copy.deepcopy(heads)
+    a = dec._run_heads_grouped(dec._grouped_plan(heads), xa.reshape(nQ * B, C), nQ, B, False)
+    b = dec._run_heads_grouped(dec._grouped_plan(twin), vb.transpose(0, 1).reshape(B * nQ, C), nQ, B, True)
+    w = {n: torch.randn(a[n].shape, generator=g) for n in dec.HEAD_NAMES}
+    ga, = torch.autograd.grad(sum((a[n] * w[n]).sum() for n in w), xa)
+    gb, = torch.autograd.grad(sum((b[n] * w[n]).sum() for n in w), xb)
+    for n in dec.HEAD_NAMES:
+        assert a[n].shape == b[n].shape == (B, nQ, a[n].shape[-1])
+        assert (a[n] - b[n]).abs().max().item() <= 1e-4 * (a[n].abs().max().item() + 1.0), n
+    assert (ga - gb.transpose(0, 1)).abs().max().item() <= 2e-4 * ga.abs().max().item()
+    # ops.linear on a batch-first-backed view: same values, same kind of view
+    lin = torch.nn.Linear(C, 64)
+    y = ops.linear(vb, lin.weight, lin.bias)
+    assert ops.batch_first_backed(y) and torch.allclose(y, torch.nn.functional.linear(x, lin.weight, lin.bias), atol=1e-5)

@@ -169,6 +169,27 @@ class PeerGroup:
             dist.barrier()           # every rank has mapped every allocation before anyone uses it
         return buf
 
+    def close(self):
+        """Unmap the peers' allocations and free this rank's (after a barrier: nobody may still be using them).  Optional: the
+        allocations otherwise live until the process exits."""
+        from . import _C
+        if self._bn_ctx is not None:
+            self.disable_sync_batchnorm()
+        torch.cuda.synchronize(self.device)
+        if self.dist:
+            dist.barrier()
+        with torch.cuda.device(self.device):
+            for buf in self._bufs:
+                for r in range(self.world):
+                    if r != self.rank:
+                        _C.check(_C.lib().vdetr_peer_close(buf.ptrs[r]))
+            if self.dist:
+                dist.barrier()
+            for buf in self._bufs:
+                buf.local = None
+                _C.check(_C.lib().vdetr_peer_free(buf._raw))
+        self._bufs = []
+
     def barrier(self, channel: int = 0):
         """Cross-GPU barrier on the current stream (a one-warp kernel; capturable in a CUDA graph)."""
         from . import _C
