@@ -170,8 +170,9 @@ class PeerGroup:
         return buf
 
     def close(self):
-        """Unmap the peers' allocations and free this rank's (after a barrier: nobody may still be using them).  Optional: the
-        allocations otherwise live until the process exits."""
+        """Unmap the peers' allocations and free this rank's (after a barrier: nobody may still be using them).  Optional --
+        the allocations otherwise live until the process exits -- and only legal once every tensor that views them is gone:
+        the parameters, gradients and flat vectors of a FlatAdamW(peer=self) live in these buffers."""
         from . import _C
         if self._bn_ctx is not None:
             self.disable_sync_batchnorm()
