@@ -41,3 +41,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("CPU oracle is too slow", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/vdetr_b200.h must compile as C (no C++, no torch or CUDA types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "vdetr_b200.h"\nint main(void) { VdetrXattnShape s; VdetrPeerCtx c; (void)s; (void)c; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-c", str(src), "-I", os.path.join(ROOT, "include"), "-o",
+                        str(tmp_path / "abi.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
