@@ -231,6 +231,12 @@ def layer_norm_supported(x, weight, bias) -> bool:
             and weight.dtype == torch.float32 and x.shape[-1] == weight.shape[0] and x.shape[-1] in (128, 256, 384, 512))
 
 
+# True while the library-wide SyncBatchNorm switch is on (parallel.PeerGroup.enable_sync_batchnorm): every training BatchNorm
+# launch then contains a cross-GPU exchange on ONE flag channel, so BatchNorm launches must stay on one stream, in the same
+# order on every rank (vdetr_transformer._run_heads does not fork streams then).
+SYNC_BN_ACTIVE = False
+
+
 def batch_first_backed(x) -> bool:
     """x is a [L, B, D] (sequence-first, the reference's convention) VIEW of contiguous batch-first memory [B, L, D].
     The decoder keeps its token activations that way: per-token ops (linear, layer norm, dropout, residual adds) run on the

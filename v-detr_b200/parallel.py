@@ -221,11 +221,15 @@ class PeerGroup:
         import ctypes
         _C.check(_C.lib().vdetr_bn_sync_set(ctypes.byref(ctx)))
         self._bn_ctx = ctx
+        from . import ops
+        ops.SYNC_BN_ACTIVE = True
 
     def disable_sync_batchnorm(self):
         from . import _C
         _C.check(_C.lib().vdetr_bn_sync_set(None))
         self._bn_ctx = None
+        from . import ops
+        ops.SYNC_BN_ACTIVE = False
 
 
 def _peer_norm_bytes():

@@ -694,7 +694,8 @@ class TransformerDecoder(nn.Module):
             if tokens:
                 return heads[n].forward_tokens(feats).view(nQ, B, -1).transpose(0, 1)
             return heads[n](feats).transpose(1, 2)
-        if not (feats.is_cuda and self.parallel_heads):
+        if not (feats.is_cuda and self.parallel_heads) or ops.SYNC_BN_ACTIVE:
+            # (SyncBatchNorm: the exchanges inside the BatchNorm launches share one flag channel -- one stream, one order)
             return {n: run(n) for n in self.HEAD_NAMES}
         cur = torch.cuda.current_stream(feats.device)
         streams = _head_streams(feats.device, len(self.HEAD_NAMES))
