@@ -494,6 +494,7 @@ def main():
                                  "dense 128 x 400 MMAs of the factored weights (96 % zeros) because that costs 13x fewer issue slots than "
                                  "sorting + register accumulation (dt3: 3.7 ms) -- see executed_dense_mma for how busy the tensor pipe is",
                          "executed_dense_mma": {"tflops": dt_dense_tf, "frac_of_peak": dt_dense_tf / peak_tf if peak_tf else None,
+                                                "frac_of_nominal_dense_fp16_peak": dt_dense_tf / 2250.0,
                                                 "flops_per_pair": 102400, "mma_floor_ms": dt_dense_flops / (2 * 4096.0 * 148 * 1.965e9) * 1e3,
                                                 "tensor_pipe_active_pct_ncu": ncu.get("dtables", {}).get("tensor_pipe_pct") if full else None},
                          "hbm_view": {"achieved_gbs": dt_gbs, "peak_gbs": peak_bw, "frac": dt_gbs / peak_bw if peak_bw else None},
