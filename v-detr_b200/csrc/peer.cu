@@ -275,9 +275,14 @@ int vdetr_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
   if (!ptr || !handle64 || bytes == 0) return VDETR_ERR_BAD_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
   VDETR_CUDA_TRY(cudaMalloc(ptr, bytes));
-  VDETR_CUDA_TRY(cudaMemset(*ptr, 0, bytes));
   cudaIpcMemHandle_t h;
-  VDETR_CUDA_TRY(cudaIpcGetMemHandle(&h, *ptr));
+  cudaError_t e = cudaMemset(*ptr, 0, bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {          // nothing is handed out on failure
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return (int)e;
+  }
   memcpy(handle64, &h, 64);
   return 0;
 }
